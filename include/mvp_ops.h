@@ -1,0 +1,147 @@
+/* mvp_ops.h — C ABI of libmvp_ops.so: the B200 (sm_100a) point-cloud operator library that replaces
+ * the native layer of paul007pl/MVP_Benchmark's `utils/metrics` and `utils/mm3d_pn2` packages.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch / pybind types.  Loadable with ctypes / dlopen.
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name ends in `_host`.
+ *   - the CALLER allocates everything, including scratch (`*_workspace_bytes` tells how much);
+ *     the callee never allocates, never synchronises the host, and launches on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - outputs need NO pre-initialisation: the zero-fills / sentinel-fills the reference's Python
+ *     performs before each call (listed per function) are done inside.
+ *   - all tensors are contiguous row-major fp32 / int32, shapes as in the reference.
+ *   - return value: 0 = ok; > 0 = a cudaError_t; < 0 = one of MVP_ERR_* (invalid argument).
+ *     The reference printf()s / exit(-1)s instead (chamfer3D.cu:145-150, ball_query_cuda.cu:73-77);
+ *     the Python layer here raises RuntimeError on any non-zero code.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef MVP_OPS_H_
+#define MVP_OPS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVP_OK 0
+#define MVP_ERR_INVALID_ARGUMENT (-1)  /* negative size, null pointer, k out of range ...          */
+#define MVP_ERR_EMD_SIZE_MISMATCH (-2) /* emd_cuda.cu:236-239 "two point clouds should have the same size" */
+#define MVP_ERR_EMD_BATCH (-3)         /* emd_cuda.cu:241-244 batch size > 512                      */
+#define MVP_ERR_EMD_MULTIPLE_1024 (-4) /* emd_cuda.cu:246-249 n % 1024 != 0                         */
+#define MVP_ERR_WORKSPACE (-5)         /* workspace pointer null or too small                      */
+#define MVP_ERR_UNSUPPORTED_DEVICE (-6)/* not an sm_100 device                                     */
+
+typedef void *mvp_stream_t; /* cudaStream_t */
+
+/* Library / build identification. */
+int mvp_abi_version(void);
+const char *mvp_build_info(void);
+/* Text for a return code of any function below (MVP_ERR_* or cudaError_t). */
+const char *mvp_error_string(int code);
+/* Number of KERNELS (memsets excluded) this library has launched in this process; monotonic. */
+unsigned long long mvp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer distance.
+ * Replaces chamfer_3D.forward  -> chamfer_cuda_forward  (utils/metrics/CD/chamfer3D/chamfer_cuda.cpp:17-19,
+ *          utils/metrics/CD/chamfer3D/chamfer3D.cu:136-154, kernel :12-134).
+ *   xyz1 (b,n,3), xyz2 (b,m,3) -> dist1 (b,n), idx1 (b,n): min_j |xyz1_i - xyz2_j|^2 and its argmin
+ *   (lowest j on ties); dist2 (b,m), idx2 (b,m): the same with roles swapped.  Bit-exact with the
+ *   reference kernel for finite inputs.  Outputs need not be zeroed (dist_chamfer_3D.py:33-42 does).
+ *   workspace: mvp_chamfer_forward_workspace_bytes(b,n,m) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m);
+int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                        float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
+                        mvp_stream_t stream);
+
+/* Replaces chamfer_3D.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:22-26, chamfer3D.cu:176-195,
+ * kernel :155-174).  gradxyz1 (b,n,3) and gradxyz2 (b,m,3) are zero-filled inside
+ * (dist_chamfer_3D.py:56-57 does it in the reference) and then accumulated with fp32 atomics. */
+int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
+                         const float *graddist1, const float *graddist2, const int *idx1,
+                         const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Earth mover's distance, auction approximation.
+ * Replaces emd.forward -> emd_cuda_forward (utils/metrics/EMD/emd.cpp:12-16, emd_cuda.cu:228-282; kernels
+ * :23-226).  xyz1, xyz2 (b,n,3), n % 1024 == 0, b <= 512 -> dist (b,n), assignment (b,n).
+ * The twelve state arrays the reference's Python allocates (emd_module.py:54-65) live in `workspace`
+ * and are initialised inside.  Near-tie winners (emd_cuda.cu:188, a last-writer race in the reference)
+ * are resolved deterministically: the highest source index wins.
+ * ------------------------------------------------------------------------------------------- */
+size_t mvp_emd_forward_workspace_bytes(int b, int n);
+int mvp_emd_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float eps, int iters,
+                    float *dist, int *assignment, void *workspace, size_t workspace_bytes,
+                    mvp_stream_t stream);
+
+/* Replaces emd.backward -> emd_cuda_backward (emd.cpp:18-21, emd_cuda.cu:302-316, kernel :284-300).
+ * gradxyz1 (b,n,3) is fully written (no pre-zeroing needed).  The reference returns zeros for xyz2
+ * (emd_module.py:78-81); that tensor is the Python layer's business. */
+int mvp_emd_backward(int b, int n, const float *xyz1, const float *xyz2, const float *graddist,
+                     const int *assignment, float *gradxyz1, mvp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointNet++ ops (utils/mm3d_pn2/ops).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces furthest_point_sampling_wrapper -> furthest_point_sampling_kernel_launcher
+ * (furthest_point_sample/src/furthest_point_sample.cpp:32-43, furthest_point_sample_cuda.cu:143-209,
+ * kernel :26-141).  xyz (b,n,3) -> idx (b,m).  `temp` (b,n) is the reference's scratch of running
+ * minimum distances (pre-filled with 1e10 by furthest_point_sample.py:30); here it may be NULL — when
+ * given, the final running distances are written to it, no pre-fill needed.  Bit-exact incl. ties. */
+int mvp_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                mvp_stream_t stream);
+
+/* Replaces furthest_point_sampling_with_dist_wrapper (furthest_point_sample.cpp:45-57,
+ * furthest_point_sample_cuda.cu:333-399, kernel :214-331).  dist (b,n,n) -> idx (b,m). */
+int mvp_furthest_point_sampling_with_dist(int b, int n, int m, const float *dist, float *temp, int *idx,
+                                          mvp_stream_t stream);
+
+/* Replaces ball_query_wrapper -> ball_query_kernel_launcher (ball_query/src/ball_query.cpp:30-43,
+ * ball_query_cuda.cu:56-78, kernel :11-54).  new_xyz (b,m,3) centres, xyz (b,n,3) -> idx (b,m,nsample);
+ * rows without any hit are zero (ball_query.py:35 zeroes idx in the reference; done inside here). */
+int mvp_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                   const float *new_xyz, const float *xyz, int *idx, mvp_stream_t stream);
+
+/* Replaces gather_points_wrapper / gather_points_grad_wrapper (gather_points/src/gather_points.cpp:28-52,
+ * gather_points_cuda.cu:28-44,72-90).  points (b,c,n), idx (b,npoints) -> out (b,c,npoints);
+ * grad_out (b,c,npoints) -> grad_points (b,c,n), zero-filled inside (gather_points.py:44). */
+int mvp_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                      mvp_stream_t stream);
+int mvp_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                           float *grad_points, mvp_stream_t stream);
+
+/* Replaces group_points_ext.forward / backward (group_points/src/group_points.cpp:31-57,
+ * group_points_cuda.cu:81-98,33-51).  points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample);
+ * grad_points zero-filled inside (group_points.py:213). */
+int mvp_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                     float *out, mvp_stream_t stream);
+int mvp_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, mvp_stream_t stream);
+
+/* Replaces three_nn_wrapper (interpolate/src/interpolate.cpp:46-56, three_nn_cuda.cu:67-86, kernel :11-65).
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances ascending, idx (b,n,3). */
+int mvp_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                 mvp_stream_t stream);
+
+/* Replaces three_interpolate_wrapper / _grad_wrapper (interpolate.cpp:58-85,
+ * three_interpolate_cuda.cu:37-59,86-106).  points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n);
+ * grad_out (b,c,n) -> grad_points (b,c,m), zero-filled inside (three_interpolate.py:53). */
+int mvp_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, mvp_stream_t stream);
+int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, mvp_stream_t stream);
+
+/* Replaces knn_wrapper (knn/src/knn.cpp:28-41, knn_cuda.cu:97-115, kernel :58-94).
+ * xyz (b,n,3), new_xyz (b,m,3) centres, 0 < nsample <= 100 -> idx (b,m,nsample), dist2 (b,m,nsample),
+ * ascending distance.  (The transpose to (b,nsample,m) stays in Python, knn.py:63.) */
+int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+            float *dist2, mvp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVP_OPS_H_ */

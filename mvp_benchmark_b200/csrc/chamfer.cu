@@ -1,0 +1,195 @@
+// Chamfer distance for sm_100a — generic one-direction kernel + fused backward.
+//
+// Replaces NmDistanceKernel / NmDistanceGradKernel of the reference
+// (utils/metrics/CD/chamfer3D/chamfer3D.cu:12-134,155-174).  Semantics kept bit-for-bit:
+//   d = fma(dz,dz, fma(dx,dx, dy*dy)) with dx = target - query (chamfer3D.cu:32-35 as contracted by nvcc),
+//   argmin = lowest target index among equal minima (strict `<` scanning upward, :36,:126).
+//
+// This file holds the GENERIC path (any n, m >= 1): one launch per direction, R queries per thread in
+// registers, targets staged through shared memory.  The large-cloud fast path (both directions from one
+// evaluation of each pair, packed fp32x2 math, TMA-staged tiles) lives in chamfer_fused.cu and is chosen
+// by mvp_chamfer_forward when the shapes allow.
+#include "common.cuh"
+
+namespace mvp {
+
+constexpr int kChThreads = 256;
+constexpr int kChTile = 1024;  // targets per shared-memory tile (AoS, 12 KB)
+
+template <int R>
+__global__ void __launch_bounds__(kChThreads)
+chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ xyz2,
+                   float *__restrict__ dist, int *__restrict__ idx) {
+  __shared__ __align__(16) float tile[kChTile * 3];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int qbase = blockIdx.x * (kChThreads * R);
+  const float *q = xyz + (size_t)b * n * 3;
+  const float *t = xyz2 + (size_t)b * m * 3;
+
+  float qx[R], qy[R], qz[R], best[R];
+  int bi[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int j = qbase + r * kChThreads + tid;
+    const int jj = j < n ? j : n - 1;
+    qx[r] = __ldg(q + jj * 3 + 0);
+    qy[r] = __ldg(q + jj * 3 + 1);
+    qz[r] = __ldg(q + jj * 3 + 2);
+    best[r] = __int_as_float(0x7f800000);  // +inf
+    bi[r] = 0;
+  }
+
+  for (int k2 = 0; k2 < m; k2 += kChTile) {
+    const int cnt = min(kChTile, m - k2);
+    const int cnt4 = (cnt + 3) & ~3;
+    for (int i = tid; i < cnt4 * 3; i += kChThreads)
+      tile[i] = i < cnt * 3 ? __ldg(t + (size_t)k2 * 3 + i) : __int_as_float(0x7f800000);
+    __syncthreads();
+    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+#pragma unroll 2
+    for (int k = 0; k < cnt4; k += 4) {
+      const float4 a = t4[(k >> 2) * 3 + 0];  // x0 y0 z0 x1
+      const float4 c = t4[(k >> 2) * 3 + 1];  // y1 z1 x2 y2
+      const float4 e = t4[(k >> 2) * 3 + 2];  // z2 x3 y3 z3
+      const int kk = k2 + k;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const float d0 = sqdist(a.x - qx[r], a.y - qy[r], a.z - qz[r]);
+        const float d1 = sqdist(a.w - qx[r], c.x - qy[r], c.y - qz[r]);
+        const float d2 = sqdist(c.z - qx[r], c.w - qy[r], e.x - qz[r]);
+        const float d3 = sqdist(e.y - qx[r], e.z - qy[r], e.w - qz[r]);
+        if (d0 < best[r]) { best[r] = d0; bi[r] = kk; }
+        if (d1 < best[r]) { best[r] = d1; bi[r] = kk + 1; }
+        if (d2 < best[r]) { best[r] = d2; bi[r] = kk + 2; }
+        if (d3 < best[r]) { best[r] = d3; bi[r] = kk + 3; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int j = qbase + r * kChThreads + tid;
+    if (j < n) {
+      dist[(size_t)b * n + j] = best[r];
+      idx[(size_t)b * n + j] = bi[r];
+    }
+  }
+}
+
+int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2, float *dist, int *idx,
+                       cudaStream_t s) {
+  // Pick R so that the grid has at least ~2 CTAs per SM where the problem allows it.
+  auto ctas = [&](int R) { return (long long)b * ((n + kChThreads * R - 1) / (kChThreads * R)); };
+  for (int by = 0; by < b; by += 65535) {
+    const int bb = min(65535, b - by);
+    const float *q = xyz + (size_t)by * n * 3;
+    const float *t = xyz2 + (size_t)by * m * 3;
+    float *d = dist + (size_t)by * n;
+    int *ix = idx + (size_t)by * n;
+    if (ctas(4) >= 2 * kNumSMs) {
+      dim3 grid((n + kChThreads * 4 - 1) / (kChThreads * 4), bb);
+      chamfer_dir_kernel<4><<<grid, kChThreads, 0, s>>>(n, m, q, t, d, ix);
+    } else if (ctas(2) >= 2 * kNumSMs) {
+      dim3 grid((n + kChThreads * 2 - 1) / (kChThreads * 2), bb);
+      chamfer_dir_kernel<2><<<grid, kChThreads, 0, s>>>(n, m, q, t, d, ix);
+    } else {
+      dim3 grid((n + kChThreads - 1) / kChThreads, bb);
+      chamfer_dir_kernel<1><<<grid, kChThreads, 0, s>>>(n, m, q, t, d, ix);
+    }
+    count_launch();
+  }
+  return launch_status();
+}
+
+// Backward: both directions in one launch.  Thread i < b*n handles point i of xyz1 (direction 1),
+// the rest handle points of xyz2 (direction 2).  chamfer3D.cu:155-174: g = grad*2; six accumulations.
+__global__ void __launch_bounds__(256)
+chamfer_grad_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                    const float *__restrict__ gd1, const float *__restrict__ gd2,
+                    const int *__restrict__ idx1, const int *__restrict__ idx2, float *gx1, float *gx2) {
+  const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const bool first = i < total1;
+    const long long p = first ? i : i - total1;
+    const int na = first ? n : m, nb = first ? m : n;
+    const long long cloud = p / na;
+    const float *A = first ? xyz1 : xyz2;
+    const float *Bp = first ? xyz2 : xyz1;
+    float *GA = first ? gx1 : gx2;
+    float *GB = first ? gx2 : gx1;
+    const int j2 = __ldg((first ? idx1 : idx2) + p);
+    const float g = __ldg((first ? gd1 : gd2) + p) * 2;
+    const float x1 = __ldg(A + p * 3 + 0), y1 = __ldg(A + p * 3 + 1), z1 = __ldg(A + p * 3 + 2);
+    const long long o = (cloud * nb + j2) * 3;
+    const float x2 = __ldg(Bp + o + 0), y2 = __ldg(Bp + o + 1), z2 = __ldg(Bp + o + 2);
+    const float vx = g * (x1 - x2), vy = g * (y1 - y2), vz = g * (z1 - z2);
+    atomicAdd(GA + p * 3 + 0, vx);
+    atomicAdd(GA + p * 3 + 1, vy);
+    atomicAdd(GA + p * 3 + 2, vz);
+    atomicAdd(GB + o + 0, -vx);
+    atomicAdd(GB + o + 1, -vy);
+    atomicAdd(GB + o + 2, -vz);
+  }
+}
+
+}  // namespace mvp
+
+using namespace mvp;
+
+namespace mvp {
+// chamfer_fused.cu
+bool chamfer_fused_supported(int b, int n, int m);
+size_t chamfer_fused_workspace_bytes(int b, int n, int m);
+int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                         float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
+}  // namespace mvp
+
+MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 16;
+  return chamfer_fused_supported(b, n, m) ? chamfer_fused_workspace_bytes(b, n, m) : 16;
+}
+
+MVP_API int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                                float *dist2, int *idx1, int *idx2, void *workspace,
+                                size_t workspace_bytes, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
+  if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;  // the reference reads out of bounds here
+  if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (chamfer_fused_supported(b, n, m)) {
+    if (!workspace || workspace_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
+    return chamfer_fused_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace,
+                                workspace_bytes, s);
+  }
+  int rc = chamfer_dir_launch(b, n, m, xyz1, xyz2, dist1, idx1, s);
+  if (rc) return rc;
+  return chamfer_dir_launch(b, m, n, xyz2, xyz1, dist2, idx2, s);
+}
+
+MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
+                                 const float *graddist1, const float *graddist2, const int *idx1,
+                                 const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
+  if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (!xyz1 || !xyz2 || !graddist1 || !graddist2 || !idx1 || !idx2 || !gradxyz1 || !gradxyz2)
+    return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e;
+  const size_t b1 = sizeof(float) * (size_t)b * n * 3, b2 = sizeof(float) * (size_t)b * m * 3;
+  if ((char *)gradxyz1 + b1 == (char *)gradxyz2) {  // one contiguous allocation: one memset
+    if ((e = cudaMemsetAsync(gradxyz1, 0, b1 + b2, s)) != cudaSuccess) return (int)e;
+  } else {
+    if ((e = cudaMemsetAsync(gradxyz1, 0, b1, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(gradxyz2, 0, b2, s)) != cudaSuccess) return (int)e;
+  }
+  const long long total = (long long)b * (n + m);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  chamfer_grad_kernel<<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2,
+                                           gradxyz1, gradxyz2);
+  count_launch();
+  return launch_status();
+}

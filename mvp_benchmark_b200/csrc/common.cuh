@@ -1,0 +1,44 @@
+// Shared device/host helpers for libmvp_ops.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "../../include/mvp_ops.h"
+
+#define MVP_API extern "C" __attribute__((visibility("default")))
+
+namespace mvp {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+extern unsigned long long g_launch_count;  // defined in capi.cu
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+// The reference's squared distance `dx*dx + dy*dy + dz*dz` as nvcc contracts it (SASS-verified for
+// chamfer3D.cu:35, furthest_point_sample_cuda.cu:65-66, ball_query_cuda.cu:41-42, three_nn_cuda.cu:41,
+// knn_cuda.cu:82, emd_cuda.cu:146,225):  t = dy*dy;  t = fma(dx,dx,t);  d = fma(dz,dz,t).
+__device__ __forceinline__ float sqdist(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t redux_max_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+__device__ __forceinline__ float ld_nc(const float *p) { return __ldg(p); }
+
+}  // namespace mvp

@@ -1,0 +1,239 @@
+// Furthest point sampling for sm_100a.
+//
+// Replaces furthest_point_sampling_kernel / furthest_point_sampling_with_dist_kernel of the reference
+// (utils/mm3d_pn2/ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:26-141, 214-331).
+//
+// The reference keeps the running minimum distances in global memory and does an 11-barrier tree per
+// selected point.  Here one CTA owns one cloud, every thread keeps its P points AND their running
+// minima in registers for the whole scan, and one selection step costs ONE block barrier:
+//   in-thread max  ->  redux.sync.max over the warp  ->  one 8-byte slot per warp in shared memory
+//   -> __syncthreads -> every warp reduces the <=32 slots redundantly (no second barrier).
+//
+// Bit-exact tie rule.  The reference thread t owns k = t (mod T), T = opt_n_threads(n) (:11-15), takes
+// the lowest k on equal distance inside a thread (strict `>`, :69-70) and its tree keeps the LOWER
+// position on equality with strides T/2..1 (:17-23), so among equal maxima the winner is the point with
+// the smallest  key(k) = (bitrev_T(k mod T), k div T).  We reduce (distance, key) with max-then-min.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mvp {
+
+__device__ __forceinline__ uint32_t fps_key(int k, int log2T) {
+  const uint32_t t = (uint32_t)k & ((1u << log2T) - 1u);
+  const uint32_t rev = log2T ? (__brev(t) >> (32 - log2T)) : 0u;
+  return (rev << 20) | ((uint32_t)k >> log2T);
+}
+__device__ __forceinline__ int fps_unkey(uint32_t key, int log2T) {
+  const uint32_t rev = key >> 20;
+  const uint32_t t = log2T ? (__brev(rev) >> (32 - log2T)) : 0u;
+  return (int)(((key & 0xfffffu) << log2T) | t);
+}
+
+__device__ __forceinline__ int redux_max_s32(int v) {
+  int r;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+// TB threads, P points per thread (k = tid + i*TB).  WITH_DIST: `data` is the (n,n) distance matrix.
+template <int TB, int P, bool WITH_DIST>
+__global__ void __launch_bounds__(TB)
+fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
+           int *__restrict__ idxs) {
+  constexpr int NW = TB / 32;
+  __shared__ int s_val[2][32];
+  __shared__ uint32_t s_key[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *dataset = data + (size_t)blockIdx.x * (WITH_DIST ? (size_t)n * n : (size_t)n * 3);
+  idxs += (size_t)blockIdx.x * m;
+
+  float px[P], py[P], pz[P], td[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    const int k = tid + i * TB;
+    if (k < n) {
+      if (!WITH_DIST) {
+        px[i] = __ldg(dataset + k * 3 + 0);
+        py[i] = __ldg(dataset + k * 3 + 1);
+        pz[i] = __ldg(dataset + k * 3 + 2);
+      }
+      td[i] = 1e10f;  // furthest_point_sample.py:30
+    } else {
+      px[i] = py[i] = pz[i] = 0.f;
+      td[i] = -1.f;  // never selected: compares below every real distance as a signed int
+    }
+  }
+  if (warp == 0) {
+    s_val[0][lane] = s_val[1][lane] = (int)0x80000000;
+    s_key[0][lane] = s_key[1][lane] = 0xffffffffu;
+  }
+  int old = 0;
+  if (tid == 0) idxs[0] = 0;
+  __syncthreads();
+
+  for (int j = 1; j < m; j++) {
+    float vmax = -1.f;
+    if (WITH_DIST) {
+      const float *row = dataset + (size_t)old * n;
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        const int k = tid + i * TB;
+        if (k < n) td[i] = fminf(__ldg(row + k), td[i]);
+        vmax = fmaxf(vmax, td[i]);
+      }
+    } else {
+      const float x1 = __ldg(dataset + old * 3 + 0);
+      const float y1 = __ldg(dataset + old * 3 + 1);
+      const float z1 = __ldg(dataset + old * 3 + 2);
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        const float d = sqdist(px[i] - x1, py[i] - y1, pz[i] - z1);  // point - old (:65-66)
+        td[i] = fminf(d, td[i]);
+        vmax = fmaxf(vmax, td[i]);
+      }
+    }
+    const int vbits = __float_as_int(vmax);
+    const int wbits = redux_max_s32(vbits);
+    uint32_t key = 0xffffffffu;
+    if (vbits == wbits) {
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        const int k = tid + i * TB;
+        if (k < n && __float_as_int(td[i]) == wbits) key = min(key, fps_key(k, log2T));
+      }
+    }
+    const uint32_t wkey = redux_min_u32(key);
+    const int buf = j & 1;
+    if (lane == 0) {
+      s_val[buf][warp] = wbits;
+      s_key[buf][warp] = wkey;
+    }
+    __syncthreads();
+    const int v = s_val[buf][lane];  // slots >= NW hold the sentinel
+    const uint32_t kk = s_key[buf][lane];
+    const int bv = redux_max_s32(v);
+    const uint32_t bk = redux_min_u32(v == bv ? kk : 0xffffffffu);
+    old = fps_unkey(bk, log2T);
+    if (tid == 0) idxs[j] = old;
+    (void)NW;
+  }
+  if (temp != nullptr) {
+    temp += (size_t)blockIdx.x * n;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = tid + i * TB;
+      if (k < n) temp[k] = td[i];
+    }
+  }
+}
+
+// Fallback for clouds too large for registers (n > 32768): running minima in global `temp`.
+template <bool WITH_DIST>
+__global__ void __launch_bounds__(1024)
+fps_big_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
+               int *__restrict__ idxs) {
+  __shared__ int s_val[2][32];
+  __shared__ uint32_t s_key[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *dataset = data + (size_t)blockIdx.x * (WITH_DIST ? (size_t)n * n : (size_t)n * 3);
+  idxs += (size_t)blockIdx.x * m;
+  temp += (size_t)blockIdx.x * n;
+  for (int k = tid; k < n; k += 1024) temp[k] = 1e10f;
+  int old = 0;
+  if (tid == 0) idxs[0] = 0;
+  __syncthreads();
+  for (int j = 1; j < m; j++) {
+    float x1 = 0, y1 = 0, z1 = 0;
+    if (!WITH_DIST) {
+      x1 = __ldg(dataset + old * 3 + 0);
+      y1 = __ldg(dataset + old * 3 + 1);
+      z1 = __ldg(dataset + old * 3 + 2);
+    }
+    int vbits = __float_as_int(-1.f);
+    uint32_t key = 0xffffffffu;
+    for (int k = tid; k < n; k += 1024) {
+      float d;
+      if (WITH_DIST)
+        d = __ldg(dataset + (size_t)old * n + k);
+      else
+        d = sqdist(__ldg(dataset + k * 3 + 0) - x1, __ldg(dataset + k * 3 + 1) - y1,
+                   __ldg(dataset + k * 3 + 2) - z1);
+      const float d2 = fminf(d, temp[k]);
+      temp[k] = d2;
+      const int bits = __float_as_int(d2);
+      const uint32_t kk = fps_key(k, log2T);
+      if (bits > vbits || (bits == vbits && kk < key)) {
+        vbits = bits;
+        key = kk;
+      }
+    }
+    const int wbits = redux_max_s32(vbits);
+    const uint32_t wkey = redux_min_u32(vbits == wbits ? key : 0xffffffffu);
+    const int buf = j & 1;
+    if (lane == 0) {
+      s_val[buf][warp] = wbits;
+      s_key[buf][warp] = wkey;
+    }
+    __syncthreads();
+    const int v = s_val[buf][lane];
+    const uint32_t kk = s_key[buf][lane];
+    const int bv = redux_max_s32(v);
+    const uint32_t bk = redux_min_u32(v == bv ? kk : 0xffffffffu);
+    old = fps_unkey(bk, log2T);
+    if (tid == 0) idxs[j] = old;
+  }
+}
+
+// furthest_point_sample_cuda.cu:11-15 — evaluated with the same double expression so that the tie order
+// matches the block size the reference would have launched.
+static int ref_block_size(int work_size) {
+  const int pow_2 = (int)(std::log(static_cast<double>(work_size)) / std::log(2.0));
+  int t = 1 << pow_2;
+  if (t > 1024) t = 1024;
+  if (t < 1) t = 1;
+  return t;
+}
+
+template <bool WD, int TB, int P>
+static void fps_launch_one(int b, int n, int m, int log2T, const float *data, float *temp, int *idx,
+                           cudaStream_t s) {
+  fps_kernel<TB, P, WD><<<b, TB, 0, s>>>(n, m, log2T, data, temp, idx);
+}
+
+template <bool WD>
+static int fps_dispatch(int b, int n, int m, const float *data, float *temp, int *idx, cudaStream_t s) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || m == 0) return MVP_OK;  // reference kernel returns immediately when m <= 0 (:34)
+  if (n == 0 || !data || !idx) return MVP_ERR_INVALID_ARGUMENT;
+  const int T = ref_block_size(n);
+  int log2T = 0;
+  while ((1 << log2T) < T) log2T++;
+  // Fewest warps that keep <= 16 points per thread; then grow P.  (TB, P) with TB*P >= n.
+  if (n <= 128 * 4) fps_launch_one<WD, 128, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 128 * 8) fps_launch_one<WD, 128, 8>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 128 * 16) fps_launch_one<WD, 128, 16>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 256 * 12) fps_launch_one<WD, 256, 12>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 256 * 16) fps_launch_one<WD, 256, 16>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 512 * 16) fps_launch_one<WD, 512, 16>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 1024 * 16) fps_launch_one<WD, 1024, 16>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 1024 * 32) fps_launch_one<WD, 1024, 32>(b, n, m, log2T, data, temp, idx, s);
+  else {
+    if (!temp) return MVP_ERR_WORKSPACE;  // the big-cloud path needs the reference's `temp` scratch
+    fps_big_kernel<WD><<<b, 1024, 0, s>>>(n, m, log2T, data, temp, idx);
+  }
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace mvp
+
+MVP_API int mvp_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                        mvp_stream_t stream) {
+  return mvp::fps_dispatch<false>(b, n, m, xyz, temp, idx, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_furthest_point_sampling_with_dist(int b, int n, int m, const float *dist, float *temp,
+                                                  int *idx, mvp_stream_t stream) {
+  return mvp::fps_dispatch<true>(b, n, m, dist, temp, idx, (cudaStream_t)stream);
+}

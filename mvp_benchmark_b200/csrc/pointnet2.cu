@@ -1,0 +1,468 @@
+// PointNet++ neighbourhood / gather ops for sm_100a: ball_query, three_nn, knn, gather_points,
+// group_points, three_interpolate (+ their backward scatters).
+//
+// Replaces the kernels of the reference under utils/mm3d_pn2/ops/:
+//   ball_query/src/ball_query_cuda.cu:11-54        interpolate/src/three_nn_cuda.cu:11-65
+//   knn/src/knn_cuda.cu:58-94                      gather_points/src/gather_points_cuda.cu:8-26,51-70
+//   group_points/src/group_points_cuda.cu:10-31,56-79
+//   interpolate/src/three_interpolate_cuda.cu:11-35,61-84
+//
+// Design differences from the reference (results are identical):
+//   * searches stage the searched cloud through shared memory once per CTA instead of every thread
+//     streaming it from global memory; ball_query uses a WARP per centre (32 candidates per step,
+//     ballot + prefix-popcount keeps the ascending-index order and the early exit);
+//   * gathers read each index (and interpolation weight) ONCE per point and loop channels inside the
+//     thread — the reference re-reads them once per channel;
+//   * outputs that the reference's Python zero-fills are zero-filled here.
+#include "common.cuh"
+
+namespace mvp {
+
+constexpr int kTile = 1024;  // searched points per shared-memory tile (AoS, 12 KB)
+
+__device__ __forceinline__ void load_tile(float *tile, const float *__restrict__ src, int cnt, int tid,
+                                          int nthreads) {
+  for (int i = tid; i < cnt * 3; i += nthreads) tile[i] = __ldg(src + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ball_query: one warp per centre.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBqWarps = 8;
+
+__global__ void __launch_bounds__(kBqWarps * 32)
+ball_query_kernel(int n, int m, float min_radius2, float max_radius2, int nsample,
+                  const float *__restrict__ new_xyz, const float *__restrict__ xyz, int *__restrict__ idx) {
+  __shared__ float tile[kTile * 3];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * kBqWarps + warp;
+  const bool active = p < m;
+  const float *pts = xyz + (size_t)b * n * 3;
+  float cx = 0, cy = 0, cz = 0;
+  int *out = nullptr;
+  if (active) {
+    const float *c = new_xyz + ((size_t)b * m + p) * 3;
+    cx = __ldg(c + 0);
+    cy = __ldg(c + 1);
+    cz = __ldg(c + 2);
+    out = idx + ((size_t)b * m + p) * nsample;
+  }
+  int cnt = 0, first = 0;
+  bool done = !active;
+  for (int k2 = 0; k2 < n; k2 += kTile) {
+    const int tcnt = min(kTile, n - k2);
+    __syncthreads();
+    load_tile(tile, pts + (size_t)k2 * 3, tcnt, threadIdx.x, kBqWarps * 32);
+    __syncthreads();
+    if (done) continue;
+    for (int k = 0; k < tcnt && !done; k += 32) {
+      const int kk = k + lane;
+      bool hit = false;
+      if (kk < tcnt) {
+        const float d2 = sqdist(cx - tile[kk * 3 + 0], cy - tile[kk * 3 + 1], cz - tile[kk * 3 + 2]);
+        hit = (d2 == 0.f) || (d2 >= min_radius2 && d2 < max_radius2);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask) {
+        if (cnt == 0) first = k2 + k + __ffs(mask) - 1;
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (hit && pos < nsample) out[pos] = k2 + kk;
+        cnt += __popc(mask);
+        if (cnt >= nsample) done = true;
+      }
+    }
+  }
+  if (active) {
+    // Rows are zero when nothing was hit (ball_query.py:35); otherwise padded with the first hit (:44-48).
+    const int filled = min(cnt, nsample);
+    for (int l = filled + lane; l < nsample; l += 32) out[l] = first;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// three_nn: one thread per target, sources broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                float *__restrict__ dist2, int *__restrict__ idx) {
+  __shared__ float tile[kTile * 3];
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const bool active = p < n;
+  const float *kn = known + (size_t)b * m * 3;
+  float ux = 0, uy = 0, uz = 0;
+  if (active) {
+    const float *u = unknown + ((size_t)b * n + p) * 3;
+    ux = __ldg(u + 0);
+    uy = __ldg(u + 1);
+    uz = __ldg(u + 2);
+  }
+  // The reference compares the fp32 distance against DOUBLE bests initialised to 1e40 and narrows on
+  // store (three_nn_cuda.cu:35,59-61); +inf in fp32 gives the same decisions and the same stored value.
+  const float inf = __int_as_float(0x7f800000);
+  float best1 = inf, best2 = inf, best3 = inf;
+  int besti1 = 0, besti2 = 0, besti3 = 0;
+  for (int k2 = 0; k2 < m; k2 += kTile) {
+    const int tcnt = min(kTile, m - k2);
+    __syncthreads();
+    load_tile(tile, kn + (size_t)k2 * 3, tcnt, threadIdx.x, 256);
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < tcnt; ++k) {
+      const float d = sqdist(ux - tile[k * 3 + 0], uy - tile[k * 3 + 1], uz - tile[k * 3 + 2]);
+      if (d < best3) {
+        const int kk = k2 + k;
+        if (d < best1) {
+          best3 = best2; besti3 = besti2;
+          best2 = best1; besti2 = besti1;
+          best1 = d; besti1 = kk;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2;
+          best2 = d; besti2 = kk;
+        } else {
+          best3 = d; besti3 = kk;
+        }
+      }
+    }
+  }
+  if (active) {
+    float *od = dist2 + ((size_t)b * n + p) * 3;
+    int *oi = idx + ((size_t)b * n + p) * 3;
+    od[0] = best1; od[1] = best2; od[2] = best3;
+    oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// knn: one thread per centre; the heap procedure is the reference's, step for step, so that the order
+// among equal distances is identical (knn_cuda.cu:26-53,72-93).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void knn_reheap(float *dist, int *idx, int k) {
+  int root = 0;
+  int child = root * 2 + 1;
+  while (child < k) {
+    if (child + 1 < k && dist[child + 1] > dist[child]) child++;
+    if (dist[root] > dist[child]) return;
+    const float tf = dist[root]; dist[root] = dist[child]; dist[child] = tf;
+    const int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+    root = child;
+    child = root * 2 + 1;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+knn_kernel(int n, int m, int nsample, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+           int *__restrict__ idx, float *__restrict__ dist2) {
+  __shared__ float tile[kTile * 3];
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const bool active = p < m;
+  const float *pts = xyz + (size_t)b * n * 3;
+  float cx = 0, cy = 0, cz = 0;
+  if (active) {
+    const float *c = new_xyz + ((size_t)b * m + p) * 3;
+    cx = __ldg(c + 0);
+    cy = __ldg(c + 1);
+    cz = __ldg(c + 2);
+  }
+  float best_dist[100];
+  int best_idx[100];
+  for (int i = 0; i < nsample; i++) {
+    best_dist[i] = 1e10f;
+    best_idx[i] = 0;
+  }
+  for (int k2 = 0; k2 < n; k2 += kTile) {
+    const int tcnt = min(kTile, n - k2);
+    __syncthreads();
+    load_tile(tile, pts + (size_t)k2 * 3, tcnt, threadIdx.x, 128);
+    __syncthreads();
+    if (!active) continue;
+    for (int i = 0; i < tcnt; i++) {
+      const float d2 = sqdist(cx - tile[i * 3 + 0], cy - tile[i * 3 + 1], cz - tile[i * 3 + 2]);
+      if (d2 < best_dist[0]) {
+        best_dist[0] = d2;
+        best_idx[0] = k2 + i;
+        knn_reheap(best_dist, best_idx, nsample);
+      }
+    }
+  }
+  if (!active) return;
+  for (int i = nsample - 1; i > 0; i--) {
+    const float tf = best_dist[0]; best_dist[0] = best_dist[i]; best_dist[i] = tf;
+    const int ti = best_idx[0]; best_idx[0] = best_idx[i]; best_idx[i] = ti;
+    knn_reheap(best_dist, best_idx, i);
+  }
+  int *oi = idx + ((size_t)b * m + p) * nsample;
+  float *od = dist2 + ((size_t)b * m + p) * nsample;
+  for (int i = 0; i < nsample; i++) {
+    oi[i] = best_idx[i];
+    od[i] = best_dist[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather_points / group_points (group is gather with npoints*nsample indices per cloud).
+// grid (ceil(M/256), csplit, B): a thread owns one output column p and walks a slice of channels;
+// stores along p are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_kernel(int c, int n, int mpts, int cper, const float *__restrict__ points,
+              const int *__restrict__ idx, float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= mpts) return;
+  const int c0 = blockIdx.y * cper, c1 = min(c, c0 + cper);
+  const int src = __ldg(idx + (size_t)b * mpts + p);
+  const float *pp = points + ((size_t)b * c + c0) * n + src;
+  float *oo = out + ((size_t)b * c + c0) * mpts + p;
+#pragma unroll 4
+  for (int ci = c0; ci < c1; ci++) {
+    *oo = __ldg(pp);
+    pp += n;
+    oo += mpts;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_grad_kernel(int c, int n, int mpts, int cper, const float *__restrict__ grad_out,
+                   const int *__restrict__ idx, float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= mpts) return;
+  const int c0 = blockIdx.y * cper, c1 = min(c, c0 + cper);
+  const int dst = __ldg(idx + (size_t)b * mpts + p);
+  float *gp = grad_points + ((size_t)b * c + c0) * n + dst;
+  const float *go = grad_out + ((size_t)b * c + c0) * mpts + p;
+#pragma unroll 4
+  for (int ci = c0; ci < c1; ci++) {
+    atomicAdd(gp, __ldg(go));
+    gp += n;
+    go += mpts;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// three_interpolate: out = fma(w2,p2, fma(w0,p0, w1*p1)) — the contraction nvcc gives
+// three_interpolate_cuda.cu:33-34 (SASS-verified).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+three_interpolate_kernel(int c, int m, int n, int cper, const float *__restrict__ points,
+                         const int *__restrict__ idx, const float *__restrict__ weight,
+                         float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n) return;
+  const int c0 = blockIdx.y * cper, c1 = min(c, c0 + cper);
+  const int *id = idx + ((size_t)b * n + p) * 3;
+  const float *w = weight + ((size_t)b * n + p) * 3;
+  const int i0 = __ldg(id + 0), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+  const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  const float *pp = points + ((size_t)b * c + c0) * m;
+  float *oo = out + ((size_t)b * c + c0) * n + p;
+#pragma unroll 4
+  for (int ci = c0; ci < c1; ci++) {
+    *oo = __fmaf_rn(w2, __ldg(pp + i2), __fmaf_rn(w0, __ldg(pp + i0), __fmul_rn(w1, __ldg(pp + i1))));
+    pp += m;
+    oo += n;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+three_interpolate_grad_kernel(int c, int n, int m, int cper, const float *__restrict__ grad_out,
+                              const int *__restrict__ idx, const float *__restrict__ weight,
+                              float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n) return;
+  const int c0 = blockIdx.y * cper, c1 = min(c, c0 + cper);
+  const int *id = idx + ((size_t)b * n + p) * 3;
+  const float *w = weight + ((size_t)b * n + p) * 3;
+  const int i0 = __ldg(id + 0), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+  const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  float *gp = grad_points + ((size_t)b * c + c0) * m;
+  const float *go = grad_out + ((size_t)b * c + c0) * n + p;
+#pragma unroll 4
+  for (int ci = c0; ci < c1; ci++) {
+    const float g = __ldg(go);
+    atomicAdd(gp + i0, __fmul_rn(g, w0));
+    atomicAdd(gp + i1, __fmul_rn(g, w1));
+    atomicAdd(gp + i2, __fmul_rn(g, w2));
+    gp += m;
+    go += n;
+  }
+}
+
+// Channel slices: enough CTAs to fill the machine (>= 4 per SM) without making slices tiny.
+static int channel_slices(int b, int c, int cols) {
+  const long long col_ctas = (long long)b * ((cols + 255) / 256);
+  int split = 1;
+  while (split < c && col_ctas * split < 4LL * kNumSMs && c / (split * 2) >= 4) split *= 2;
+  return split;
+}
+
+static bool bad_dims(int b, int c, int n, int mpts) { return b < 0 || c < 0 || n < 0 || mpts < 0; }
+
+static int gather_launch(int b, int c, int n, int mpts, const float *points, const int *idx, float *out,
+                         cudaStream_t s) {
+  if (bad_dims(b, c, n, mpts)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0 || mpts == 0) return MVP_OK;
+  if (n == 0 || !points || !idx || !out) return MVP_ERR_INVALID_ARGUMENT;
+  const int split = channel_slices(b, c, mpts);
+  const int cper = (c + split - 1) / split;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((mpts + 255) / 256, (c + cper - 1) / cper, bb);
+    gather_kernel<<<grid, 256, 0, s>>>(c, n, mpts, cper, points + (size_t)b0 * c * n,
+                                       idx + (size_t)b0 * mpts, out + (size_t)b0 * c * mpts);
+    count_launch();
+  }
+  return launch_status();
+}
+
+static int gather_grad_launch(int b, int c, int n, int mpts, const float *grad_out, const int *idx,
+                              float *grad_points, cudaStream_t s) {
+  if (bad_dims(b, c, n, mpts)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0 || n == 0) return MVP_OK;
+  if (!grad_points) return MVP_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * c * n, s);
+  if (e != cudaSuccess) return (int)e;
+  if (mpts == 0) return MVP_OK;
+  if (!grad_out || !idx) return MVP_ERR_INVALID_ARGUMENT;
+  const int split = channel_slices(b, c, mpts);
+  const int cper = (c + split - 1) / split;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((mpts + 255) / 256, (c + cper - 1) / cper, bb);
+    gather_grad_kernel<<<grid, 256, 0, s>>>(c, n, mpts, cper, grad_out + (size_t)b0 * c * mpts,
+                                            idx + (size_t)b0 * mpts, grad_points + (size_t)b0 * c * n);
+    count_launch();
+  }
+  return launch_status();
+}
+
+}  // namespace mvp
+
+using namespace mvp;
+
+MVP_API int mvp_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                           const float *new_xyz, const float *xyz, int *idx, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || nsample < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || m == 0 || nsample == 0) return MVP_OK;
+  if (!new_xyz || !idx || (n > 0 && !xyz)) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)b * m * nsample, s);  // ball_query.py:35
+  if (e != cudaSuccess) return (int)e;
+  if (n == 0) return MVP_OK;
+  // Radii are squared in fp32 exactly as ball_query_cuda.cu:30-31 does.
+  const float max_radius2 = max_radius * max_radius;
+  const float min_radius2 = min_radius * min_radius;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((m + kBqWarps - 1) / kBqWarps, bb);
+    ball_query_kernel<<<grid, kBqWarps * 32, 0, s>>>(n, m, min_radius2, max_radius2, nsample,
+                                                     new_xyz + (size_t)b0 * m * 3, xyz + (size_t)b0 * n * 3,
+                                                     idx + (size_t)b0 * m * nsample);
+    count_launch();
+  }
+  return launch_status();
+}
+
+MVP_API int mvp_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                         int *idx, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0) return MVP_OK;
+  if (!unknown || !dist2 || !idx || (m > 0 && !known)) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((n + 255) / 256, bb);
+    three_nn_kernel<<<grid, 256, 0, s>>>(n, m, unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
+                                         dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3);
+    count_launch();
+  }
+  return launch_status();
+}
+
+MVP_API int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                    float *dist2, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (nsample <= 0 || nsample > 100) return MVP_ERR_INVALID_ARGUMENT;  // knn_cuda.cu:72-73 (100 slots)
+  if (b == 0 || m == 0) return MVP_OK;
+  if (!new_xyz || !idx || !dist2 || (n > 0 && !xyz)) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((m + 127) / 128, bb);
+    knn_kernel<<<grid, 128, 0, s>>>(n, m, nsample, xyz + (size_t)b0 * n * 3, new_xyz + (size_t)b0 * m * 3,
+                                    idx + (size_t)b0 * m * nsample, dist2 + (size_t)b0 * m * nsample);
+    count_launch();
+  }
+  return launch_status();
+}
+
+MVP_API int mvp_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                              float *out, mvp_stream_t stream) {
+  return gather_launch(b, c, n, npoints, points, idx, out, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                   float *grad_points, mvp_stream_t stream) {
+  return gather_grad_launch(b, c, n, npoints, grad_out, idx, grad_points, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                             const int *idx, float *out, mvp_stream_t stream) {
+  if (npoints < 0 || nsample < 0 || (long long)npoints * nsample > 0x7fffffffLL)
+    return MVP_ERR_INVALID_ARGUMENT;
+  return gather_launch(b, c, n, npoints * nsample, points, idx, out, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                  const int *idx, float *grad_points, mvp_stream_t stream) {
+  if (npoints < 0 || nsample < 0 || (long long)npoints * nsample > 0x7fffffffLL)
+    return MVP_ERR_INVALID_ARGUMENT;
+  return gather_grad_launch(b, c, n, npoints * nsample, grad_out, idx, grad_points, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                                  const float *weight, float *out, mvp_stream_t stream) {
+  if (bad_dims(b, c, m, n)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0 || n == 0) return MVP_OK;
+  if (m == 0 || !points || !idx || !weight || !out) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int split = channel_slices(b, c, n);
+  const int cper = (c + split - 1) / split;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((n + 255) / 256, (c + cper - 1) / cper, bb);
+    three_interpolate_kernel<<<grid, 256, 0, s>>>(c, m, n, cper, points + (size_t)b0 * c * m,
+                                                  idx + (size_t)b0 * n * 3, weight + (size_t)b0 * n * 3,
+                                                  out + (size_t)b0 * c * n);
+    count_launch();
+  }
+  return launch_status();
+}
+
+MVP_API int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                       const float *weight, float *grad_points, mvp_stream_t stream) {
+  if (bad_dims(b, c, m, n)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0 || m == 0) return MVP_OK;
+  if (!grad_points) return MVP_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * c * m, s);
+  if (e != cudaSuccess) return (int)e;
+  if (n == 0) return MVP_OK;
+  if (!grad_out || !idx || !weight) return MVP_ERR_INVALID_ARGUMENT;
+  const int split = channel_slices(b, c, n);
+  const int cper = (c + split - 1) / split;
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    dim3 grid((n + 255) / 256, (c + cper - 1) / cper, bb);
+    three_interpolate_grad_kernel<<<grid, 256, 0, s>>>(c, n, m, cper, grad_out + (size_t)b0 * c * n,
+                                                       idx + (size_t)b0 * n * 3, weight + (size_t)b0 * n * 3,
+                                                       grad_points + (size_t)b0 * c * m);
+    count_launch();
+  }
+  return launch_status();
+}

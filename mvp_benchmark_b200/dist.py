@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the operator hot path: one process per GPU, the batch sharded across ranks,
+NO collective on the operator path (every op is independent per cloud) and ONE all-reduce
+of fp32 gradients per training step (what replaces the reference's single-process nn.DataParallel,
+completion/train.py:49,141).  Backend-agnostic: NCCL over NVLink on the B200 box, gloo in CPU tests.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world,
+    local_rank); a single-process run (no RANK in the env) returns (0, 1, 0) without initialising."""
+    if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous slice [lo, hi) of `total` clouds owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(t, rank, world, dim=0):
+    lo, hi = shard_bounds(t.size(dim), rank, world)
+    return t.narrow(dim, lo, hi - lo)
+
+
+def allreduce_gradients(params, world=None, bucket_bytes=32 << 20, average=True):
+    """Sum (or average) the .grad of `params` across ranks with as few collectives as possible: grads are
+    flattened into buckets of `bucket_bytes` (sized for launch latency, not link count — NVSwitch gives
+    every pair full bandwidth).  Returns the number of collectives issued."""
+    if not dist.is_initialized():
+        return 0
+    world = world or dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    calls, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal calls, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat /= world
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        calls += 1
+        bucket, size = [], 0
+
+    for g in grads:
+        nbytes = g.numel() * g.element_size()
+        if size + nbytes > bucket_bytes and bucket:
+            flush()
+        bucket.append(g)
+        size += nbytes
+    flush()
+    return calls
+
+
+def max_over_ranks(value, device):
+    """max of a python float over ranks (timing: a multi-GPU number is the slowest rank's)."""
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()

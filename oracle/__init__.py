@@ -1,0 +1,233 @@
+"""TEST INFRASTRUCTURE — numpy-facing wrapper of the CPU oracle (oracle/oracle.c) and, when it was
+built, of the reference CUDA kernels recompiled for sm_100a (oracle/_ref/libref_ops.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+package.  Nothing under mvp_benchmark_b200/ does: the product path has no CPU fallback.
+
+Each function names the reference lines it restates in oracle/oracle.c.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+_f = ctypes.POINTER(ctypes.c_float)
+_i = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force=False):
+    """gcc recipe for liboracle.so (plain C + OpenMP; -mavx2 -mfma so fmaf is one instruction)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if not force and os.path.isfile(_LIB_PATH) and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src):
+        return _LIB_PATH
+    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-mavx2", "-mfma",
+           "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", src, "-o", _LIB_PATH, "-lm"]
+    subprocess.check_call(cmd)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.oracle_emd_forward.restype = ctypes.c_int
+        _lib.oracle_knn.restype = ctypes.c_int
+        _lib.oracle_fps_block_size.restype = ctypes.c_int
+        _lib.oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def chamfer_forward(xyz1, xyz2):
+    """chamfer3D.cu:12-154 -> (dist1, dist2, idx1, idx2)."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist1 = np.empty((b, n), np.float32)
+    dist2 = np.empty((b, m), np.float32)
+    idx1 = np.empty((b, n), np.int32)
+    idx2 = np.empty((b, m), np.int32)
+    lib().oracle_chamfer_forward(b, n, m, _fp(xyz1), _fp(xyz2), _fp(dist1), _fp(dist2), _ip(idx1), _ip(idx2))
+    return dist1, dist2, idx1, idx2
+
+
+def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
+    """chamfer3D.cu:155-195 -> (gradxyz1, gradxyz2)."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    g1, g2, idx1, idx2 = _f32(graddist1), _f32(graddist2), _i32(idx1), _i32(idx2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    gx1 = np.empty((b, n, 3), np.float32)
+    gx2 = np.empty((b, m, 3), np.float32)
+    lib().oracle_chamfer_backward(b, n, m, _fp(xyz1), _fp(xyz2), _fp(g1), _fp(g2), _ip(idx1), _ip(idx2),
+                                  _fp(gx1), _fp(gx2))
+    return gx1, gx2
+
+
+def emd_forward(xyz1, xyz2, eps, iters, return_price=False):
+    """emd_cuda.cu:23-282 -> (dist, assignment[, price])."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, _ = xyz1.shape
+    assert xyz2.shape == xyz1.shape
+    dist = np.empty((b, n), np.float32)
+    asg = np.empty((b, n), np.int32)
+    price = np.empty((b, n), np.float32)
+    rc = lib().oracle_emd_forward(b, n, _fp(xyz1), _fp(xyz2), ctypes.c_float(eps), int(iters), _fp(dist),
+                                  _ip(asg), _fp(price))
+    if rc != 0:
+        raise ValueError("oracle_emd_forward: invalid input (b<=512, n%1024==0 required)")
+    return (dist, asg, price) if return_price else (dist, asg)
+
+
+def emd_backward(xyz1, xyz2, graddist, assignment):
+    """emd_cuda.cu:284-316 -> gradxyz1."""
+    xyz1, xyz2, g, a = _f32(xyz1), _f32(xyz2), _f32(graddist), _i32(assignment)
+    b, n, _ = xyz1.shape
+    out = np.empty((b, n, 3), np.float32)
+    lib().oracle_emd_backward(b, n, _fp(xyz1), _fp(xyz2), _fp(g), _ip(a), _fp(out))
+    return out
+
+
+def fps_block_size(n):
+    """furthest_point_sample_cuda.cu:11-15."""
+    return lib().oracle_fps_block_size(int(n))
+
+
+def furthest_point_sample(xyz, m):
+    """furthest_point_sample_cuda.cu:26-141 -> idx (B, m) int32."""
+    xyz = _f32(xyz)
+    b, n, _ = xyz.shape
+    idx = np.zeros((b, m), np.int32)
+    lib().oracle_fps(b, n, int(m), _fp(xyz), _ip(idx))
+    return idx
+
+
+def furthest_point_sample_with_dist(dist, m):
+    """furthest_point_sample_cuda.cu:214-331 -> idx (B, m) int32."""
+    dist = _f32(dist)
+    b, n, _ = dist.shape
+    idx = np.zeros((b, m), np.int32)
+    lib().oracle_fps_with_dist(b, n, int(m), _fp(dist), _ip(idx))
+    return idx
+
+
+def ball_query(min_radius, max_radius, nsample, xyz, center_xyz):
+    """ball_query_cuda.cu:11-54 -> idx (B, npoint, nsample) int32."""
+    xyz, c = _f32(xyz), _f32(center_xyz)
+    b, n, _ = xyz.shape
+    m = c.shape[1]
+    idx = np.empty((b, m, nsample), np.int32)
+    lib().oracle_ball_query(b, n, m, ctypes.c_float(min_radius), ctypes.c_float(max_radius), int(nsample),
+                            _fp(c), _fp(xyz), _ip(idx))
+    return idx
+
+
+def gather_points(points, idx):
+    """gather_points_cuda.cu:8-26 -> (B, C, M)."""
+    points, idx = _f32(points), _i32(idx)
+    b, c, n = points.shape
+    m = idx.shape[1]
+    out = np.empty((b, c, m), np.float32)
+    lib().oracle_gather_points(b, c, n, m, _fp(points), _ip(idx), _fp(out))
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    """gather_points_cuda.cu:51-70 -> (B, C, N)."""
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    b, c, m = grad_out.shape
+    out = np.empty((b, c, n), np.float32)
+    lib().oracle_gather_points_grad(b, c, n, m, _fp(grad_out), _ip(idx), _fp(out))
+    return out
+
+
+def group_points(points, idx):
+    """group_points_cuda.cu:56-79 -> (B, C, npoint, nsample)."""
+    points, idx = _f32(points), _i32(idx)
+    b, c, n = points.shape
+    _, p, s = idx.shape
+    out = np.empty((b, c, p, s), np.float32)
+    lib().oracle_group_points(b, c, n, p, s, _fp(points), _ip(idx), _fp(out))
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """group_points_cuda.cu:10-31 -> (B, C, N)."""
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    b, c, p, s = grad_out.shape
+    out = np.empty((b, c, n), np.float32)
+    lib().oracle_group_points_grad(b, c, n, p, s, _fp(grad_out), _ip(idx), _fp(out))
+    return out
+
+
+def three_nn(unknown, known):
+    """three_nn_cuda.cu:11-65 -> (dist2 SQUARED (B,N,3), idx (B,N,3))."""
+    unknown, known = _f32(unknown), _f32(known)
+    b, n, _ = unknown.shape
+    m = known.shape[1]
+    d = np.empty((b, n, 3), np.float32)
+    idx = np.empty((b, n, 3), np.int32)
+    lib().oracle_three_nn(b, n, m, _fp(unknown), _fp(known), _fp(d), _ip(idx))
+    return d, idx
+
+
+def three_interpolate(points, idx, weight):
+    """three_interpolate_cuda.cu:11-35 -> (B, C, n)."""
+    points, idx, weight = _f32(points), _i32(idx), _f32(weight)
+    b, c, m = points.shape
+    n = idx.shape[1]
+    out = np.empty((b, c, n), np.float32)
+    lib().oracle_three_interpolate(b, c, m, n, _fp(points), _ip(idx), _fp(weight), _fp(out))
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """three_interpolate_cuda.cu:61-84 -> (B, C, m)."""
+    grad_out, idx, weight = _f32(grad_out), _i32(idx), _f32(weight)
+    b, c, n = grad_out.shape
+    out = np.empty((b, c, m), np.float32)
+    lib().oracle_three_interpolate_grad(b, c, n, m, _fp(grad_out), _ip(idx), _fp(weight), _fp(out))
+    return out
+
+
+def knn(k, xyz, center_xyz):
+    """knn_cuda.cu:58-94 -> (idx (B, npoint, k) int32, dist2 (B, npoint, k)) — before the Python
+    transpose of knn.py:63."""
+    xyz, c = _f32(xyz), _f32(center_xyz)
+    b, n, _ = xyz.shape
+    m = c.shape[1]
+    idx = np.empty((b, m, k), np.int32)
+    d = np.empty((b, m, k), np.float32)
+    rc = lib().oracle_knn(b, n, m, int(k), _fp(xyz), _fp(c), _ip(idx), _fp(d))
+    if rc != 0:
+        raise ValueError("oracle_knn: 0 < k <= 100 required (knn_cuda.cu:72-73)")
+    return idx, d

@@ -1,0 +1,72 @@
+"""CPU-only, world_size 2 over gloo: the N>1 plumbing (batch sharding, bucketed gradient all-reduce,
+max-over-ranks timing) used by bench.py --gpus N and by a data-parallel training step."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from mvp_benchmark_b200 import dist as mdist
+    r, w, _ = mdist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    batch = torch.arange(7 * 3, dtype=torch.float32).view(7, 3)          # 7 clouds over 2 ranks -> 4 + 3
+    mine = mdist.shard_batch(batch, r, w)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.Linear(5, 2))
+    torch.manual_seed(0)
+    for p in model.parameters():
+        torch.nn.init.normal_(p)
+    model(mine).sum().backward()
+    calls = mdist.allreduce_gradients(list(model.parameters()), bucket_bytes=64, average=False)
+    slowest = mdist.max_over_ranks(1.0 + rank, torch.device("cpu"))
+    mdist.barrier()
+    q.put((rank, mine.shape[0], calls, slowest, [p.grad.tolist() for p in model.parameters()]))
+    torch.distributed.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    from mvp_benchmark_b200.dist import shard_bounds
+    for total in (1, 7, 32, 256):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_sharded_step_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [4, 3]                      # contiguous batch slices
+    assert res[0][2] == res[1][2] and res[0][2] >= 2           # bucketed: several small collectives
+    assert res[0][3] == res[1][3] == 2.0                       # max over ranks
+    # summed gradients equal the single-process gradient on the whole batch
+    batch = torch.arange(7 * 3, dtype=torch.float32).view(7, 3)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.Linear(5, 2))
+    torch.manual_seed(0)
+    for p in model.parameters():
+        torch.nn.init.normal_(p)
+    model(batch).sum().backward()
+    for g0, g1, p in zip(res[0][4], res[1][4], model.parameters()):
+        g0, g1 = torch.tensor(g0), torch.tensor(g1)
+        assert torch.allclose(g0, g1) and torch.allclose(g0, p.grad, rtol=1e-5, atol=1e-5)

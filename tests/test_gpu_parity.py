@@ -1,0 +1,299 @@
+"""GPU parity tests proper: the product (libmvp_ops.so through its C ABI) against
+  (a) the CPU oracle on seeded inputs,
+  (b) the committed goldens of the reference CUDA kernels,
+  (c) the reference CUDA kernels themselves, live, when oracle/_ref/libref_ops.so travelled to the box,
+  (d) size-independent properties at BASELINE.json's full sizes.
+Bars: SURVEY.md §A5 — bit-exact indices / distances / gathers; 1e-5 relative for atomically accumulated
+gradients (tolerance constants in tests/_cases.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _cases
+import _data
+from _impls import CudaImpl, OracleImpl
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_GOLD = os.path.join(HERE, "golden", "ref_cuda_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def gpu(cuda):
+    return CudaImpl(str(cuda))
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    return OracleImpl()
+
+
+@pytest.fixture(scope="module")
+def ref(cuda):
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_ops.so not built")
+    return ref_cuda
+
+
+def test_extension_is_loaded_and_launches(gpu):
+    from mvp_benchmark_b200 import _lib
+    before = _lib.launch_count()
+    gpu.fps(_data.uniform(1, 64, 0), 8)
+    assert _lib.launch_count() > before
+    assert any("libmvp_ops.so" in line for line in open("/proc/self/maps"))
+
+
+# ---------------------------------------------------------------------------------------------- goldens
+def _gold_cases():
+    if not os.path.isfile(CUDA_GOLD):
+        return []
+    return [nm for nm, _ in _cases.all_cases(np.load(CUDA_GOLD))]
+
+
+@pytest.mark.skipif(not os.path.isfile(CUDA_GOLD), reason="ref_cuda_golden.npz not generated yet")
+@pytest.mark.parametrize("case", _gold_cases())
+def test_product_vs_reference_cuda_golden(gpu, case):
+    G = dict(np.load(CUDA_GOLD))
+    dict(_cases.all_cases(G))[case](gpu, _cases.group(G, case), case)
+
+
+# ---------------------------------------------------------------------------------------------- Chamfer
+CD_SHAPES = [(4, 2048, 2048), (2, 100, 200), (3, 1, 1), (2, 1, 700), (2, 513, 1023), (1, 1025, 1024), (2, 2048, 3072),
+             (1, 5000, 333), (5, 257, 4097)]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "sphere", "duplicates", "lattice"])
+@pytest.mark.parametrize("b,n,m", CD_SHAPES)
+def test_chamfer_forward_vs_oracle(gpu, cpu, kind, b, n, m):
+    x1, x2 = _data.cloud(kind, b, n, 1), _data.cloud(kind, b, m, 2)
+    got, want = gpu.chamfer_forward(x1, x2), cpu.chamfer_forward(x1, x2)
+    for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+        _cases.eq(g, w, f"chamfer {kind} {b}x{n}x{m} {nm}")
+
+
+def test_chamfer_self_distance_is_zero_with_lowest_duplicate(gpu):
+    x = _data.duplicates(2, 1500, 3, frac=0.2)
+    d1, d2, i1, i2 = gpu.chamfer_forward(x, x)
+    assert (d1 == 0).all() and (d2 == 0).all()
+    # lowest index among coincident points (strict `<` scanning upward, chamfer3D.cu:36,126)
+    for b in range(2):
+        first = {}
+        for j, p in enumerate(map(bytes, x[b])):
+            first.setdefault(p, j)
+        want = np.array([first[bytes(p)] for p in x[b]], np.int32)
+        assert (i1[b] == want).all() and (i2[b] == want).all()
+
+
+@pytest.mark.parametrize("b,n,m", [(4, 2048, 2048), (2, 100, 200), (2, 1, 700), (3, 4097, 129)])
+def test_chamfer_backward_vs_oracle(gpu, cpu, b, n, m):
+    x1, x2 = _data.uniform(b, n, 5), _data.uniform(b, m, 6)
+    rng = np.random.default_rng(0)
+    g1, g2 = rng.random((b, n), dtype=np.float32), rng.random((b, m), dtype=np.float32)
+    _, _, i1, i2 = cpu.chamfer_forward(x1, x2)
+    got, want = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2), cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
+    _cases.close(got[0], want[0], "gradxyz1")
+    _cases.close(got[1], want[1], "gradxyz2")
+
+
+def test_chamfer_full_size_properties_and_reference(gpu, ref, cuda):
+    """BASELINE target size B=32, N=M=16384: checked through properties and against the reference
+    kernels live (the CPU oracle would need minutes)."""
+    import torch
+    b, n, m = 32, 16384, 16384
+    x1, x2 = _data.uniform(b, n, 11), _data.uniform(b, m, 12)
+    d1, d2, i1, i2 = gpu.chamfer_forward(x1, x2)
+    assert i1.min() >= 0 and i1.max() < m and i2.min() >= 0 and i2.max() < n
+    # (1) the reported distance is the distance to the reported neighbour, bit for bit
+    for d, i, a, c in [(d1, i1, x1, x2), (d2, i2, x2, x1)]:
+        t = np.take_along_axis(c, i[..., None].astype(np.int64), axis=1)
+        dx, dy, dz = (t - a)[..., 0], (t - a)[..., 1], (t - a)[..., 2]
+        r = (dy * dy).astype(np.float32)
+        r = (dx.astype(np.float64) * dx + r).astype(np.float32)
+        r = (dz.astype(np.float64) * dz + r).astype(np.float32)
+        np.testing.assert_array_max_ulp(d, r, maxulp=1)
+    # (2) no sampled candidate is closer
+    rng = np.random.default_rng(0)
+    cand = rng.integers(0, m, 64)
+    dd = ((x1[:, :, None, :] - x2[:, None, cand, :]) ** 2).sum(-1)
+    assert (d1[..., None] <= dd * (1 + 1e-5) + 1e-12).all()
+    # (3) swapping the clouds swaps the outputs
+    e1, e2, j1, j2 = gpu.chamfer_forward(x2, x1)
+    _cases.eq(e1, d2, "swap dist"), _cases.eq(e2, d1, "swap dist"), _cases.eq(j1, i2, "swap idx"), _cases.eq(j2, i1, "swap idx")
+    # (4) the reference kernels agree bit for bit
+    r1, r2, ri1, ri2 = ref.chamfer_forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda))
+    _cases.eq(d1, r1.cpu().numpy(), "dist1 vs reference CUDA")
+    _cases.eq(d2, r2.cpu().numpy(), "dist2 vs reference CUDA")
+    _cases.eq(i1, ri1.cpu().numpy(), "idx1 vs reference CUDA")
+    _cases.eq(i2, ri2.cpu().numpy(), "idx2 vs reference CUDA")
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "duplicates"])
+@pytest.mark.parametrize("b,n,m", [(64, 2048, 3072), (32, 2048, 1024), (4, 16384, 1024), (3, 777, 5001)])
+def test_chamfer_vs_reference_cuda_live(gpu, ref, cuda, kind, b, n, m):
+    import torch
+    x1, x2 = _data.cloud(kind, b, n, 21), _data.cloud(kind, b, m, 22)
+    got = gpu.chamfer_forward(x1, x2)
+    want = ref.chamfer_forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda))
+    for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+        _cases.eq(g, w.cpu().numpy(), f"{nm} vs reference CUDA")
+    rng = np.random.default_rng(1)
+    g1, g2 = rng.random((b, n), dtype=np.float32), rng.random((b, m), dtype=np.float32)
+    gx = gpu.chamfer_backward(x1, x2, g1, g2, got[2], got[3])
+    T = lambda a: torch.from_numpy(a).to(cuda)  # noqa: E731
+    rx = ref.chamfer_backward(T(x1), T(x2), T(g1), T(g2), want[2], want[3])
+    _cases.close(gx[0], rx[0].cpu().numpy(), "gradxyz1 vs reference CUDA")
+    _cases.close(gx[1], rx[1].cpu().numpy(), "gradxyz2 vs reference CUDA")
+
+
+# ---------------------------------------------------------------------------------------------- EMD
+@pytest.mark.parametrize("kind,b,n,eps,iters", [("uniform", 2, 1024, 0.005, 50), ("sphere", 3, 2048, 0.005, 50),
+                                                ("uniform", 1, 3072, 0.005, 30), ("uniform", 2, 1024, 0.002, 1),
+                                                ("duplicates", 2, 1024, 0.005, 20), ("lattice", 1, 1024, 0.01, 40),
+                                                ("uniform", 1, 4096, 0.004, 400)])
+def test_emd_vs_oracle(gpu, cpu, kind, b, n, eps, iters):
+    x1, x2 = _data.cloud(kind, b, n, 31), _data.cloud(kind, b, n, 32)
+    d, a = gpu.emd_forward(x1, x2, eps, iters)
+    wd, wa = cpu.emd_forward(x1, x2, eps, iters)
+    _cases.eq(a, wa, f"emd {kind} assignment")
+    _cases.eq(d, wd, f"emd {kind} dist")
+    g = np.random.default_rng(3).random((b, n), dtype=np.float32)
+    _cases.eq(gpu.emd_backward(x1, x2, g, a), cpu.emd_backward(x1, x2, g, a), "emd gradxyz1")
+
+
+def test_emd_c5_shape_properties_and_reference(gpu, ref, cuda):
+    """BASELINE config C5 (B=64 is scaled to 8 here to keep the reference leg short), n=8192."""
+    import torch
+    b, n = 8, 8192
+    x1, x2 = _data.uniform(b, n, 41), _data.uniform(b, n, 42)
+    d, a = gpu.emd_forward(x1, x2, 0.005, 50)
+    _cases.emd_consistent(x1, x2, d, a)
+    rd, ra = ref.emd_forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), 0.005, 50)
+    rd, ra = rd.cpu().numpy(), ra.cpu().numpy()
+    frac = (a == ra).mean()
+    m, r = np.sqrt(d).mean(), np.sqrt(rd).mean()
+    print(f"\nEMD n=8192 iters=50: identical assignments {frac:.6f}; mean sqrt(dist) ours {m:.7f} reference {r:.7f}")
+    assert abs(m - r) <= 1e-3 * r
+    assert frac > 0.99
+
+
+def test_emd_input_errors(gpu):
+    from mvp_benchmark_b200._lib import MvpOpsError
+    x = _data.uniform(1, 1000, 0)
+    with pytest.raises(MvpOpsError, match="multiple of 1024"):
+        gpu.emd_forward(x, x, 0.005, 5)
+
+
+# ---------------------------------------------------------------------------------------------- FPS
+FPS_CASES = [("uniform", 32, 2048, 2048), ("uniform", 4, 3072, 1536), ("uniform", 4, 1536, 768), ("uniform", 4, 768, 384),
+             ("uniform", 4, 3072, 2048), ("lattice", 2, 2048, 2048), ("duplicates", 2, 1000, 1000), ("sphere", 2, 16384, 256),
+             ("uniform", 2, 1, 1), ("uniform", 2, 5, 9), ("lattice", 2, 100, 100), ("uniform", 1, 40000, 64),
+             ("duplicates", 1, 4096, 4096), ("uniform", 2, 6000, 50), ("uniform", 2, 20000, 40)]
+
+
+@pytest.mark.parametrize("kind,b,n,m", FPS_CASES)
+def test_fps_vs_oracle(gpu, cpu, kind, b, n, m):
+    x = _data.cloud(kind, b, n, 51)
+    _cases.eq(gpu.fps(x, m), cpu.fps(x, m), f"fps {kind} {b}x{n}->{m}")
+
+
+def test_fps_with_dist_vs_oracle(gpu, cpu):
+    x = _data.lattice(2, 300, 7)
+    dm = ((x[:, :, None, :] - x[:, None, :, :]) ** 2).sum(-1).astype(np.float32)
+    _cases.eq(gpu.fps_with_dist(dm, 300), cpu.fps_with_dist(dm, 300), "fps_with_dist lattice")
+    x = _data.uniform(2, 1100, 8)
+    dm = ((x[:, :, None, :] - x[:, None, :, :]) ** 2).sum(-1).astype(np.float32)
+    _cases.eq(gpu.fps_with_dist(dm, 200), cpu.fps_with_dist(dm, 200), "fps_with_dist uniform")
+
+
+@pytest.mark.parametrize("kind,b,n,m", [("uniform", 64, 3072, 2048), ("lattice", 8, 1536, 768), ("duplicates", 8, 768, 384)])
+def test_fps_vs_reference_cuda_live(gpu, ref, cuda, kind, b, n, m):
+    import torch
+    x = _data.cloud(kind, b, n, 52)
+    _cases.eq(gpu.fps(x, m), ref.furthest_point_sample(torch.from_numpy(x).to(cuda), m).cpu().numpy(), "fps vs reference")
+
+
+# ---------------------------------------------------------------------------------------------- neighbourhood ops
+@pytest.mark.parametrize("kind,b,n,p,rmin,rmax,ns", [("uniform", 32, 2048, 102, 0.0, 0.0632455532, 8),
+                                                      ("uniform", 4, 1024, 51, 0.0, 0.1095445115, 12),
+                                                      ("lattice", 2, 1500, 33, 0.0, 0.13, 24), ("uniform", 2, 3000, 257, 0.05, 0.2, 64),
+                                                      ("uniform", 2, 40, 9, 0.0, 5.0, 50), ("uniform", 1, 2500, 10, 0.0, 1e-6, 4)])
+def test_ball_query_vs_oracle(gpu, cpu, kind, b, n, p, rmin, rmax, ns):
+    x = _data.cloud(kind, b, n, 61)
+    c = x[:, :p].copy() if p <= n else _data.cloud(kind, b, p, 62)
+    _cases.eq(gpu.ball_query(rmin, rmax, ns, x, c), cpu.ball_query(rmin, rmax, ns, x, c), "ball_query")
+
+
+@pytest.mark.parametrize("kind,b,n,m", [("uniform", 64, 768, 384), ("uniform", 8, 1536, 768), ("uniform", 8, 3072, 1536),
+                                        ("lattice", 2, 500, 300), ("uniform", 2, 10, 2), ("uniform", 2, 1300, 1025)])
+def test_three_nn_vs_oracle(gpu, cpu, kind, b, n, m):
+    u, k = _data.cloud(kind, b, n, 71), _data.cloud(kind, b, m, 72)
+    got, want = gpu.three_nn(u, k), cpu.three_nn(u, k)
+    _cases.eq(got[1], want[1], "three_nn idx")
+    _cases.eq(got[0], want[0], "three_nn dist2")
+
+
+@pytest.mark.parametrize("kind,b,n,p,k", [("uniform", 2, 2048, 512, 16), ("lattice", 2, 700, 128, 10), ("uniform", 1, 300, 300, 100),
+                                          ("uniform", 2, 5, 7, 8), ("duplicates", 2, 1030, 65, 3)])
+def test_knn_vs_oracle(gpu, cpu, kind, b, n, p, k):
+    x, c = _data.cloud(kind, b, n, 81), _data.cloud(kind, b, p, 82)
+    got, want = gpu.knn(k, x, c), cpu.knn(k, x, c)
+    _cases.eq(got[1], want[1], "knn dist2")
+    _cases.eq(got[0], want[0], "knn idx")
+
+
+# ---------------------------------------------------------------------------------------------- gathers
+@pytest.mark.parametrize("b,c,n,m", [(64, 3, 2048, 2048), (8, 64, 3072, 15360), (2, 256, 768, 3840), (2, 1, 5, 1), (3, 7, 100, 1000)])
+def test_gather_vs_oracle(gpu, cpu, b, c, n, m):
+    rng = np.random.default_rng(91)
+    pts = rng.standard_normal((b, c, n)).astype(np.float32)
+    idx = rng.integers(0, n, (b, m)).astype(np.int32)
+    go = rng.standard_normal((b, c, m)).astype(np.float32)
+    _cases.eq(gpu.gather(pts, idx), cpu.gather(pts, idx), "gather")
+    _cases.close(gpu.gather_grad(go, idx, n), cpu.gather_grad(go, idx, n), "gather grad", atol=1e-5)
+
+
+@pytest.mark.parametrize("b,c,n,p,s", [(8, 64, 3072, 1536, 1), (4, 3, 2048, 102, 24), (2, 128, 1536, 768, 1), (1, 2, 9, 4, 3)])
+def test_group_vs_oracle(gpu, cpu, b, c, n, p, s):
+    rng = np.random.default_rng(92)
+    pts = rng.standard_normal((b, c, n)).astype(np.float32)
+    idx = rng.integers(0, n, (b, p, s)).astype(np.int32)
+    go = rng.standard_normal((b, c, p, s)).astype(np.float32)
+    _cases.eq(gpu.group(pts, idx), cpu.group(pts, idx), "group")
+    _cases.close(gpu.group_grad(go, idx, n), cpu.group_grad(go, idx, n), "group grad", atol=1e-5)
+
+
+@pytest.mark.parametrize("b,c,m,n", [(8, 512, 384, 768), (4, 256, 768, 1536), (2, 128, 1536, 3072), (1, 3, 4, 5)])
+def test_three_interpolate_vs_oracle(gpu, cpu, b, c, m, n):
+    rng = np.random.default_rng(93)
+    pts = rng.standard_normal((b, c, m)).astype(np.float32)
+    idx = rng.integers(0, m, (b, n, 3)).astype(np.int32)
+    w = rng.random((b, n, 3), dtype=np.float32)
+    go = rng.standard_normal((b, c, n)).astype(np.float32)
+    _cases.eq(gpu.three_interpolate(pts, idx, w), cpu.three_interpolate(pts, idx, w), "three_interpolate")
+    _cases.close(gpu.three_interpolate_grad(go, idx, w, m), cpu.three_interpolate_grad(go, idx, w, m), "interp grad", atol=1e-5)
+
+
+def test_mm3d_ops_vs_reference_cuda_live(gpu, ref, cuda):
+    import torch
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)  # noqa: E731
+    x, c = _data.uniform(8, 2048, 101), _data.uniform(8, 102, 102)
+    _cases.eq(gpu.ball_query(0.0, 0.0774596669, 12, x, c), ref.ball_query(0.0, 0.0774596669, 12, T(x), T(c)).cpu().numpy(), "bq")
+    u, k = _data.uniform(8, 3072, 103), _data.uniform(8, 1536, 104)
+    gd, gi = gpu.three_nn(u, k)
+    rd, ri = ref.three_nn(T(u), T(k))
+    _cases.eq(gi, ri.cpu().numpy(), "three_nn idx"), _cases.eq(gd, rd.cpu().numpy(), "three_nn dist2")
+    gi, gd = gpu.knn(16, x, c)
+    ri, rd = ref.knn(16, T(x), T(c))
+    _cases.eq(gi, ri.cpu().numpy(), "knn idx"), _cases.eq(gd, rd.cpu().numpy(), "knn dist2")
+    rng = np.random.default_rng(5)
+    pts = rng.standard_normal((8, 64, 3072)).astype(np.float32)
+    idx = rng.integers(0, 3072, (8, 15360)).astype(np.int32)
+    _cases.eq(gpu.gather(pts, idx), ref.gather_points(T(pts), T(idx)).cpu().numpy(), "gather")
+    i3 = rng.integers(0, 1536, (8, 3072, 3)).astype(np.int32)
+    w = rng.random((8, 3072, 3), dtype=np.float32)
+    f = rng.standard_normal((8, 128, 1536)).astype(np.float32)
+    _cases.eq(gpu.three_interpolate(f, i3, w), ref.three_interpolate(T(f), T(i3), T(w)).cpu().numpy(), "interp")

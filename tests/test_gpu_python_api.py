@@ -1,0 +1,142 @@
+"""GPU: the reference-facing Python layer (autograd Functions / Modules named as in the reference)
+drives the same kernels — shapes, dtypes, non-differentiable outputs, backward arities, streams."""
+import numpy as np
+import pytest
+import torch
+
+import _cases
+import _data
+from _impls import OracleImpl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    return OracleImpl()
+
+
+def T(a, dev, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.requires_grad_(True) if grad else t
+
+
+def test_cd_module_forward_backward(ops, cuda, cpu):
+    metrics, _ = ops
+    x1, x2 = _data.uniform(4, 100, 0), _data.uniform(4, 200, 1)      # shapes of unit_test.py:15-16
+    a, c = T(x1, cuda, True), T(x2, cuda, True)
+    dist1, dist2, idx1, idx2 = metrics.cd()(a, c)
+    assert dist1.shape == (4, 100) and dist2.shape == (4, 200) and idx1.dtype == torch.int32 and idx2.dtype == torch.int32
+    assert not idx1.requires_grad and dist1.requires_grad
+    w1, w2 = torch.rand_like(dist1), torch.rand_like(dist2)
+    ((dist1 * w1).sum() + (dist2 * w2).sum()).backward()
+    od1, od2, oi1, oi2 = cpu.chamfer_forward(x1, x2)
+    _cases.eq(dist1.detach().cpu().numpy(), od1, "dist1"), _cases.eq(idx2.cpu().numpy(), oi2, "idx2")
+    g1, g2 = cpu.chamfer_backward(x1, x2, w1.cpu().numpy(), w2.cpu().numpy(), oi1, oi2)
+    _cases.close(a.grad.cpu().numpy(), g1, "gradxyz1"), _cases.close(c.grad.cpu().numpy(), g2, "gradxyz2")
+    # the reference's own assertion against its pure-torch Chamfer (unit_test.py:22-33)
+    from metrics.CD import chamfer_python
+    m1, m2, mi1, mi2 = chamfer_python.distChamfer(a.detach(), c.detach())
+    assert (torch.mean((dist1 - m1) ** 2) + torch.mean((dist2 - m2) ** 2)).item() < 1e-8
+    assert (idx1 == mi1).all() and (idx2 == mi2).all()
+    f, p1, p2 = metrics.fscore(dist1, dist2)
+    assert f.shape == (4,)
+
+
+def test_cd_noncontiguous_and_only_one_output_used(ops, cuda):
+    metrics, _ = ops
+    a = torch.rand(2, 3, 300, device=cuda).transpose(1, 2).requires_grad_(True)     # (2,300,3) non-contiguous
+    c = torch.rand(2, 150, 3, device=cuda)
+    d1, _, _, _ = metrics.cd()(a, c)
+    d1.mean().backward()
+    assert a.grad is not None and a.grad.shape == (2, 300, 3) and torch.isfinite(a.grad).all()
+
+
+def test_calc_cd_formula_as_the_models_use_it(ops, cuda):
+    """completion/model_utils.py:67-77 on top of the op."""
+    metrics, _ = ops
+    out, gt = torch.rand(3, 512, 3, device=cuda), torch.rand(3, 700, 3, device=cuda)
+    dist1, dist2, _, _ = metrics.cd()(gt, out)
+    cd_p = (torch.sqrt(dist1).mean(1) + torch.sqrt(dist2).mean(1)) / 2
+    cd_t = dist1.mean(1) + dist2.mean(1)
+    ref = torch.cdist(gt.double(), out.double()) ** 2
+    assert torch.allclose(cd_t.double(), ref.min(2)[0].mean(1) + ref.min(1)[0].mean(1), rtol=1e-5)
+    assert cd_p.shape == (3,)
+
+
+def test_emd_module(ops, cuda, cpu):
+    metrics, _ = ops
+    x1, x2 = _data.uniform(2, 1024, 3), _data.uniform(2, 1024, 4)
+    a = T(x1, cuda, True)
+    dist, asg = metrics.emd()(a, T(x2, cuda), 0.005, 50)
+    assert dist.shape == (2, 1024) and asg.dtype == torch.int32 and not asg.requires_grad
+    torch.sqrt(dist).mean(1).sum().backward()                       # calc_emd, model_utils.py:80-85
+    od, oa = cpu.emd_forward(x1, x2, 0.005, 50)
+    _cases.eq(asg.cpu().numpy(), oa, "assignment"), _cases.eq(dist.detach().cpu().numpy(), od, "dist")
+    assert torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0
+    with pytest.raises(AssertionError):
+        metrics.emd()(a, torch.rand(2, 2048, 3, device=cuda), 0.005, 5)     # emd_module.py:47
+    with pytest.raises(RuntimeError, match="multiple of 1024"):
+        metrics.emd()(torch.rand(1, 1000, 3, device=cuda), torch.rand(1, 1000, 3, device=cuda), 0.005, 5)
+
+
+def test_sampling_chain_as_in_vrcnet(ops, cuda, cpu):
+    """FPS -> gather -> group -> three_nn -> three_interpolate, as completion/model_utils.py:88-110,286-293."""
+    _, mm = ops
+    B, N, C, S = 4, 1536, 64, 768
+    xyz = T(_data.uniform(B, N, 5), cuda)
+    feat = torch.randn(B, C, N, device=cuda, requires_grad=True)
+    p_idx = mm.furthest_point_sample(xyz, S)
+    assert p_idx.dtype == torch.int32 and p_idx.shape == (B, S) and not p_idx.requires_grad
+    _cases.eq(p_idx.cpu().numpy(), cpu.fps(xyz.cpu().numpy(), S), "fps")
+    pts = mm.gather_points(xyz.transpose(1, 2).contiguous(), p_idx).transpose(1, 2).contiguous()
+    assert torch.equal(pts, torch.gather(xyz, 1, p_idx.long()[..., None].expand(-1, -1, 3)))
+    center = mm.grouping_operation(feat, p_idx.unsqueeze(2).contiguous()).view(B, -1, S)
+    assert torch.equal(center, torch.gather(feat, 2, p_idx.long()[:, None, :].expand(-1, C, -1)))
+    dist, idx = mm.three_nn(xyz, pts)
+    assert dist.shape == (B, N, 3) and idx.dtype == torch.int32
+    d2, i2 = cpu.three_nn(xyz.cpu().numpy(), pts.cpu().numpy())
+    _cases.eq(idx.cpu().numpy(), i2, "three_nn idx")
+    np.testing.assert_array_max_ulp(dist.cpu().numpy(), np.sqrt(d2), maxulp=1)
+    dist = torch.max(dist, torch.ones(1, device=cuda) * 1e-10)
+    w = (1.0 / dist) / torch.sum(1.0 / dist, 2, keepdim=True)
+    up = mm.three_interpolate(center.contiguous(), idx, w.contiguous())
+    assert up.shape == (B, C, N)
+    up.square().sum().backward()
+    assert feat.grad is not None and torch.isfinite(feat.grad).all() and feat.grad.abs().sum() > 0
+
+
+def test_ball_query_group_knn_modules(ops, cuda, cpu):
+    _, mm = ops
+    xyz = T(_data.uniform(2, 1024, 6), cuda)
+    new_xyz = xyz[:, :51].contiguous()
+    idx = mm.ball_query(0, 0.0774596669, 6, xyz, new_xyz)           # model_utils.py:211
+    _cases.eq(idx.cpu().numpy(), cpu.ball_query(0, 0.0774596669, 6, xyz.cpu().numpy(), new_xyz.cpu().numpy()), "bq")
+    grouped = mm.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+    assert grouped.shape == (2, 3, 51, 6)
+    k_idx = mm.knn(8, xyz, new_xyz, False)
+    assert k_idx.shape == (2, 8, 51)
+    oi, _ = cpu.knn(8, xyz.cpu().numpy(), new_xyz.cpu().numpy())
+    _cases.eq(k_idx.cpu().numpy(), oi.transpose(0, 2, 1), "knn")
+    assert torch.equal(mm.knn(8, xyz.transpose(1, 2).contiguous(), new_xyz.transpose(1, 2).contiguous(), True), k_idx)
+    feats = torch.randn(2, 5, 1024, device=cuda)
+    out = mm.QueryAndGroup(0.1, 16)(xyz, new_xyz, feats)
+    assert out.shape == (2, 8, 51, 16)
+    out = mm.QueryAndGroup(None, 4, return_grouped_xyz=True)(xyz, new_xyz, feats)
+    assert out[0].shape == (2, 8, 51, 4) and out[1].shape == (2, 3, 51, 4)
+    s = mm.Points_Sampler([16, 16], ['D-FPS', 'F-FPS'], [512, -1])(xyz, feats)
+    assert s.shape == (2, 32) and s[:, :16].max() < 512 and s[:, 16:].min() >= 512
+    d = mm.furthest_point_sample_with_dist(torch.cdist(xyz[:, :200], xyz[:, :200]).contiguous(), 20)
+    assert d.shape == (2, 20) and (d[:, 0] == 0).all()
+
+
+def test_ops_follow_the_current_stream(ops, cuda):
+    metrics, _ = ops
+    s = torch.cuda.Stream(device=cuda)
+    a, c = torch.rand(8, 2048, 3, device=cuda), torch.rand(8, 2048, 3, device=cuda)
+    torch.cuda.synchronize()
+    want = metrics.cd()(a, c)[0].clone()
+    with torch.cuda.stream(s):
+        got = metrics.cd()(a, c)[0]
+    s.synchronize()
+    assert torch.equal(got, want)

@@ -1,0 +1,70 @@
+"""CPU-only: pins the oracle (oracle/oracle.c) to
+  (1) the reference's own pure-torch Chamfer, with the reference's own assertions
+      (utils/metrics/CD/unit_test.py:22-33: summed mean-squared error < 1e-8, indices identical);
+  (2) outputs of the reference's CUDA kernels recompiled for sm_100a and run on a B200
+      (tests/golden/ref_cuda_golden.npz, made by tests/golden/make_golden_gpu.py) — every op.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _cases
+from _impls import OracleImpl
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PY_GOLD = os.path.join(HERE, "golden", "chamfer_python_ref.npz")
+CUDA_GOLD = os.path.join(HERE, "golden", "ref_cuda_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def impl():
+    return OracleImpl()
+
+
+@pytest.mark.parametrize("case", ["unit", "unit1", "c1"])
+def test_oracle_chamfer_vs_reference_python(impl, case):
+    G = np.load(PY_GOLD)
+    d1, d2, i1, i2 = impl.chamfer_forward(G[case + "_xyz1"], G[case + "_xyz2"])
+    err = ((d1 - G[case + "_dist1"]) ** 2).mean() + ((d2 - G[case + "_dist2"]) ** 2).mean()
+    assert err < 1e-8                                   # unit_test.py:23-27
+    assert (i1 == G[case + "_idx1"]).all() and (i2 == G[case + "_idx2"]).all()  # unit_test.py:29-33
+
+
+def _cuda_cases():
+    if not os.path.isfile(CUDA_GOLD):
+        return []
+    return [nm for nm, _ in _cases.all_cases(np.load(CUDA_GOLD))]
+
+
+@pytest.mark.skipif(not os.path.isfile(CUDA_GOLD), reason="ref_cuda_golden.npz not generated yet")
+@pytest.mark.parametrize("case", _cuda_cases())
+def test_oracle_vs_reference_cuda_golden(impl, case):
+    G = dict(np.load(CUDA_GOLD))
+    fn = dict(_cases.all_cases(G))[case]
+    fn(impl, _cases.group(G, case), case)
+
+
+def test_oracle_fps_block_size_rule():
+    import oracle
+    # furthest_point_sample_cuda.cu:11-15 — largest power of two <= n, capped at 1024
+    for n, t in [(1, 1), (2, 2), (3, 2), (100, 64), (384, 256), (768, 512), (1024, 1024), (1536, 1024), (16384, 1024)]:
+        assert oracle.fps_block_size(n) == t
+
+
+def test_oracle_emd_rejects_bad_sizes():
+    import oracle
+    x = np.zeros((1, 1000, 3), np.float32)
+    with pytest.raises(ValueError):
+        oracle.emd_forward(x, x, 0.005, 5)     # n % 1024 != 0, emd_cuda.cu:246-249
+
+
+def test_oracle_emd_invariants():
+    import oracle
+    import _data
+    x1, x2 = _data.uniform(2, 1024, 5), _data.uniform(2, 1024, 6)
+    d, a = oracle.emd_forward(x1, x2, 0.005, 50)
+    _cases.emd_consistent(x1, x2, d, a)
+    assert len(np.unique(a[0])) > 900          # near-bijection after 50 rounds (emd_module.py:99)
+    d3k, a3k = oracle.emd_forward(x1, x2, 0.002, 3000)
+    assert len(np.unique(a3k[0])) >= len(np.unique(a[0]))
