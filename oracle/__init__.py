@@ -37,6 +37,7 @@ def lib():
         build()
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.oracle_emd_forward.restype = ctypes.c_int
+        _lib.oracle_emd_forward_state.restype = ctypes.c_int
         _lib.oracle_knn.restype = ctypes.c_int
         _lib.oracle_fps_block_size.restype = ctypes.c_int
         _lib.oracle_num_threads.restype = ctypes.c_int
@@ -106,6 +107,38 @@ def emd_forward(xyz1, xyz2, eps, iters, return_price=False):
     if rc != 0:
         raise ValueError("oracle_emd_forward: invalid input (b<=512, n%1024==0 required)")
     return (dist, asg, price) if return_price else (dist, asg)
+
+
+def emd_last_ambiguous():
+    """Number of GetMax windows (target, round) that held two or more bidders during the last
+    emd_forward / emd_forward_state call: on such inputs the reference's result is a last-writer race
+    (emd_cuda.cu:188-191) and no deterministic implementation can be required to reproduce it."""
+    lib().oracle_emd_last_ambiguous.restype = ctypes.c_longlong
+    return int(lib().oracle_emd_last_ambiguous())
+
+
+def emd_set_tie_policy(p):
+    """0 = highest source index wins GetMax near-ties (default, = the product), 1 = lowest."""
+    lib().oracle_emd_set_tie_policy(int(p))
+
+
+def emd_forward_state(xyz1, xyz2, eps, iters):
+    """One cloud (n,3): dict of every state array after `iters` rounds (debug aid for the GetMax race)."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    n = xyz1.shape[0]
+    f = lambda: np.empty(n, np.float32)  # noqa: E731
+    i = lambda: np.empty(n, np.int32)  # noqa: E731
+    last_unass = i()
+    st = dict(dist=f(), assignment=i(), price=f(), assignment_inv=i(), bid=i(), bid_increments=f(),
+              max_increments=f(), max_idx=i())
+    rc = lib().oracle_emd_forward_state(n, _fp(xyz1), _fp(xyz2), ctypes.c_float(eps), int(iters), _fp(st["dist"]),
+                                        _ip(st["assignment"]), _fp(st["price"]), _ip(st["assignment_inv"]),
+                                        _ip(st["bid"]), _fp(st["bid_increments"]), _fp(st["max_increments"]),
+                                        _ip(st["max_idx"]), _ip(last_unass))
+    if rc < 0:
+        raise ValueError("oracle_emd_forward_state: n % 1024 == 0 required")
+    st["last_unassigned"] = last_unass[:rc].copy()
+    return st
 
 
 def emd_backward(xyz1, xyz2, graddist, assignment):

@@ -63,13 +63,13 @@ def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
     m = xyz2.shape[1]
     g1 = torch.zeros_like(xyz1)
     g2 = torch.zeros_like(xyz2)
-    lib().ref_chamfer_backward(b, n, m, _p(xyz1), _p(xyz2), _p(g1), _p(g2), _p(graddist1.contiguous()),
-                               _p(graddist2.contiguous()), _p(idx1), _p(idx2))
+    gd1, gd2 = graddist1.contiguous(), graddist2.contiguous()
+    lib().ref_chamfer_backward(b, n, m, _p(xyz1), _p(xyz2), _p(g1), _p(g2), _p(gd1), _p(gd2), _p(idx1), _p(idx2))
     return g1, g2
 
 
-def emd_forward(xyz1, xyz2, eps, iters):
-    """emd_module.py:42-70 -> (dist, assignment)."""
+def emd_forward(xyz1, xyz2, eps, iters, return_state=False):
+    """emd_module.py:42-70 -> (dist, assignment) [or the dict of all state tensors]."""
     b, n, _ = xyz1.shape
     dev = xyz1.device
     i32 = dict(device=dev, dtype=torch.int32)
@@ -88,6 +88,9 @@ def emd_forward(xyz1, xyz2, eps, iters):
     lib().ref_emd_forward(b, n, _p(xyz1), _p(xyz2), _p(dist), _p(assignment), _p(price), _p(assignment_inv),
                           _p(bid), _p(bid_increments), _p(max_increments), _p(unass_idx), _p(unass_cnt),
                           _p(unass_cnt_sum), _p(cnt_tmp), _p(max_idx), _f(eps), int(iters))
+    if return_state:
+        return dict(dist=dist, assignment=assignment, price=price, assignment_inv=assignment_inv, bid=bid,
+                    bid_increments=bid_increments, max_increments=max_increments, max_idx=max_idx.view(b, n))
     return dist, assignment
 
 
@@ -95,7 +98,8 @@ def emd_backward(xyz1, xyz2, graddist, assignment):
     """emd_module.py:73-81 -> gradxyz1."""
     b, n, _ = xyz1.shape
     g = torch.zeros_like(xyz1)
-    lib().ref_emd_backward(b, n, _p(xyz1), _p(xyz2), _p(g), _p(graddist.contiguous()), _p(assignment))
+    gd = graddist.contiguous()
+    lib().ref_emd_backward(b, n, _p(xyz1), _p(xyz2), _p(g), _p(gd), _p(assignment))
     return g
 
 

@@ -57,17 +57,28 @@ def emd_consistent(x1, x2, dist, asg):
     np.testing.assert_array_max_ulp(dist, ref, maxulp=1)
 
 
+EMD_RACE_RTOL = 1e-2  # mean sqrt(dist) when the reference's own result is a last-writer race (see below)
+
+
 def check_emd(impl, c, name):
+    """Identical assignment and dist whenever the input is race-free for the reference.  The reference's
+    GetMax lets ANY bidder inside a +-1e-6 window of the target's best increment win — the last writer
+    (emd_cuda.cu:188-191).  The oracle counts those windows (`emd_last_ambiguous`); when one occurred, one
+    coin-flip reroutes the rest of the auction (198 of 2048 assignments in golden `emd_2048`, although two
+    reference runs agreed with each other), so only the mean transport cost is compared there."""
+    import oracle
+    oracle.emd_forward(c["xyz1"], c["xyz2"], float(c["eps"]), int(c["iters"]))
+    race_free = oracle.emd_last_ambiguous() == 0
     d, a = impl.emd_forward(c["xyz1"], c["xyz2"], c["eps"], c["iters"])
     emd_consistent(c["xyz1"], c["xyz2"], d, a)
     same = (a == c["assignment"]).all()
-    if bool(c["stable"]):
-        # the reference agreed with itself on this input: require the identical assignment
+    if race_free:
+        assert bool(c["stable"]), f"{name}: race-free input but the reference disagreed with itself"
         assert same, f"{name}: assignment differs from the reference in {(a != c['assignment']).sum()} places"
         eq(d, c["dist"], f"{name} dist")
     elif not same:
         m, r = np.sqrt(d).mean(), np.sqrt(c["dist"]).mean()
-        assert abs(m - r) <= 1e-3 * r, f"{name}: mean sqrt(dist) {m} vs reference {r} (reference unstable here)"
+        assert abs(m - r) <= EMD_RACE_RTOL * r, f"{name}: mean sqrt(dist) {m} vs reference {r} (reference races here)"
     gx = impl.emd_backward(c["xyz1"], c["xyz2"], c["graddist"], c["assignment"])
     close(gx, c["gradxyz1"], f"{name} gradxyz1")
 

@@ -116,8 +116,9 @@ class CudaImpl:
         b, n, _ = a.shape
         m = c.shape[1]
         gx1, gx2 = self.E((b, n, 3), t.float32), self.E((b, m, 3), t.float32)
-        L.check(L.lib.mvp_chamfer_backward(b, n, m, p(a), p(c), p(self.T(g1)), p(self.T(g2)), p(self.T(i1)),
-                                           p(self.T(i2)), p(gx1), p(gx2), self.S()), "mvp_chamfer_backward")
+        tg1, tg2, ti1, ti2 = self.T(g1), self.T(g2), self.T(i1), self.T(i2)  # keep alive across the call
+        L.check(L.lib.mvp_chamfer_backward(b, n, m, p(a), p(c), p(tg1), p(tg2), p(ti1), p(ti2), p(gx1), p(gx2),
+                                           self.S()), "mvp_chamfer_backward")
         return self.N(gx1, gx2)
 
     def emd_forward(self, x1, x2, eps, iters):
@@ -136,8 +137,8 @@ class CudaImpl:
         a, c = self.T(x1), self.T(x2)
         b, n, _ = a.shape
         gx = self.E((b, n, 3), t.float32)
-        L.check(L.lib.mvp_emd_backward(b, n, p(a), p(c), p(self.T(g)), p(self.T(asg)), p(gx), self.S()),
-                "mvp_emd_backward")
+        tg, ta = self.T(g), self.T(asg)  # keep alive across the call
+        L.check(L.lib.mvp_emd_backward(b, n, p(a), p(c), p(tg), p(ta), p(gx), self.S()), "mvp_emd_backward")
         return self.N(gx)
 
     def fps(self, xyz, m):
