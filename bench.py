@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Headline benchmark of the point-cloud operator hot path (BASELINE.json: Chamfer point-pairs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extra]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One STEP = one Chamfer-distance forward + backward over one batch of synthetic clouds at the size
+BASELINE.json's north_star quotes: B=32, N=M=16384 fp32 (the CD of config C2 at its full 16384-point
+resolution).  point-pairs = B*N*M per step (each unordered pair counted once although both directions
+are produced).  Multi-GPU: every rank owns its own B=32 clouds (batch sharding, weak
+scaling, no collective on the operator path — SURVEY.md §8e); value = N * pairs / max-over-ranks time.
+
+Numbers on the JSON line:
+  value      device-resident: inputs already in HBM, C-ABI calls (mvp_chamfer_forward/backward) on the
+             current stream, CUDA events around exactly K steps.  Input sets rotate through > L2-size
+             (126 MB) worth of clouds so no step finds its inputs in L2.
+  e2e        the same metric through the reference-facing Python API (metrics.cd() autograd Function)
+             with HOST buffers: per step pinned-host -> device copies of both clouds, forward,
+             backward, and device -> pinned-host copies of dist1/dist2/idx1/idx2/gradxyz1/gradxyz2.
+  roofline   the dominant kernel (Chamfer forward), algorithmic bytes 20*B*(N+M) per forward
+              / its average duration (CUDA events inside the timed region) against the
+             measured HBM copy peak in MEASURED_PEAKS.json.  Brute-force Chamfer is FP32-issue bound,
+             not HBM bound: `roofline_fp32` reports the binding roofline.
+  cpu_baseline  the CPU oracle (oracle/oracle.c, a port of the reference kernels' arithmetic, OpenMP
+             over all host cores) on a bounded sample of the same workload.
+--impl reference: the same metric for the reference's algorithm on the host CPU cores (the oracle
+port; the reference's own kernels are CUDA-only and its Python needs mmcv — DESIGN.md), rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, N, M = 32, 16384, 16384
+L2_BYTES = 126 << 20
+METRIC = "chamfer_fwd_bwd_point_pairs_per_s"
+UNIT = "point-pairs/s"
+WORKLOAD = "chamfer_distance_fwd_bwd B=32 N=M=16384 fp32 uniform[0,1)^3 (PCN/C2 fine-output CD size)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (EMD, FPS, reference CUDA kernels)")
+    ap.add_argument("--batch", type=int, default=B)
+    ap.add_argument("--points", type=int, default=N)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, 20 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _names(self, mask):
+        nv = self.nv
+        table = [("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"), ("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("hw_power_brake", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown"),
+                 ("sync_boost", "nvmlClocksThrottleReasonSyncBoost"),
+                 ("app_clocks", "nvmlClocksThrottleReasonApplicationsClocksSetting")]
+        return [n for n, a in table if hasattr(nv, a) and (mask & getattr(nv, a))]
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons.update(self._names(int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_chamfer_sample(budget_s, b=B, n=N, m=M, seed=0):
+    """Times the oracle port on a bounded sample: whole clouds when they fit the budget, else the first
+    `nq` queries of both directions of one cloud.  Returns (pairs_per_s, cores, description, seconds)."""
+    import numpy as np
+    import oracle
+    cores = oracle.num_threads()
+    rng = np.random.default_rng(seed)
+    x1 = rng.random((n, 3), dtype=np.float32)
+    x2 = rng.random((m, 3), dtype=np.float32)
+    g1, g2 = rng.random(n, dtype=np.float32), rng.random(m, dtype=np.float32)
+    probe = max(64, min(n, 512))
+    oracle.chamfer_sample(x1, x2, g1, g2, 64)  # thread-pool warm-up
+    t0 = time.perf_counter()
+    oracle.chamfer_sample(x1, x2, g1, g2, probe)
+    per_query = (time.perf_counter() - t0) / probe
+    nq = int(max(64, min(budget_s / max(per_query, 1e-9), float(max(n, m)) * b)))
+    clouds, rem = divmod(nq, max(n, m))
+    plan = [max(n, m)] * min(clouds, b) + ([rem] if clouds < b and rem else [])
+    pairs = 0.0
+    t0 = time.perf_counter()
+    for q in plan:
+        q1, q2 = min(q, n), min(q, m)
+        oracle.chamfer_sample(x1, x2, g1, g2, q)
+        pairs += 0.5 * (q1 * m + q2 * n)  # each unordered pair counted once, as in B*N*M
+    dt = time.perf_counter() - t0
+    desc = (f"oracle/oracle.c chamfer fwd+bwd, {len(plan)} call(s) on one (n={n}, m={m}) cloud pair covering "
+            f"{sum(plan)} queries per direction (= {sum(plan) / max(n, m):.3f} clouds of the B={b} batch)")
+    return pairs / dt, cores, desc, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    budget = min(4.0, 90.0 / (steps + warm))  # the whole run ends within a couple of minutes
+    n = m = args.points
+    for _ in range(warm):
+        cpu_chamfer_sample(budget, args.batch, n, m)
+    tot_pairs, tot_t, cores, desc = 0.0, 0.0, 1, ""
+    for i in range(steps):
+        v, cores, desc, dt = cpu_chamfer_sample(budget, args.batch, n, m, seed=i)
+        tot_pairs += v * dt
+        tot_t += dt
+    value = tot_pairs / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.replace("B=32", f"B={args.batch}").replace("16384", str(n)),
+                   "note": "host CPU only; each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc + " per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from mvp_benchmark_b200 import dist as mdist
+    rank, world, local = mdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the operators have no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import mvp_benchmark_b200
+    mvp_benchmark_b200.install()
+    import metrics
+    from mvp_benchmark_b200 import _lib
+    L, P = _lib.lib, _lib.ptr
+
+    b, n, m = args.batch, args.points, args.points
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    pairs = float(b) * n * m
+    hbm_gbs, peak_src, sm_max = peaks()
+
+    # ---- synthetic inputs: enough rotating sets that the inputs alone exceed L2
+    set_bytes = 12 * b * (n + m)
+    nsets = max(2, -(-int(1.1 * L2_BYTES) // set_bytes))
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    X1 = [torch.rand(b, n, 3, device=dev, generator=g) for _ in range(nsets)]
+    X2 = [torch.rand(b, m, 3, device=dev, generator=g) for _ in range(nsets)]
+    G1 = torch.rand(b, n, device=dev, generator=g)
+    G2 = torch.rand(b, m, device=dev, generator=g)
+    d1 = torch.empty(b, n, device=dev)
+    d2 = torch.empty(b, m, device=dev)
+    i1 = torch.empty(b, n, device=dev, dtype=torch.int32)
+    i2 = torch.empty(b, m, device=dev, dtype=torch.int32)
+    gx = torch.empty(b * (n + m) * 3, device=dev)
+    gx1, gx2 = gx[:b * n * 3], gx[b * n * 3:]
+    ws = _lib.workspace(L.mvp_chamfer_forward_workspace_bytes(b, n, m), dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step(k):
+        a, c = X1[k % nsets], X2[k % nsets]
+        _lib.check(L.mvp_chamfer_forward(b, n, m, P(a), P(c), P(d1), P(d2), P(i1), P(i2), P(ws), ws.numel(), stream),
+                   "mvp_chamfer_forward")
+        return a, c
+
+    def step_bwd(a, c):
+        _lib.check(L.mvp_chamfer_backward(b, n, m, P(a), P(c), P(G1), P(G2), P(i1), P(i2), P(gx1), P(gx2), stream),
+                   "mvp_chamfer_backward")
+
+    for k in range(warm):
+        step_bwd(*step(k))
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly `steps` steps, CUDA events on the launching stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    mdist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        t_wall = time.perf_counter()
+        for k in range(steps):
+            ev[k][0].record()
+            a, c = step(warm + k)
+            ev[k][1].record()
+            step_bwd(a, c)
+            ev[k][2].record()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count() - launches0
+    mdist.barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    total_ms = mdist.max_over_ranks(total_ms, dev)
+    ms_per_step = total_ms / steps
+    value = world * pairs / (ms_per_step * 1e-3)
+
+    # ---- e2e: reference-facing Python API, host buffers in, host buffers out
+    cd = metrics.cd()
+    h1 = [x.cpu().pin_memory() for x in X1[:2]]
+    h2 = [x.cpu().pin_memory() for x in X2[:2]]
+    out_host = {k: torch.empty(s, dtype=t).pin_memory() for k, s, t in
+                [("d1", (b, n), torch.float32), ("d2", (b, m), torch.float32), ("i1", (b, n), torch.int32),
+                 ("i2", (b, m), torch.int32), ("g1", (b, n, 3), torch.float32), ("g2", (b, m, 3), torch.float32)]}
+    h2d = sum(t.numel() * t.element_size() for t in (h1[0], h2[0]))
+    d2h = sum(t.numel() * t.element_size() for t in out_host.values())
+
+    def e2e_step(k):
+        a = h1[k % 2].to(dev, non_blocking=True).requires_grad_(True)
+        c = h2[k % 2].to(dev, non_blocking=True).requires_grad_(True)
+        o1, o2, j1, j2 = cd(a, c)
+        torch.autograd.backward([o1, o2], [G1, G2])
+        out_host["d1"].copy_(o1.detach(), non_blocking=True)
+        out_host["d2"].copy_(o2.detach(), non_blocking=True)
+        out_host["i1"].copy_(j1, non_blocking=True)
+        out_host["i2"].copy_(j2, non_blocking=True)
+        out_host["g1"].copy_(a.grad, non_blocking=True)
+        out_host["g2"].copy_(c.grad, non_blocking=True)
+
+    for k in range(warm):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    mdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(steps):
+        e2e_step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    mdist.barrier()
+    e2e_ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    e2e_value = world * pairs / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (Chamfer forward)
+    fwd_bytes = 20.0 * b * (n + m)
+    achieved = fwd_bytes / (fwd_ms * 1e-3) / 1e9
+    clocks = clk.summary()
+    f_mhz = clocks.get("sm_mhz") or sm_max
+    # FP32 issue roofline: a brute-force pair costs >= 3.5 issue slots with packed fp32x2 math
+    # (3 sub + 1 mul + 2 fma per TWO pairs, + 1 min per pair) on 148 SMs x 4 schedulers x 32 lanes.
+    lanes_per_s = 148 * 128 * f_mhz * 1e6
+    fp32 = {"bound": "fp32_issue", "unit": "pair-evaluations/s", "achieved": pairs / (fwd_ms * 1e-3),
+            "peak": lanes_per_s / 3.5, "peak_model": "148 SM x 128 lanes x sampled SM clock / 3.5 issue slots per pair "
+            "(packed f32x2 sub/mul/fma + one min per pair; each pair evaluated once for both directions)",
+            "sm_mhz_used": f_mhz}
+    fp32["frac"] = fp32["achieved"] / fp32["peak"]
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.replace("B=32", f"B={b}").replace("16384", str(n)), "per_gpu_batch": b,
+                   "global_batch": b * world, "n": n, "m": m, "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2": f"inputs rotate through {nsets} sets = {nsets * set_bytes >> 20} MiB > 126 MiB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "api": "metrics.cd()(xyz1, xyz2) + autograd backward, pinned host in/out"},
+        "gpu_launches": int(launches),
+        "kernel_ms": {"chamfer_forward": fwd_ms, "chamfer_backward": bwd_ms, "wall_ms_per_step": 1e3 * t_wall / steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": None, "kernel": "chamfer forward (both directions)", "algorithmic_bytes": fwd_bytes,
+                     "peak_source": peak_src,
+                     "note": "brute-force Chamfer is FP32-issue bound (2200 instr/byte); see roofline_fp32"},
+        "roofline_fp32": fp32,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1:
+        v, cores, desc, dt = cpu_chamfer_sample(15.0, b, n, m)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                "seconds": dt}
+        if not args.no_extra:
+            try:
+                import bench_extra
+                line["extra"] = bench_extra.run(dev)
+            except Exception as e:  # secondary numbers must never lose the headline line
+                line["extra"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

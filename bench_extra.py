@@ -1,0 +1,141 @@
+"""Secondary measurements printed inside bench.py's JSON line under "extra" (N=1 only): the other
+operators of the hot path at the sizes the reference's models use them, each next to
+the REFERENCE's own CUDA kernel recompiled for sm_100a (oracle/_ref/libref_ops.so — a checker/baseline,
+never on the product path).  CUDA events, 3 warm-up + `iters` timed calls, median.
+"""
+import torch
+
+
+def _time(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def run(dev, hbm_gbs=None):
+    import json
+    import os
+
+    import mvp_benchmark_b200
+    mvp_benchmark_b200.install()
+    import metrics
+    import mm3d_pn2 as mm
+    from oracle import ref_cuda
+    have_ref = ref_cuda.available()
+    if hbm_gbs is None:
+        try:
+            hbm_gbs = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            hbm_gbs = 6650.0
+    out = {"hbm_peak_gbs": hbm_gbs, "reference_cuda_available": have_ref}
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    R = lambda *s: torch.rand(*s, device=dev, generator=g)  # noqa: E731
+
+    def entry(name, ours_ms, ref_ms, unit_count, unit, alg_bytes=None):
+        e = {"ours_ms": ours_ms, "ours_per_s": unit_count / (ours_ms * 1e-3), "unit": unit}
+        if ref_ms is not None:
+            e["ref_cuda_ms"] = ref_ms
+            e["speedup_vs_ref_cuda"] = ref_ms / ours_ms
+        if alg_bytes is not None:
+            e["algorithmic_GBps"] = alg_bytes / (ours_ms * 1e-3) / 1e9
+            e["hbm_frac"] = e["algorithmic_GBps"] / hbm_gbs
+        out[name] = e
+
+    # ---- Chamfer at the headline size, reference CUDA kernels for comparison (fwd+bwd)
+    b, n = 32, 16384
+    x1, x2, g1, g2 = R(b, n, 3), R(b, n, 3), R(b, n), R(b, n)
+    cd = metrics.cd()
+
+    def ours_cd():
+        a, c = x1.detach().requires_grad_(True), x2.detach().requires_grad_(True)
+        o1, o2, _, _ = cd(a, c)
+        torch.autograd.backward([o1, o2], [g1, g2])
+
+    def ref_cd():
+        o1, o2, j1, j2 = ref_cuda.chamfer_forward(x1, x2)
+        ref_cuda.chamfer_backward(x1, x2, g1, g2, j1, j2)
+
+    entry("chamfer_fwd_bwd_32x16384x16384", _time(ours_cd, 5), _time(ref_cd, 5) if have_ref else None,
+          float(b) * n * n, "point-pairs/s", 52.0 * b * 2 * n)
+
+    # ---- Chamfer at the VRCNet sizes (B=64: 2048 x {1024, 3072, 2048, 2048}, vrcnet.py:509-512)
+    gt = R(64, 2048, 3)
+    outs = [R(64, k, 3) for k in (1024, 3072, 2048, 2048)]
+    gs = [(R(64, 2048), R(64, k)) for k in (1024, 3072, 2048, 2048)]
+
+    def ours_cd4():
+        for o, (ga, gb) in zip(outs, gs):
+            a, c = gt.detach().requires_grad_(True), o.detach().requires_grad_(True)
+            p, q, _, _ = cd(a, c)
+            torch.autograd.backward([p, q], [ga, gb])
+
+    def ref_cd4():
+        for o, (ga, gb) in zip(outs, gs):
+            p, q, j1, j2 = ref_cuda.chamfer_forward(gt, o)
+            ref_cuda.chamfer_backward(gt, o, ga, gb, j1, j2)
+
+    entry("chamfer_fwd_bwd_vrcnet_4calls_B64", _time(ours_cd4), _time(ref_cd4) if have_ref else None,
+          64.0 * 2048 * (1024 + 3072 + 2048 + 2048), "point-pairs/s")
+
+    # ---- EMD, config C5: B=64, n=8192, eps 0.005, 50 rounds (forward; the backward is a trivial gather)
+    e1, e2 = R(64, 8192, 3), R(64, 8192, 3)
+    emd = metrics.emd()
+    entry("emd_forward_64x8192_iters50", _time(lambda: emd(e1, e2, 0.005, 50), 3, 1),
+          _time(lambda: ref_cuda.emd_forward(e1, e2, 0.005, 50), 3, 1) if have_ref else None,
+          64.0 * 8192 * 8192, "point-pairs/s", 32.0 * 64 * 8192)
+    e1s, e2s = R(32, 2048, 3), R(32, 2048, 3)
+    entry("emd_forward_32x2048_iters50", _time(lambda: emd(e1s, e2s, 0.005, 50), 5, 2),
+          _time(lambda: ref_cuda.emd_forward(e1s, e2s, 0.005, 50), 5, 2) if have_ref else None,
+          32.0 * 2048 * 2048, "point-pairs/s", 32.0 * 32 * 2048)
+
+    # ---- FPS at the VRCNet sizes
+    for (bb, nn, mm_) in [(32, 2048, 2048), (64, 3072, 2048), (64, 3072, 1536), (64, 1536, 768), (64, 768, 384)]:
+        x = R(bb, nn, 3)
+        entry(f"fps_{bb}x{nn}to{mm_}", _time(lambda: mm.furthest_point_sample(x, mm_), 5),
+              _time(lambda: ref_cuda.furthest_point_sample(x, mm_), 5) if have_ref else None,
+              float(bb) * mm_, "selected points/s", 12.0 * bb * nn + 4.0 * bb * mm_)
+
+    # ---- bandwidth ops
+    bb, c, nn, mp = 64, 64, 3072, 15360
+    feat = torch.randn(bb, c, nn, device=dev, generator=g)
+    idx = torch.randint(0, nn, (bb, mp), device=dev, generator=g, dtype=torch.int32)
+    entry("gather_points_64x64x3072_to_15360", _time(lambda: mm.gather_points(feat, idx)),
+          _time(lambda: ref_cuda.gather_points(feat, idx)) if have_ref else None,
+          float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1))
+    go = torch.randn(bb, c, mp, device=dev, generator=g)
+    from mvp_benchmark_b200 import _lib
+    gp = torch.empty(bb, c, nn, device=dev)
+
+    def ours_gg():
+        _lib.check(_lib.lib.mvp_gather_points_grad(bb, c, nn, mp, _lib.ptr(go), _lib.ptr(idx), _lib.ptr(gp),
+                                                   _lib.stream_of(go)), "gather grad")
+
+    entry("gather_points_grad_64x64x3072_from_15360", _time(ours_gg),
+          _time(lambda: ref_cuda.gather_points_grad(go, idx, nn)) if have_ref else None,
+          float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1) + 4.0 * bb * c * nn)
+    u, k = R(64, 3072, 3), R(64, 1536, 3)
+    entry("three_nn_64x3072_from_1536", _time(lambda: mm.three_nn(u, k)),
+          _time(lambda: ref_cuda.three_nn(u, k)) if have_ref else None, 64.0 * 3072 * 1536, "point-pairs/s",
+          12.0 * 64 * (3072 + 1536) + 24.0 * 64 * 3072)
+    f = torch.randn(64, 128, 1536, device=dev, generator=g)
+    i3 = torch.randint(0, 1536, (64, 3072, 3), device=dev, generator=g, dtype=torch.int32)
+    w = R(64, 3072, 3)
+    entry("three_interpolate_64x128x1536_to_3072", _time(lambda: mm.three_interpolate(f, i3, w)),
+          _time(lambda: ref_cuda.three_interpolate(f, i3, w)) if have_ref else None, 64.0 * 128 * 3072, "elements/s",
+          4.0 * 64 * 3072 * (2 * 128 + 6))
+    xyz, ctr = R(32, 2048, 3), R(32, 102, 3)
+    entry("ball_query_32x2048_102centres_ns12", _time(lambda: mm.ball_query(0, 0.0774596669, 12, xyz, ctr)),
+          _time(lambda: ref_cuda.ball_query(0, 0.0774596669, 12, xyz, ctr)) if have_ref else None, 32.0 * 102,
+          "centres/s", 12.0 * 32 * (2048 + 102) + 4.0 * 32 * 102 * 12)
+    return out

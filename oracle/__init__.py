@@ -94,6 +94,25 @@ def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
     return gx1, gx2
 
 
+def chamfer_sample(xyz1, xyz2, graddist1, graddist2, nq):
+    """Bounded CPU sample of one Chamfer forward+backward for ONE cloud pair (n,3)/(m,3): both directions
+    for the first `nq` queries of each cloud against the whole other cloud (chamfer3D.cu:12-134), then the
+    backward scatter of those queries (:155-174).  Pair evaluations = nq*m + nq*n.  Returns
+    (dist1[:nq], idx1[:nq], dist2[:nq], idx2[:nq], gradxyz1, gradxyz2)."""
+    xyz1, xyz2, g1, g2 = _f32(xyz1), _f32(xyz2), _f32(graddist1), _f32(graddist2)
+    n, m = xyz1.shape[0], xyz2.shape[0]
+    q1, q2 = min(nq, n), min(nq, m)
+    d1, i1 = np.empty(q1, np.float32), np.empty(q1, np.int32)
+    d2, i2 = np.empty(q2, np.float32), np.empty(q2, np.int32)
+    L = lib()
+    L.oracle_nm_distance(q1, _fp(xyz1), m, _fp(xyz2), _fp(d1), _ip(i1))
+    L.oracle_nm_distance(q2, _fp(xyz2), n, _fp(xyz1), _fp(d2), _ip(i2))
+    gx1, gx2 = np.zeros((n, 3), np.float32), np.zeros((m, 3), np.float32)
+    L.oracle_nm_distance_grad(q1, _fp(xyz1), m, _fp(xyz2), _fp(g1), _ip(i1), _fp(gx1), _fp(gx2))
+    L.oracle_nm_distance_grad(q2, _fp(xyz2), n, _fp(xyz1), _fp(g2), _ip(i2), _fp(gx2), _fp(gx1))
+    return d1, i1, d2, i2, gx1, gx2
+
+
 def emd_forward(xyz1, xyz2, eps, iters, return_price=False):
     """emd_cuda.cu:23-282 -> (dist, assignment[, price])."""
     xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
