@@ -1,12 +1,345 @@
-// Large-cloud Chamfer fast path (placeholder until the fused kernel lands): reports "unsupported" so
-// mvp_chamfer_forward uses the generic one-direction kernel of chamfer.cu.
+// Chamfer distance, large-cloud path for sm_100a: BOTH directions from ONE evaluation of each pair.
+//
+// Replaces the two NmDistanceKernel launches of the reference (utils/metrics/CD/chamfer3D/chamfer3D.cu:12-134,
+// 142-143), which evaluate every pair twice (once per direction).  The squared distance
+//     d(i,j) = fma(dz,dz, fma(dx,dx, dy*dy)),  dx = xyz2[j].x - xyz1[i].x ...
+// is bit-identical for the swapped direction (only the signs of dx,dy,dz flip, chamfer3D.cu:32-35), so one
+// evaluation serves dist1/idx1 (row minima) and dist2/idx2 (column minima).
+//
+// Pass 1  chamfer_pair_kernel — a CTA owns a tile of TM = 256*WARPS rows (points of xyz1, 8 per thread, held in
+//   registers as duplicated fp32x2 pairs) and sweeps column tiles of 1024 points of xyz2 staged in shared memory
+//   (1-D bulk TMA of the raw xyz rows into a double buffer, then re-laid as x/y/z quads so that four columns are
+//   three broadcast LDS.128).  Distances are computed two columns at a time with packed FADD2/FMUL2/FFMA2
+//   (3 issue slots per pair instead of 6); minima are tracked as VALUES only, with three-input FMNMX3:
+//     rows:    running minimum per row; per 256-column chunk a compare records WHICH CHUNK improved it;
+//     columns: per-thread minimum over its 8 rows, one redux.sync.min.u32 per column across the warp
+//              (d >= +0, so the fp32 bit pattern orders like an unsigned integer), parked per warp in shared
+//              memory, merged over the CTA's warps at the end of the tile.
+//   Partial results meet in global memory as 64-bit keys  (bits(d) << 32) | block  through atomicMin: `block` is
+//   the index of the 256-wide chunk of columns (for a row) or of rows (for a column) that produced the minimum,
+//   so equal distances resolve to the LOWEST block — the reference's lowest-index tie rule at block granularity.
+// Pass 2  chamfer_resolve_kernel — one warp per point re-evaluates the 256 candidates of its winning block and
+//   takes the first one whose distance has exactly the winning bit pattern: the lowest index among equal minima,
+//   as the reference's strict `<` scan gives (chamfer3D.cu:36,126).  Costs 256/N of pass 1.
 #include "common.cuh"
 
 namespace mvp {
-bool chamfer_fused_supported(int, int, int) { return false; }
-size_t chamfer_fused_workspace_bytes(int, int, int) { return 16; }
-int chamfer_fused_launch(int, int, int, const float *, const float *, float *, float *, int *, int *,
-                         void *, size_t, cudaStream_t) {
-  return MVP_ERR_INVALID_ARGUMENT;
+
+typedef unsigned long long u64;
+
+constexpr int kBlk = 256;      // granularity of the "which block won" half of a key (rows and columns alike)
+constexpr int kRows = 8;       // rows per thread
+constexpr int kTN = 1024;      // columns per shared-memory tile
+constexpr float kPadRow = 2e19f, kPadCol = -2e19f;  // padding coordinates: any distance to them overflows to +inf
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// two columns (packed) against one row (duplicated): the reference's contraction, lane by lane
+__device__ __forceinline__ u64 dist2(u64 X, u64 Y, u64 Z, u64 qx, u64 qy, u64 qz) {
+  const u64 dx = sub2(X, qx), dy = sub2(Y, qy), dz = sub2(Z, qz);
+  return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int WARPS>
+struct PairSmem {
+  float raw[2][kTN * 3];             // TMA landing zone: xyz rows as they lie in global memory (2 x 12 KB)
+  ulonglong2 x[kTN / 4], y[kTN / 4], z[kTN / 4];  // the tile as quads: (x0,x1 | x2,x3) ...          (12 KB)
+  uint32_t wmin[WARPS][kTN];           // per-warp column minima of the current tile                   (32 KB)
+  uint64_t bar[2];
+};
+
+// grid: x = row tile, y = column split, z = cloud.  WARPS warps per CTA, TM = 256 * WARPS rows per tile.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS >= 8 ? 2 : 4)
+chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *__restrict__ xyz1,
+                    const float *__restrict__ xyz2, u64 *__restrict__ rowkey, u64 *__restrict__ colkey) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PairSmem<WARPS> &S = *reinterpret_cast<PairSmem<WARPS> *>(smem_raw);
+  constexpr int T = WARPS * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const float *A = xyz1 + (size_t)b * n * 3;
+  const float *Bc = xyz2 + (size_t)b * m * 3;
+  const int row0 = blockIdx.x * (WARPS * kBlk) + warp * kBlk;  // first row of this warp's 256-row block
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int ntiles_all = (m + kTN - 1) / kTN;
+  const int ntiles = min(tiles_per_cta, ntiles_all - tile0);
+  const float inf = __int_as_float(0x7f800000);
+
+  // ---- this thread's rows, duplicated into fp32x2 operands
+  u64 qx[kRows], qy[kRows], qz[kRows];
+  float best[kRows], prev[kRows];
+  int bchunk[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; r++) {
+    const int i = row0 + lane + 32 * r;
+    float x = kPadRow, y = kPadRow, z = kPadRow;
+    if (i < n) {
+      x = __ldg(A + (size_t)i * 3 + 0);
+      y = __ldg(A + (size_t)i * 3 + 1);
+      z = __ldg(A + (size_t)i * 3 + 2);
+    }
+    qx[r] = pack2(x, x);
+    qy[r] = pack2(y, y);
+    qz[r] = pack2(z, z);
+    best[r] = prev[r] = inf;
+    bchunk[r] = 0;
+  }
+
+  if (use_tma && tid == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_tma = [&](int t) {  // thread 0: fetch column tile t (a FULL tile) into raw[t & 1]
+    const int buf = t & 1;
+    mbar_expect_tx(&S.bar[buf], kTN * 12);
+    tma_load_1d(S.raw[buf], Bc + (size_t)(tile0 + t) * kTN * 3, kTN * 12, &S.bar[buf]);
+  };
+  // A tile goes through TMA when it is full and 16-byte aligned in global memory; else plain loads.
+  auto tile_by_tma = [&](int t) { return use_tma && (tile0 + t + 1) * kTN <= m; };
+  if (ntiles > 0 && tile_by_tma(0) && tid == 0) issue_tma(0);
+
+  for (int t = 0; t < ntiles; t++) {
+    const int col0 = (tile0 + t) * kTN;
+    // ---- stage the tile as x/y/z quads
+    float *sx = reinterpret_cast<float *>(S.x), *sy = reinterpret_cast<float *>(S.y),
+          *sz = reinterpret_cast<float *>(S.z);
+    if (tile_by_tma(t)) {
+      mbar_wait(&S.bar[t & 1], (t >> 1) & 1);
+      const float *raw = S.raw[t & 1];
+      for (int j = tid; j < kTN; j += T) {
+        sx[j] = raw[j * 3 + 0];
+        sy[j] = raw[j * 3 + 1];
+        sz[j] = raw[j * 3 + 2];
+      }
+    } else {
+      for (int j = tid; j < kTN; j += T) {
+        const int c = col0 + j;
+        float x = kPadCol, y = kPadCol, z = kPadCol;
+        if (c < m) {
+          x = __ldg(Bc + (size_t)c * 3 + 0);
+          y = __ldg(Bc + (size_t)c * 3 + 1);
+          z = __ldg(Bc + (size_t)c * 3 + 2);
+        }
+        sx[j] = x;
+        sy[j] = y;
+        sz[j] = z;
+      }
+    }
+    __syncthreads();
+    if (t + 1 < ntiles && tile_by_tma(t + 1) && tid == 0) issue_tma(t + 1);  // overlaps the sweep below
+
+    // ---- sweep: 4 chunks of 256 columns, 4 columns per step
+    const int cols_here = min(kTN, m - col0);
+    const int nchunks = (cols_here + kBlk - 1) / kBlk;
+    for (int c = 0; c < nchunks; c++) {
+#pragma unroll 1
+      for (int g = c * (kBlk / 4); g < (c + 1) * (kBlk / 4); g++) {
+        const ulonglong2 X = S.x[g], Y = S.y[g], Z = S.z[g];
+        float cm0 = inf, cm1 = inf, cm2 = inf, cm3 = inf;
+#pragma unroll
+        for (int r = 0; r < kRows; r += 2) {
+          const u64 a0 = dist2(X.x, Y.x, Z.x, qx[r], qy[r], qz[r]);
+          const u64 b0 = dist2(X.y, Y.y, Z.y, qx[r], qy[r], qz[r]);
+          const u64 a1 = dist2(X.x, Y.x, Z.x, qx[r + 1], qy[r + 1], qz[r + 1]);
+          const u64 b1 = dist2(X.y, Y.y, Z.y, qx[r + 1], qy[r + 1], qz[r + 1]);
+          float a0l, a0h, b0l, b0h, a1l, a1h, b1l, b1h;
+          unpack2(a0, a0l, a0h);
+          unpack2(b0, b0l, b0h);
+          unpack2(a1, a1l, a1h);
+          unpack2(b1, b1l, b1h);
+          best[r] = min3(min3(best[r], a0l, a0h), b0l, b0h);
+          best[r + 1] = min3(min3(best[r + 1], a1l, a1h), b1l, b1h);
+          cm0 = min3(cm0, a0l, a1l);
+          cm1 = min3(cm1, a0h, a1h);
+          cm2 = min3(cm2, b0l, b1l);
+          cm3 = min3(cm3, b0h, b1h);
+        }
+        uint4 w;
+        w.x = redux_min_u32(__float_as_uint(cm0));
+        w.y = redux_min_u32(__float_as_uint(cm1));
+        w.z = redux_min_u32(__float_as_uint(cm2));
+        w.w = redux_min_u32(__float_as_uint(cm3));
+        if (lane == 0) *reinterpret_cast<uint4 *>(&S.wmin[warp][g * 4]) = w;
+      }
+      const int chunk = (col0 >> 8) + c;
+#pragma unroll
+      for (int r = 0; r < kRows; r++) {
+        if (best[r] < prev[r]) {
+          prev[r] = best[r];
+          bchunk[r] = chunk;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- column keys of this tile: minimum over the CTA's warps, lowest row block on ties
+    for (int j = tid; j < cols_here; j += T) {
+      u64 k = ~0ull;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) {
+        const u64 cand = ((u64)S.wmin[w][j] << 32) | (unsigned)((blockIdx.x * WARPS + w));
+        k = cand < k ? cand : k;
+      }
+      atomicMin(colkey + (size_t)b * m + col0 + j, k);
+    }
+    // (the next iteration's staging writes S.x/y/z, which nobody reads any more; S.wmin is rewritten only
+    //  after the __syncthreads that follows the staging)
+  }
+  // ---- row keys
+#pragma unroll
+  for (int r = 0; r < kRows; r++) {
+    const int i = row0 + lane + 32 * r;
+    if (i < n && ntiles > 0)
+      atomicMin(rowkey + (size_t)b * n + i, ((u64)__float_as_uint(best[r]) << 32) | (unsigned)bchunk[r]);
+  }
+}
+
+// One warp per point p of cloud P (np points): key = (bits(d) << 32) | block; scan the 256 points of cloud Q in that
+// block, ascending, for the first whose distance to p has exactly those bits.
+__global__ void __launch_bounds__(256)
+chamfer_resolve_kernel(long long total, int np, int nq, const float *__restrict__ P, const float *__restrict__ Q,
+                       const u64 *__restrict__ key, float *__restrict__ dist, int *__restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= total) return;
+  const long long cloud = wid / np;
+  const u64 k = __ldg(key + wid);
+  const uint32_t bits = (uint32_t)(k >> 32);
+  const int base = (int)(uint32_t)k * kBlk;
+  const float px = __ldg(P + wid * 3 + 0), py = __ldg(P + wid * 3 + 1), pz = __ldg(P + wid * 3 + 2);
+  const float *q = Q + (size_t)cloud * nq * 3;
+  int found = base;
+#pragma unroll 1
+  for (int s = 0; s < kBlk; s += 32) {
+    const int j = base + s + lane;
+    bool hit = false;
+    if (j < nq) {
+      const float d = sqdist(__ldg(q + (size_t)j * 3 + 0) - px, __ldg(q + (size_t)j * 3 + 1) - py,
+                             __ldg(q + (size_t)j * 3 + 2) - pz);
+      hit = __float_as_uint(d) == bits;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      found = base + s + __ffs(mask) - 1;
+      break;
+    }
+  }
+  if (lane == 0) {
+    dist[wid] = __uint_as_float(bits);
+    idx[wid] = found;
+  }
+}
+
+bool chamfer_fused_supported(int b, int n, int m) {
+  // worth it once a cloud pair has enough work to amortise the key round-trip; tiny clouds use chamfer.cu
+  return b > 0 && n >= 512 && m >= 512 && (long long)b <= 65535;
+}
+
+size_t chamfer_fused_workspace_bytes(int b, int n, int m) { return sizeof(u64) * (size_t)b * ((size_t)n + m); }
+
+template <int WARPS>
+static int pair_launch(int b, int n, int m, int split, int tiles_per_cta, int use_tma, const float *xyz1,
+                       const float *xyz2, u64 *rowkey, u64 *colkey, cudaStream_t s) {
+  const size_t smem = sizeof(PairSmem<WARPS>);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid((n + WARPS * kBlk - 1) / (WARPS * kBlk), split, b);
+  chamfer_pair_kernel<WARPS><<<grid, WARPS * 32, smem, s>>>(n, m, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey);
+  count_launch();
+  return launch_status();
+}
+
+int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                         int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
+  u64 *rowkey = reinterpret_cast<u64 *>(ws);
+  u64 *colkey = rowkey + (size_t)b * n;
+  cudaError_t e = cudaMemsetAsync(ws, 0xff, chamfer_fused_workspace_bytes(b, n, m), s);
+  if (e != cudaSuccess) return (int)e;
+
+  // Tile shape: the largest row tile that still yields >= 4 CTAs per SM worth of tiles, then split the column
+  // sweep so that the tail of the last wave is short.
+  const int ntiles = (m + kTN - 1) / kTN;
+  auto ctas = [&](int warps, int split) { return (long long)b * ((n + warps * kBlk - 1) / (warps * kBlk)) * split; };
+  int warps = 8;
+  while (warps > 2 && ctas(warps, ntiles) < 4LL * kNumSMs) warps >>= 1;
+  int tiles_per_cta = ntiles;
+  while (tiles_per_cta > 1 && ctas(warps, (ntiles + tiles_per_cta - 1) / tiles_per_cta) < 12LL * kNumSMs)
+    tiles_per_cta = (tiles_per_cta + 1) / 2;
+  const int split = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
+  // bulk TMA needs 16-byte aligned sources: tiles start at multiples of 1024 points (12 KB), clouds at
+  // multiples of m*12 bytes
+  const int use_tma = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
+  int rc;
+  if (warps == 8) rc = pair_launch<8>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
+  else if (warps == 4) rc = pair_launch<4>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
+  else rc = pair_launch<2>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
+  if (rc) return rc;
+
+  const long long t1 = (long long)b * n, t2 = (long long)b * m;
+  chamfer_resolve_kernel<<<(unsigned)((t1 * 32 + 255) / 256), 256, 0, s>>>(t1, n, m, xyz1, xyz2, rowkey, dist1, idx1);
+  chamfer_resolve_kernel<<<(unsigned)((t2 * 32 + 255) / 256), 256, 0, s>>>(t2, m, n, xyz2, xyz1, colkey, dist2, idx2);
+  count_launch(2);
+  return launch_status();
+}
+
 }  // namespace mvp
