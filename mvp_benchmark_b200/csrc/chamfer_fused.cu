@@ -6,30 +6,46 @@
 // is bit-identical for the swapped direction (only the signs of dx,dy,dz flip, chamfer3D.cu:32-35), so one
 // evaluation serves dist1/idx1 (row minima) and dist2/idx2 (column minima).
 //
-// Pass 1  chamfer_pair_kernel — a CTA owns a tile of TM = 256*WARPS rows (points of xyz1, 8 per thread, held in
+// Pass 1  chamfer_pair_kernel — a CTA owns a tile of TM = kBlk*WARPS rows (points of xyz1, kRows = 4 per thread, held in
 //   registers as duplicated fp32x2 pairs) and sweeps column tiles of 1024 points of xyz2 staged in shared memory
 //   (1-D bulk TMA of the raw xyz rows into a double buffer, then re-laid as x/y/z quads so that four columns are
 //   three broadcast LDS.128).  Distances are computed two columns at a time with packed FADD2/FMUL2/FFMA2
 //   (3 issue slots per pair instead of 6); minima are tracked as VALUES only, with three-input FMNMX3:
-//     rows:    running minimum per row; per 256-column chunk a compare records WHICH CHUNK improved it;
-//     columns: per-thread minimum over its 8 rows, one redux.sync.min.u32 per column across the warp
+//     rows:    running minimum per row; per kBlk-column chunk (kBlk = 32*kRows = 128) a compare records WHICH
+//              CHUNK improved it;
+//     columns: per-thread minimum over its kRows rows, one redux.sync.min.u32 per column across the warp
 //              (d >= +0, so the fp32 bit pattern orders like an unsigned integer), parked per warp in shared
 //              memory, merged over the CTA's warps at the end of the tile.
 //   Partial results meet in global memory as 64-bit keys  (bits(d) << 32) | block  through atomicMin: `block` is
-//   the index of the 256-wide chunk of columns (for a row) or of rows (for a column) that produced the minimum,
+//   the index of the kBlk-wide chunk of columns (for a row) or of rows (for a column) that produced the minimum,
 //   so equal distances resolve to the LOWEST block — the reference's lowest-index tie rule at block granularity.
-// Pass 2  chamfer_resolve_kernel — one warp per point re-evaluates the 256 candidates of its winning block and
+// Pass 2  chamfer_resolve_kernel — one warp per point re-evaluates the kBlk candidates of its winning block and
 //   takes the first one whose distance has exactly the winning bit pattern: the lowest index among equal minima,
-//   as the reference's strict `<` scan gives (chamfer3D.cu:36,126).  Costs 256/N of pass 1.
+//   as the reference's strict `<` scan gives (chamfer3D.cu:36,126).  Costs kBlk/N of pass 1.
 #include "common.cuh"
 
 namespace mvp {
 
 typedef unsigned long long u64;
 
-constexpr int kBlk = 256;      // granularity of the "which block won" half of a key (rows and columns alike)
-constexpr int kRows = 8;       // rows per thread
-constexpr int kTN = 1024;      // columns per shared-memory tile
+// Tuning knobs (tools/pair_variants.py builds the alternatives; the defaults are the measured best).
+#ifndef MVP_PAIR_ROWS
+#define MVP_PAIR_ROWS 4  // rows per thread (4: 72 registers, 3 CTAs/SM — measured best; 8: 126 registers, 2 CTAs/SM)
+#endif
+#ifndef MVP_PAIR_COLS
+#define MVP_PAIR_COLS 4  // columns per inner step (2 or 4)
+#endif
+#ifndef MVP_PAIR_MINB
+#define MVP_PAIR_MINB 3  // resident CTAs per SM asked of ptxas for the 8-warp tile
+#endif
+#ifndef MVP_PAIR_SCALAR
+#define MVP_PAIR_SCALAR 0  // 1: scalar FADD/FMUL/FFMA instead of the packed fp32x2 forms
+#endif
+
+constexpr int kRows = MVP_PAIR_ROWS;
+constexpr int kBlk = 32 * kRows;  // granularity of the "which block won" half of a key (rows and columns alike)
+constexpr int kCps = MVP_PAIR_COLS;
+constexpr int kTN = 1024;         // columns per shared-memory tile
 constexpr float kPadRow = 2e19f, kPadCol = -2e19f;  // padding coordinates: any distance to them overflows to +inf
 
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
@@ -62,8 +78,15 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 }
 // two columns (packed) against one row (duplicated): the reference's contraction, lane by lane
 __device__ __forceinline__ u64 dist2(u64 X, u64 Y, u64 Z, u64 qx, u64 qy, u64 qz) {
+#if MVP_PAIR_SCALAR
+  float xl, xh, yl, yh, zl, zh, ql, qh, rl, rh, sl, sh;
+  unpack2(X, xl, xh), unpack2(Y, yl, yh), unpack2(Z, zl, zh);
+  unpack2(qx, ql, qh), unpack2(qy, rl, rh), unpack2(qz, sl, sh);
+  return pack2(sqdist(xl - ql, yl - rl, zl - sl), sqdist(xh - qh, yh - rh, zh - sh));
+#else
   const u64 dx = sub2(X, qx), dy = sub2(Y, qy), dz = sub2(Z, qz);
   return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+#endif
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,9 +123,9 @@ struct PairSmem {
   uint64_t bar[2];
 };
 
-// grid: x = row tile, y = column split, z = cloud.  WARPS warps per CTA, TM = 256 * WARPS rows per tile.
+// grid: x = row tile, y = column split, z = cloud.  WARPS warps per CTA, TM = kBlk * WARPS rows per tile.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS >= 8 ? 2 : 4)
+__global__ void __launch_bounds__(WARPS * 32, WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4))
 chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *__restrict__ xyz1,
                     const float *__restrict__ xyz2, u64 *__restrict__ rowkey, u64 *__restrict__ colkey) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,7 +135,7 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
   const int b = blockIdx.z;
   const float *A = xyz1 + (size_t)b * n * 3;
   const float *Bc = xyz2 + (size_t)b * m * 3;
-  const int row0 = blockIdx.x * (WARPS * kBlk) + warp * kBlk;  // first row of this warp's 256-row block
+  const int row0 = blockIdx.x * (WARPS * kBlk) + warp * kBlk;  // first row of this warp's kBlk-row block
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int ntiles_all = (m + kTN - 1) / kTN;
   const int ntiles = min(tiles_per_cta, ntiles_all - tile0);
@@ -183,40 +206,50 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
     __syncthreads();
     if (t + 1 < ntiles && tile_by_tma(t + 1) && tid == 0) issue_tma(t + 1);  // overlaps the sweep below
 
-    // ---- sweep: 4 chunks of 256 columns, 4 columns per step
+    // ---- sweep: kTN/kBlk chunks of kBlk columns, kCps columns per step
     const int cols_here = min(kTN, m - col0);
     const int nchunks = (cols_here + kBlk - 1) / kBlk;
     for (int c = 0; c < nchunks; c++) {
 #pragma unroll 1
-      for (int g = c * (kBlk / 4); g < (c + 1) * (kBlk / 4); g++) {
-        const ulonglong2 X = S.x[g], Y = S.y[g], Z = S.z[g];
-        float cm0 = inf, cm1 = inf, cm2 = inf, cm3 = inf;
+      for (int g = c * (kBlk / kCps); g < (c + 1) * (kBlk / kCps); g++) {
+        u64 X[kCps / 2], Y[kCps / 2], Z[kCps / 2];
+        if (kCps == 4) {
+          const ulonglong2 x4 = S.x[g], y4 = S.y[g], z4 = S.z[g];
+          X[0] = x4.x, X[kCps / 2 - 1] = x4.y, Y[0] = y4.x, Y[kCps / 2 - 1] = y4.y, Z[0] = z4.x, Z[kCps / 2 - 1] = z4.y;
+        } else {
+          X[0] = reinterpret_cast<const u64 *>(S.x)[g];
+          Y[0] = reinterpret_cast<const u64 *>(S.y)[g];
+          Z[0] = reinterpret_cast<const u64 *>(S.z)[g];
+        }
+        float cm[kCps];
+#pragma unroll
+        for (int h = 0; h < kCps; h++) cm[h] = inf;
 #pragma unroll
         for (int r = 0; r < kRows; r += 2) {
-          const u64 a0 = dist2(X.x, Y.x, Z.x, qx[r], qy[r], qz[r]);
-          const u64 b0 = dist2(X.y, Y.y, Z.y, qx[r], qy[r], qz[r]);
-          const u64 a1 = dist2(X.x, Y.x, Z.x, qx[r + 1], qy[r + 1], qz[r + 1]);
-          const u64 b1 = dist2(X.y, Y.y, Z.y, qx[r + 1], qy[r + 1], qz[r + 1]);
-          float a0l, a0h, b0l, b0h, a1l, a1h, b1l, b1h;
-          unpack2(a0, a0l, a0h);
-          unpack2(b0, b0l, b0h);
-          unpack2(a1, a1l, a1h);
-          unpack2(b1, b1l, b1h);
-          best[r] = min3(min3(best[r], a0l, a0h), b0l, b0h);
-          best[r + 1] = min3(min3(best[r + 1], a1l, a1h), b1l, b1h);
-          cm0 = min3(cm0, a0l, a1l);
-          cm1 = min3(cm1, a0h, a1h);
-          cm2 = min3(cm2, b0l, b1l);
-          cm3 = min3(cm3, b0h, b1h);
+#pragma unroll
+          for (int h = 0; h < kCps / 2; h++) {
+            const u64 d0 = dist2(X[h], Y[h], Z[h], qx[r], qy[r], qz[r]);
+            const u64 d1 = dist2(X[h], Y[h], Z[h], qx[r + 1], qy[r + 1], qz[r + 1]);
+            float d0l, d0h, d1l, d1h;
+            unpack2(d0, d0l, d0h);
+            unpack2(d1, d1l, d1h);
+            best[r] = min3(best[r], d0l, d0h);
+            best[r + 1] = min3(best[r + 1], d1l, d1h);
+            cm[2 * h] = min3(cm[2 * h], d0l, d1l);
+            cm[2 * h + 1] = min3(cm[2 * h + 1], d0h, d1h);
+          }
         }
-        uint4 w;
-        w.x = redux_min_u32(__float_as_uint(cm0));
-        w.y = redux_min_u32(__float_as_uint(cm1));
-        w.z = redux_min_u32(__float_as_uint(cm2));
-        w.w = redux_min_u32(__float_as_uint(cm3));
-        if (lane == 0) *reinterpret_cast<uint4 *>(&S.wmin[warp][g * 4]) = w;
+        uint32_t w[kCps];
+#pragma unroll
+        for (int h = 0; h < kCps; h++) w[h] = redux_min_u32(__float_as_uint(cm[h]));
+        if (lane == 0) {
+          if (kCps == 4)
+            *reinterpret_cast<uint4 *>(&S.wmin[warp][g * 4]) = make_uint4(w[0], w[1], w[kCps - 2], w[kCps - 1]);
+          else
+            *reinterpret_cast<uint2 *>(&S.wmin[warp][g * 2]) = make_uint2(w[0], w[1]);
+        }
       }
-      const int chunk = (col0 >> 8) + c;
+      const int chunk = col0 / kBlk + c;
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
         if (best[r] < prev[r]) {
@@ -248,11 +281,14 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
   }
 }
 
-// One warp per point p of cloud P (np points): key = (bits(d) << 32) | block; scan the 256 points of cloud Q in that
-// block, ascending, for the first whose distance to p has exactly those bits.
+// One warp per point p of cloud P (np points): key = (bits(d) << 32) | block.  The kBlk points of cloud Q in that
+// block are re-evaluated, kBlk/32 consecutive candidates per lane (128-bit loads when the block is whole and
+// 16-byte aligned), and the first one whose distance to p has exactly those bits is the answer.
 __global__ void __launch_bounds__(256)
-chamfer_resolve_kernel(long long total, int np, int nq, const float *__restrict__ P, const float *__restrict__ Q,
-                       const u64 *__restrict__ key, float *__restrict__ dist, int *__restrict__ idx) {
+chamfer_resolve_kernel(long long total, int np, int nq, int vec_ok, const float *__restrict__ P,
+                       const float *__restrict__ Q, const u64 *__restrict__ key, float *__restrict__ dist,
+                       int *__restrict__ idx) {
+  constexpr int PER = kBlk / 32;  // candidates per lane
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= total) return;
@@ -261,26 +297,39 @@ chamfer_resolve_kernel(long long total, int np, int nq, const float *__restrict_
   const uint32_t bits = (uint32_t)(k >> 32);
   const int base = (int)(uint32_t)k * kBlk;
   const float px = __ldg(P + wid * 3 + 0), py = __ldg(P + wid * 3 + 1), pz = __ldg(P + wid * 3 + 2);
-  const float *q = Q + (size_t)cloud * nq * 3;
-  int found = base;
-#pragma unroll 1
-  for (int s = 0; s < kBlk; s += 32) {
-    const int j = base + s + lane;
-    bool hit = false;
-    if (j < nq) {
-      const float d = sqdist(__ldg(q + (size_t)j * 3 + 0) - px, __ldg(q + (size_t)j * 3 + 1) - py,
-                             __ldg(q + (size_t)j * 3 + 2) - pz);
-      hit = __float_as_uint(d) == bits;
+  const float *q = Q + ((size_t)cloud * nq + base + lane * PER) * 3;
+  float c[PER * 3];
+  if (vec_ok && base + kBlk <= nq) {
+    const float4 *q4 = reinterpret_cast<const float4 *>(q);
+#pragma unroll
+    for (int v = 0; v < PER * 3 / 4; v++) {
+      const float4 t = __ldg(q4 + v);
+      c[v * 4 + 0] = t.x;
+      c[v * 4 + 1] = t.y;
+      c[v * 4 + 2] = t.z;
+      c[v * 4 + 3] = t.w;
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-    if (mask) {
-      found = base + s + __ffs(mask) - 1;
-      break;
+  } else {
+#pragma unroll
+    for (int v = 0; v < PER; v++) {
+      const bool ok = base + lane * PER + v < nq;
+      c[v * 3 + 0] = ok ? __ldg(q + v * 3 + 0) : kPadCol;
+      c[v * 3 + 1] = ok ? __ldg(q + v * 3 + 1) : kPadCol;
+      c[v * 3 + 2] = ok ? __ldg(q + v * 3 + 2) : kPadCol;
     }
   }
+  int first = PER;
+#pragma unroll
+  for (int v = PER - 1; v >= 0; v--) {
+    const float d = sqdist(c[v * 3 + 0] - px, c[v * 3 + 1] - py, c[v * 3 + 2] - pz);
+    if (__float_as_uint(d) == bits) first = v;
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, first < PER);
+  const int src = mask ? __ffs(mask) - 1 : 0;
+  const int v = __shfl_sync(0xffffffffu, first, src);
   if (lane == 0) {
     dist[wid] = __uint_as_float(bits);
-    idx[wid] = found;
+    idx[wid] = mask ? base + src * PER + v : base;
   }
 }
 
@@ -336,8 +385,12 @@ int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xy
   if (rc) return rc;
 
   const long long t1 = (long long)b * n, t2 = (long long)b * m;
-  chamfer_resolve_kernel<<<(unsigned)((t1 * 32 + 255) / 256), 256, 0, s>>>(t1, n, m, xyz1, xyz2, rowkey, dist1, idx1);
-  chamfer_resolve_kernel<<<(unsigned)((t2 * 32 + 255) / 256), 256, 0, s>>>(t2, m, n, xyz2, xyz1, colkey, dist2, idx2);
+  const int vec2 = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
+  const int vec1 = ((reinterpret_cast<uintptr_t>(xyz1) & 15) == 0 && (n % 4) == 0) ? 1 : 0;
+  chamfer_resolve_kernel<<<(unsigned)((t1 * 32 + 255) / 256), 256, 0, s>>>(t1, n, m, vec2, xyz1, xyz2, rowkey, dist1,
+                                                                            idx1);
+  chamfer_resolve_kernel<<<(unsigned)((t2 * 32 + 255) / 256), 256, 0, s>>>(t2, m, n, vec1, xyz2, xyz1, colkey, dist2,
+                                                                            idx2);
   count_launch(2);
   return launch_status();
 }
