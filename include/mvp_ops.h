@@ -57,6 +57,20 @@ int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz
                         float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
                         mvp_stream_t stream);
 
+/* The same operator with the algorithm named explicitly (tests and benchmarks use it; results are
+ * bit-identical for all three):
+ *   MVP_CHAMFER_AUTO  what mvp_chamfer_forward does: GRID when the shape supports it, else BRUTE;
+ *   MVP_CHAMFER_BRUTE every pair evaluated (tiled B*N*M argmin, both directions from one evaluation);
+ *   MVP_CHAMFER_GRID  exact nearest neighbour through a uniform grid built per cloud, pruned with
+ *                     conservative lower bounds, left-over points finished by brute force
+ *                     (n, m >= 512; MVP_ERR_INVALID_ARGUMENT otherwise). */
+#define MVP_CHAMFER_AUTO 0
+#define MVP_CHAMFER_BRUTE 1
+#define MVP_CHAMFER_GRID 2
+int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
+                             float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
+                             size_t workspace_bytes, mvp_stream_t stream);
+
 /* Replaces chamfer_3D.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:22-26, chamfer3D.cu:176-195,
  * kernel :155-174).  gradxyz1 (b,n,3) and gradxyz2 (b,m,3) are zero-filled inside
  * (dist_chamfer_3D.py:56-57 does it in the reference) and then accumulated with fp32 atomics. */

@@ -16,23 +16,30 @@ namespace mvp {
 constexpr int kChThreads = 256;
 constexpr int kChTile = 1024;  // targets per shared-memory tile (AoS, 12 KB)
 
-template <int R>
-__global__ void __launch_bounds__(kChThreads)
-chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ xyz2,
-                   float *__restrict__ dist, int *__restrict__ idx) {
+// kRest: the queries are the `count[b]` entries of `list + b*n` (the grid path's left-over points, chamfer_grid.cu)
+// instead of all n points of the cloud; CTAs beyond the list length exit at once.
+template <int R, bool kRest>
+__device__ __forceinline__ void chamfer_dir_body(int b, int n, int m, const float *__restrict__ xyz,
+                                                 const float *__restrict__ xyz2, float *__restrict__ dist,
+                                                 int *__restrict__ idx, const int *__restrict__ list,
+                                                 const int *__restrict__ count) {
   __shared__ __align__(16) float tile[kChTile * 3];
-  const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int qbase = blockIdx.x * (kChThreads * R);
+  const int nq = kRest ? __ldg(count + b) : n;
+  if (qbase >= nq) return;
+  if (kRest) list += (size_t)b * n;
   const float *q = xyz + (size_t)b * n * 3;
   const float *t = xyz2 + (size_t)b * m * 3;
 
   float qx[R], qy[R], qz[R], best[R];
-  int bi[R];
+  int bi[R], qi[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int j = qbase + r * kChThreads + tid;
-    const int jj = j < n ? j : n - 1;
+    int jj = j < nq ? j : nq - 1;
+    if (kRest) jj = __ldg(list + jj);
+    qi[r] = jj;
     qx[r] = __ldg(q + jj * 3 + 0);
     qy[r] = __ldg(q + jj * 3 + 1);
     qz[r] = __ldg(q + jj * 3 + 2);
@@ -70,11 +77,40 @@ chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__r
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int j = qbase + r * kChThreads + tid;
-    if (j < n) {
-      dist[(size_t)b * n + j] = best[r];
-      idx[(size_t)b * n + j] = bi[r];
+    if (j < nq) {
+      dist[(size_t)b * n + qi[r]] = best[r];
+      idx[(size_t)b * n + qi[r]] = bi[r];
     }
   }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kChThreads)
+chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ xyz2,
+                   float *__restrict__ dist, int *__restrict__ idx) {
+  chamfer_dir_body<R, false>(blockIdx.y, n, m, xyz, xyz2, dist, idx, nullptr, nullptr);
+}
+
+// both directions of the left-over pass in one launch: blockIdx.z = direction
+__global__ void __launch_bounds__(kChThreads)
+chamfer_rest_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                    float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
+                    int *__restrict__ idx2, const int *__restrict__ list1, const int *__restrict__ list2,
+                    const int *__restrict__ count) {
+  if (blockIdx.z == 0)
+    chamfer_dir_body<2, true>(blockIdx.y, n, m, xyz1, xyz2, dist1, idx1, list1, count);
+  else
+    chamfer_dir_body<2, true>(blockIdx.y, m, n, xyz2, xyz1, dist2, idx2, list2, count + b);
+}
+
+int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count,
+                        cudaStream_t s) {
+  const int big = n > m ? n : m;
+  dim3 grid((big + kChThreads * 2 - 1) / (kChThreads * 2), b, 2);
+  chamfer_rest_kernel<<<grid, kChThreads, 0, s>>>(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, list1, list2, count);
+  count_launch();
+  return launch_status();
 }
 
 int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2, float *dist, int *idx,
@@ -144,21 +180,36 @@ bool chamfer_fused_supported(int b, int n, int m);
 size_t chamfer_fused_workspace_bytes(int b, int n, int m);
 int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
                          float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
+// chamfer_grid.cu
+bool chamfer_grid_supported(int b, int n, int m);
+size_t chamfer_grid_workspace_bytes(int b, int n, int m);
+int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                        float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
 }  // namespace mvp
 
 MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 16;
-  return chamfer_fused_supported(b, n, m) ? chamfer_fused_workspace_bytes(b, n, m) : 16;
+  size_t need = 16;  // one size serves every algorithm, so the caller need not know which one runs
+  if (chamfer_fused_supported(b, n, m)) need = std::max(need, chamfer_fused_workspace_bytes(b, n, m));
+  if (chamfer_grid_supported(b, n, m)) need = std::max(need, chamfer_grid_workspace_bytes(b, n, m));
+  return need;
 }
 
-MVP_API int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
-                                float *dist2, int *idx1, int *idx2, void *workspace,
-                                size_t workspace_bytes, mvp_stream_t stream) {
+MVP_API int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
+                                     float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
+                                     size_t workspace_bytes, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (algo < MVP_CHAMFER_AUTO || algo > MVP_CHAMFER_GRID) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
   if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;  // the reference reads out of bounds here
   if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
+  const bool grid_ok = chamfer_grid_supported(b, n, m);
+  if (algo == MVP_CHAMFER_GRID && !grid_ok) return MVP_ERR_INVALID_ARGUMENT;
+  if (grid_ok && algo != MVP_CHAMFER_BRUTE) {
+    if (!workspace || workspace_bytes < chamfer_grid_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
+    return chamfer_grid_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace, workspace_bytes, s);
+  }
   if (chamfer_fused_supported(b, n, m)) {
     if (!workspace || workspace_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
     return chamfer_fused_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace,
@@ -167,6 +218,13 @@ MVP_API int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const fl
   int rc = chamfer_dir_launch(b, n, m, xyz1, xyz2, dist1, idx1, s);
   if (rc) return rc;
   return chamfer_dir_launch(b, m, n, xyz2, xyz1, dist2, idx2, s);
+}
+
+MVP_API int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                                float *dist2, int *idx1, int *idx2, void *workspace,
+                                size_t workspace_bytes, mvp_stream_t stream) {
+  return mvp_chamfer_forward_algo(MVP_CHAMFER_AUTO, b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace,
+                                  workspace_bytes, stream);
 }
 
 MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,

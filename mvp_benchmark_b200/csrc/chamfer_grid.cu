@@ -1,0 +1,425 @@
+// Chamfer distance, grid-pruned exact path for sm_100a.
+//
+// Same outputs, bit for bit, as the brute-force kernels (chamfer.cu / chamfer_fused.cu) and therefore as the
+// reference's NmDistanceKernel (utils/metrics/CD/chamfer3D/chamfer3D.cu:12-134): every candidate that is
+// evaluated uses the reference's contraction  d = fma(dz,dz, fma(dx,dx, dy*dy)),  equal minima resolve to the
+// lowest index (:36,:126), and a candidate is only ever SKIPPED when a conservative lower bound of its distance
+// is strictly greater than a distance already found.  What changes is the amount of work: B*N*M pair
+// evaluations become ~B*(N+M)*(a few dozen).
+//
+//   build   one CTA per (cloud, side): bounding box -> isotropic cell size with <= `cap` cells -> counting sort of
+//           the cloud by cell (shared-memory histogram, block scan, scatter) into a float4 array
+//           (x, y, z, original index) + a cell-start table.  x is the fastest-varying cell coordinate, so a run of
+//           cells along x is ONE contiguous range of the sorted array.
+//   query   one thread per point, visited in the SORTED order of its own cloud (neighbouring threads look at
+//           neighbouring cells of the other cloud's grid).  Cubes of cells of growing radius r around the
+//           point's cell; rows of cells whose lower bound exceeds the best distance are skipped; the search
+//           stops when the best distance is below the distance to the unvisited exterior.  A point that has
+//           not finished after kMaxRing rings or kBudget candidates (far outside the other cloud, or inside a
+//           very dense cell) is appended to a left-over list instead.
+//   rest    left-over points are finished by the tiled brute-force kernel of chamfer.cu, gathering its queries
+//           through the list (CTAs beyond the list length exit at once; normally all of them do).
+//
+// Degenerate inputs (non-finite coordinates, zero or astronomically large extent) mark the grid invalid; all
+// queries against it go to the left-over list, i.e. the brute-force path and its semantics.
+#include "common.cuh"
+
+namespace mvp {
+
+constexpr int kGridThreads = 1024;   // build CTA
+constexpr int kGridMaxCells = 32768; // shared-memory histogram: 128 KB
+constexpr int kGridQThreads = 128;   // query CTA
+#ifndef MVP_GRID_PPC
+#define MVP_GRID_PPC 2               // target points per cell
+#endif
+#ifndef MVP_GRID_MAXRING
+#define MVP_GRID_MAXRING 3
+#endif
+#ifndef MVP_GRID_BUDGET
+#define MVP_GRID_BUDGET 1536         // candidate evaluations per query before it gives up
+#endif
+
+struct __align__(16) GridHdr {
+  float lo[3];
+  float inv_s;
+  float s;
+  int g[3];
+  int ncell;
+  int valid;
+  int pad[6];
+};
+static_assert(sizeof(GridHdr) == 64, "GridHdr layout");
+
+struct GridWs {  // carved out of the caller's workspace by grid_plan()
+  GridHdr *hdr;        // [2][b]
+  int *count;          // [2][b]  left-over list lengths
+  int *start[2];       // [b][cap_side + 1]
+  float4 *sorted[2];   // [b][n] / [b][m]
+  int *list[2];        // [b][n] / [b][m]
+  int cap[2];
+};
+
+static int grid_cap(int npts) {
+  int c = npts / MVP_GRID_PPC;
+  c = std::max(c, 8);
+  return std::min(c, kGridMaxCells);
+}
+
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
+  size_t off = 0;
+  unsigned char *p = reinterpret_cast<unsigned char *>(base);
+  auto take = [&](size_t bytes) {
+    unsigned char *r = p ? p + off : nullptr;
+    off += align16(bytes);
+    return r;
+  };
+  const int cap0 = grid_cap(n), cap1 = grid_cap(m);
+  GridWs t;
+  t.cap[0] = cap0;
+  t.cap[1] = cap1;
+  t.hdr = reinterpret_cast<GridHdr *>(take(sizeof(GridHdr) * 2 * (size_t)b));
+  t.count = reinterpret_cast<int *>(take(sizeof(int) * 2 * (size_t)b));
+  t.start[0] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap0 + 1)));
+  t.start[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap1 + 1)));
+  t.sorted[0] = reinterpret_cast<float4 *>(take(sizeof(float4) * (size_t)b * n));
+  t.sorted[1] = reinterpret_cast<float4 *>(take(sizeof(float4) * (size_t)b * m));
+  t.list[0] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * n));
+  t.list[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * m));
+  if (w) *w = t;
+  return off;
+}
+
+__device__ __forceinline__ int cell_coord(float u, int g) {
+  // floor + clamp in float first: u may be far outside the int range for a query outside the grid
+  return (int)fminf(fmaxf(floorf(u), 0.f), (float)(g - 1));
+}
+
+// ------------------------------------------------------------------------------------------------ build
+__global__ void __launch_bounds__(kGridThreads, 1)
+chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                          GridWs W) {
+  extern __shared__ int hist[];  // cap ints
+  __shared__ float s_red[6][32];
+  __shared__ int s_fin[32];
+  __shared__ int s_warp[32];
+  __shared__ GridHdr s_hdr;
+  const int cloud = blockIdx.x, side = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = side ? m : n;
+  const int cap = side ? W.cap[1] : W.cap[0];
+  const float *P = (side ? xyz2 : xyz1) + (size_t)cloud * np * 3;
+  const float inf = __int_as_float(0x7f800000);
+
+  // ---- pass 1: bounding box and finiteness
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  int fin = 1;
+  for (int i = tid; i < np; i += kGridThreads) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float v = __ldg(P + (size_t)i * 3 + a);
+      lo[a] = fminf(lo[a], v);
+      hi[a] = fmaxf(hi[a], v);
+      fin &= (fabsf(v) <= 3.0e38f) ? 1 : 0;  // false for NaN and +-inf
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+    fin &= __shfl_xor_sync(0xffffffffu, fin, off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      s_red[a][warp] = lo[a];
+      s_red[3 + a][warp] = hi[a];
+    }
+    s_fin[warp] = fin;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kGridThreads / 32; w++) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        lo[a] = fminf(lo[a], s_red[a][w]);
+        hi[a] = fmaxf(hi[a], s_red[3 + a][w]);
+      }
+      fin &= s_fin[w];
+    }
+    GridHdr h;
+    float ex[3], emax = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      ex[a] = hi[a] - lo[a];
+      emax = fmaxf(emax, ex[a]);
+      h.lo[a] = lo[a];
+    }
+    h.valid = (fin && emax > 0.f && emax < 1e18f) ? 1 : 0;
+    h.g[0] = h.g[1] = h.g[2] = 1;
+    h.s = 1.f;
+    h.inv_s = 1.f;
+    if (!h.valid) {
+      h.lo[0] = h.lo[1] = h.lo[2] = 0.f;
+    } else {
+      // isotropic cell side: start from the volume heuristic (thin extents padded), grow until <= cap cells
+      float vol = 1.f;
+#pragma unroll
+      for (int a = 0; a < 3; a++) vol *= fmaxf(ex[a], emax * 1e-3f) / emax;  // relative: no overflow
+      float s = emax * cbrtf(vol / (float)cap);
+      for (int it = 0; it < 400; it++) {
+        float cells = 1.f;
+#pragma unroll
+        for (int a = 0; a < 3; a++) cells *= floorf(ex[a] / s) + 1.f;
+        if (cells <= (float)cap) break;
+        s *= 1.04f;
+      }
+      const float inv_s = 1.0f / s;
+      long long cells = 1;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        // one more cell than floor(extent / s): the largest coordinate never needs the clamp by more than rounding
+        float gf = floorf(ex[a] * inv_s) + 1.f;
+        h.g[a] = (int)fminf(gf, (float)cap);
+        cells *= h.g[a];
+      }
+      if (cells > cap || !(inv_s > 0.f) || !(inv_s < 3.0e38f)) {  // pathological rounding: fall back
+        h.valid = 0;
+        h.g[0] = h.g[1] = h.g[2] = 1;
+        h.lo[0] = h.lo[1] = h.lo[2] = 0.f;
+      } else {
+        h.s = s;
+        h.inv_s = inv_s;
+      }
+    }
+    h.ncell = h.g[0] * h.g[1] * h.g[2];
+#pragma unroll
+    for (int a = 0; a < 6; a++) h.pad[a] = 0;
+    s_hdr = h;
+    W.hdr[side * b + cloud] = h;
+    W.count[side * b + cloud] = 0;
+  }
+  __syncthreads();
+  const GridHdr h = s_hdr;
+  const int ncell = h.ncell;
+  for (int c = tid; c < ncell; c += kGridThreads) hist[c] = 0;
+  __syncthreads();
+
+  auto cell_of = [&](float x, float y, float z) {
+    if (!h.valid) return 0;
+    const int cx = cell_coord((x - h.lo[0]) * h.inv_s, h.g[0]);
+    const int cy = cell_coord((y - h.lo[1]) * h.inv_s, h.g[1]);
+    const int cz = cell_coord((z - h.lo[2]) * h.inv_s, h.g[2]);
+    return (cz * h.g[1] + cy) * h.g[0] + cx;
+  };
+
+  // ---- pass 2: histogram
+  for (int i = tid; i < np; i += kGridThreads)
+    atomicAdd(&hist[cell_of(__ldg(P + (size_t)i * 3 + 0), __ldg(P + (size_t)i * 3 + 1), __ldg(P + (size_t)i * 3 + 2))], 1);
+  __syncthreads();
+
+  // ---- exclusive scan over the cells (contiguous chunk per thread, warp scan, scan of warp totals)
+  const int per = (ncell + kGridThreads - 1) / kGridThreads;
+  const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
+  int sum = 0;
+  for (int c = c0; c < c1; c++) sum += hist[c];
+  int incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_warp[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+  int *start = (side ? W.start[1] : W.start[0]) + (size_t)cloud * (cap + 1);
+  for (int c = c0; c < c1; c++) {
+    const int cnt = hist[c];
+    hist[c] = run;  // becomes the fill cursor of the scatter pass
+    start[c] = run;
+    run += cnt;
+  }
+  if (tid == 0) start[ncell] = np;
+  __syncthreads();
+
+  // ---- pass 3: scatter (order inside a cell is arbitrary; the query's tie rule is explicit)
+  float4 *S = (side ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * np;
+  for (int i = tid; i < np; i += kGridThreads) {
+    const float x = __ldg(P + (size_t)i * 3 + 0), y = __ldg(P + (size_t)i * 3 + 1), z = __ldg(P + (size_t)i * 3 + 2);
+    const int pos = atomicAdd(&hist[cell_of(x, y, z)], 1);
+    S[pos] = make_float4(x, y, z, __int_as_float(i));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ query
+__global__ void __launch_bounds__(kGridQThreads)
+chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
+                          int *__restrict__ idx1, int *__restrict__ idx2) {
+  const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
+  const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
+  if (t >= total) return;
+  const int dir = t >= total1 ? 1 : 0;       // 0: points of xyz1 against xyz2's grid; 1: the other way round
+  const long long pi = dir ? t - total1 : t;
+  const int nq = dir ? m : n, nt = dir ? n : m;
+  const int cloud = (int)(pi / nq);
+  const float4 self = __ldg((dir ? W.sorted[1] : W.sorted[0]) + pi);
+  const int orig = __float_as_int(self.w);
+  const int ts = 1 - dir;  // target side
+  const GridHdr *hp = W.hdr + ts * b + cloud;
+  const int4 h0 = __ldg(reinterpret_cast<const int4 *>(hp));      // lo.xyz, inv_s
+  const int4 h1 = __ldg(reinterpret_cast<const int4 *>(hp) + 1);  // s, g.xyz
+  const int4 h2 = __ldg(reinterpret_cast<const int4 *>(hp) + 2);  // ncell, valid
+  const float inv_s = __int_as_float(h0.w), s = __int_as_float(h1.x);
+  const int gx = h1.y, gy = h1.z, gz = h1.w;
+  const int *start = (ts ? W.start[1] : W.start[0]) + (size_t)cloud * ((ts ? W.cap[1] : W.cap[0]) + 1);
+  const float4 *T = (ts ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * nt;
+  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq;
+  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq;
+
+  const float inf = __int_as_float(0x7f800000);
+  float best = inf;
+  int bi = 0x7fffffff;
+  bool done = false;
+  if (h2.y) {
+    const float ux = (self.x - __int_as_float(h0.x)) * inv_s;
+    const float uy = (self.y - __int_as_float(h0.y)) * inv_s;
+    const float uz = (self.z - __int_as_float(h0.z)) * inv_s;
+    const int cx = cell_coord(ux, gx), cy = cell_coord(uy, gy), cz = cell_coord(uz, gz);
+    // rounding slack of the cell coordinates, in cells (derivation in DESIGN.md §4.1): 2^-23 (|u| + g), 8x margin
+    const float slx = 1e-4f + 1e-6f * (fabsf(ux) + (float)gx);
+    const float sly = 1e-4f + 1e-6f * (fabsf(uy) + (float)gy);
+    const float slz = 1e-4f + 1e-6f * (fabsf(uz) + (float)gz);
+    const float s2 = s * s * (1.f - 1e-5f);  // (cells -> squared distance), rounded DOWN generously
+    // a query astronomically far from the grid (or with an overflowing cell coordinate) cannot be pruned
+    int budget = (fabsf(ux) < 1e6f && fabsf(uy) < 1e6f && fabsf(uz) < 1e6f) ? MVP_GRID_BUDGET : -1;
+
+    // distance (in cells, >= 0, conservative) from coordinate u to the slab of cell c
+    auto gap = [](float u, int c, float slack) {
+      const float g = fmaxf((float)c - u, u - (float)(c + 1));
+      return fmaxf(g - slack, 0.f);
+    };
+    auto scan = [&](int a, int e) {
+      if (e - a > budget) {  // too dense here: give up, the brute-force pass finishes this point
+        budget = -1;
+        return;
+      }
+      budget -= e - a;
+      for (int i = a; i < e; i++) {
+        const float4 q = __ldg(T + i);
+        const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
+        const int qi = __float_as_int(q.w);
+        if (d < best || (d == best && qi < bi)) {
+          best = d;
+          bi = qi;
+        }
+      }
+    };
+    // cells [x0, x1] of row (yy, zz), clipped at both ends by the per-cell bound
+    auto row = [&](int x0, int x1, int yy, int zz, float lbyz) {
+      x0 = max(x0, 0);
+      x1 = min(x1, gx - 1);
+      while (x0 <= x1) {
+        const float g = gap(ux, x0, slx);
+        if (fmaf(g, g, lbyz) * s2 > best) x0++; else break;
+      }
+      while (x1 >= x0) {
+        const float g = gap(ux, x1, slx);
+        if (fmaf(g, g, lbyz) * s2 > best) x1--; else break;
+      }
+      if (x0 > x1) return;
+      const int base = (zz * gy + yy) * gx;
+      scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
+    };
+
+    for (int r = 1; r <= MVP_GRID_MAXRING && !done && budget >= 0; r++) {
+      if (r == 1) row(cx - 1, cx + 1, cy, cz, 0.f);  // the centre row first: a good `best` prunes the rest
+      for (int dz = -r; dz <= r && budget >= 0; dz++) {
+        const int zz = cz + dz;
+        if (zz < 0 || zz >= gz) continue;
+        const float gzz = gap(uz, zz, slz);
+        if (gzz * gzz * s2 > best) continue;
+        for (int dy = -r; dy <= r; dy++) {
+          const int yy = cy + dy;
+          if (yy < 0 || yy >= gy) continue;
+          const float gyy = gap(uy, yy, sly);
+          const float lbyz = fmaf(gyy, gyy, gzz * gzz);
+          if (lbyz * s2 > best) continue;
+          const bool shell = (dz == -r || dz == r || dy == -r || dy == r);
+          if (shell) {
+            row(cx - r, cx + r, yy, zz, lbyz);
+          } else if (r > 1) {  // interior row: only its two new end cells
+            row(cx - r, cx - r, yy, zz, lbyz);
+            row(cx + r, cx + r, yy, zz, lbyz);
+          }
+        }
+      }
+      if (budget < 0) break;
+      // everything outside the cube of radius r is at least `ext` cells away
+      float ext = inf;
+      if (cx - r > 0) ext = fminf(ext, ux - (float)(cx - r) - slx);
+      if (cx + r + 1 < gx) ext = fminf(ext, (float)(cx + r + 1) - ux - slx);
+      if (cy - r > 0) ext = fminf(ext, uy - (float)(cy - r) - sly);
+      if (cy + r + 1 < gy) ext = fminf(ext, (float)(cy + r + 1) - uy - sly);
+      if (cz - r > 0) ext = fminf(ext, uz - (float)(cz - r) - slz);
+      if (cz + r + 1 < gz) ext = fminf(ext, (float)(cz + r + 1) - uz - slz);
+      ext = fmaxf(ext, 0.f);
+      if (ext == inf || best < ext * ext * s2) done = true;
+    }
+  }
+  if (done) {
+    dist[orig] = best;
+    idx[orig] = bi;
+  } else {
+    const int pos = atomicAdd(W.count + dir * b + cloud, 1);
+    ((dir ? W.list[1] : W.list[0]) + (size_t)cloud * nq)[pos] = orig;
+  }
+}
+
+// chamfer.cu
+int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, cudaStream_t s);
+
+bool chamfer_grid_supported(int b, int n, int m) {
+  return b > 0 && b <= 65535 && n >= 512 && m >= 512 && n <= (1 << 20) && m <= (1 << 20) &&
+         (long long)b * ((long long)n + m) < (1LL << 31);
+}
+
+size_t chamfer_grid_workspace_bytes(int b, int n, int m) { return grid_plan(b, n, m, nullptr, nullptr); }
+
+int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                        int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
+  GridWs W;
+  if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
+  const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * kGridMaxCells));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
+  const long long total = (long long)b * ((long long)n + m);
+  chamfer_grid_query_kernel<<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+      b, n, m, W, dist1, dist2, idx1, idx2);
+  count_launch(2);
+  int rc = launch_status();
+  if (rc) return rc;
+  return chamfer_rest_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, W.list[0], W.list[1], W.count, s);
+}
+
+}  // namespace mvp

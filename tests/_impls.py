@@ -98,7 +98,9 @@ class CudaImpl:
         return r if len(r) > 1 else r[0]
 
     # -- ops
-    def chamfer_forward(self, x1, x2):
+    ALGOS = {"auto": 0, "brute": 1, "grid": 2}
+
+    def chamfer_forward(self, x1, x2, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr
         a, c = self.T(x1), self.T(x2)
         b, n, _ = a.shape
@@ -106,8 +108,13 @@ class CudaImpl:
         d1, d2 = self.E((b, n), t.float32), self.E((b, m), t.float32)
         i1, i2 = self.E((b, n), t.int32), self.E((b, m), t.int32)
         ws = L.workspace(L.lib.mvp_chamfer_forward_workspace_bytes(b, n, m), self.dev)
-        L.check(L.lib.mvp_chamfer_forward(b, n, m, p(a), p(c), p(d1), p(d2), p(i1), p(i2), p(ws), ws.numel(), self.S()),
-                "mvp_chamfer_forward")
+        ws.fill_(0xA5)
+        if algo == "auto":
+            rc = L.lib.mvp_chamfer_forward(b, n, m, p(a), p(c), p(d1), p(d2), p(i1), p(i2), p(ws), ws.numel(), self.S())
+        else:
+            rc = L.lib.mvp_chamfer_forward_algo(self.ALGOS[algo], b, n, m, p(a), p(c), p(d1), p(d2), p(i1), p(i2), p(ws),
+                                                ws.numel(), self.S())
+        L.check(rc, "mvp_chamfer_forward")
         return self.N(d1, d2, i1, i2)
 
     def chamfer_backward(self, x1, x2, g1, g2, i1, i2):

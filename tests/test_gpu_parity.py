@@ -75,6 +75,56 @@ def test_chamfer_forward_vs_oracle(gpu, cpu, kind, b, n, m):
         _cases.eq(g, w, f"chamfer {kind} {b}x{n}x{m} {nm}")
 
 
+GRID_SHAPES = [(4, 2048, 2048), (2, 513, 1023), (2, 2048, 3072), (1, 5000, 777), (3, 600, 4097), (2, 8192, 8192)]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "sphere", "duplicates", "lattice", "clustered", "planar", "outliers",
+                                  "shifted", "tiny", "constant"])
+@pytest.mark.parametrize("b,n,m", GRID_SHAPES)
+def test_chamfer_grid_is_bit_identical_to_brute_force(gpu, kind, b, n, m):
+    """The grid-pruned path (mvp_chamfer_forward's default for n, m >= 512) against the brute-force kernels on
+    benign and hostile point distributions: dense clusters, zero-extent axes, far outliers, disjoint clouds,
+    underflowing distances, identical points."""
+    x1, x2 = _data.cloud(kind, b, n, 1), _data.cloud(kind, b, m, 2)
+    want = gpu.chamfer_forward(x1, x2, algo="brute")
+    for algo in ("grid", "auto"):
+        got = gpu.chamfer_forward(x1, x2, algo=algo)
+        for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+            _cases.eq(g, w, f"chamfer {algo} vs brute, {kind} {b}x{n}x{m} {nm}")
+
+
+@pytest.mark.parametrize("kind", ["clustered", "planar", "outliers", "shifted"])
+def test_chamfer_grid_vs_oracle_hostile(gpu, cpu, kind):
+    x1, x2 = _data.cloud(kind, 2, 1500, 3), _data.cloud(kind, 2, 2100, 4)
+    got, want = gpu.chamfer_forward(x1, x2, algo="grid"), cpu.chamfer_forward(x1, x2)
+    for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+        _cases.eq(g, w, f"chamfer grid vs oracle {kind} {nm}")
+
+
+def test_chamfer_grid_mixed_pair_kinds(gpu):
+    """Different distributions on the two sides of a pair (a collapsed prediction against a full cloud, ...)."""
+    for k1, k2 in [("constant", "uniform"), ("uniform", "constant"), ("clustered", "sphere"), ("tiny", "uniform"),
+                   ("outliers", "planar")]:
+        x1, x2 = _data.cloud(k1, 3, 2048, 7), _data.cloud(k2, 3, 1536, 8)
+        want = gpu.chamfer_forward(x1, x2, algo="brute")
+        got = gpu.chamfer_forward(x1, x2, algo="grid")
+        for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+            _cases.eq(g, w, f"chamfer grid vs brute {k1}/{k2} {nm}")
+
+
+def test_chamfer_grid_non_finite_input_does_not_hang(gpu):
+    x1, x2 = _data.uniform(3, 1024, 1), _data.uniform(3, 1024, 2)
+    x1[0, 5, 1] = np.nan
+    x2[1, 7, 2] = np.inf
+    want = gpu.chamfer_forward(x1, x2, algo="brute")
+    got = gpu.chamfer_forward(x1, x2, algo="grid")
+    # a pair without a non-finite coordinate is unaffected by its neighbours in the batch; the others are sent to
+    # the brute-force pass (whose NaN behaviour is not specified by the reference) and only have to terminate
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g[2], w[2])
+    assert (got[2][:, :] >= 0).all() and (got[3][:, :] >= 0).all()
+
+
 def test_chamfer_self_distance_is_zero_with_lowest_duplicate(gpu):
     x = _data.duplicates(2, 1500, 3, frac=0.2)
     d1, d2, i1, i2 = gpu.chamfer_forward(x, x)
@@ -123,7 +173,10 @@ def test_chamfer_full_size_properties_and_reference(gpu, ref, cuda):
     # (3) swapping the clouds swaps the outputs
     e1, e2, j1, j2 = gpu.chamfer_forward(x2, x1)
     _cases.eq(e1, d2, "swap dist"), _cases.eq(e2, d1, "swap dist"), _cases.eq(j1, i2, "swap idx"), _cases.eq(j2, i1, "swap idx")
-    # (4) the reference kernels agree bit for bit
+    # (4) the brute-force kernels agree bit for bit with the (default) grid path
+    for g, w in zip(gpu.chamfer_forward(x1, x2, algo="brute"), (d1, d2, i1, i2)):
+        _cases.eq(g, w, "brute vs grid at full size")
+    # (5) the reference kernels agree bit for bit
     r1, r2, ri1, ri2 = ref.chamfer_forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda))
     _cases.eq(d1, r1.cpu().numpy(), "dist1 vs reference CUDA")
     _cases.eq(d2, r2.cpu().numpy(), "dist2 vs reference CUDA")
