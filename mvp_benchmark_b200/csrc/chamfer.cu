@@ -19,13 +19,13 @@ constexpr int kChTile = 1024;  // targets per shared-memory tile (AoS, 12 KB)
 // kRest: the queries are the `count[b]` entries of `list + b*n` (the grid path's left-over points, chamfer_grid.cu)
 // instead of all n points of the cloud; CTAs beyond the list length exit at once.
 template <int R, bool kRest>
-__device__ __forceinline__ void chamfer_dir_body(int b, int n, int m, const float *__restrict__ xyz,
+__device__ __forceinline__ void chamfer_dir_body(int chunk, int b, int n, int m, const float *__restrict__ xyz,
                                                  const float *__restrict__ xyz2, float *__restrict__ dist,
                                                  int *__restrict__ idx, const int *__restrict__ list,
                                                  const int *__restrict__ count) {
   __shared__ __align__(16) float tile[kChTile * 3];
   const int tid = threadIdx.x;
-  const int qbase = blockIdx.x * (kChThreads * R);
+  const int qbase = chunk * (kChThreads * R);
   const int nq = kRest ? __ldg(count + b) : n;
   if (qbase >= nq) return;
   if (kRest) list += (size_t)b * n;
@@ -88,29 +88,7 @@ template <int R>
 __global__ void __launch_bounds__(kChThreads)
 chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ xyz2,
                    float *__restrict__ dist, int *__restrict__ idx) {
-  chamfer_dir_body<R, false>(blockIdx.y, n, m, xyz, xyz2, dist, idx, nullptr, nullptr);
-}
-
-// both directions of the left-over pass in one launch: blockIdx.z = direction
-__global__ void __launch_bounds__(kChThreads)
-chamfer_rest_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                    float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
-                    int *__restrict__ idx2, const int *__restrict__ list1, const int *__restrict__ list2,
-                    const int *__restrict__ count) {
-  if (blockIdx.z == 0)
-    chamfer_dir_body<2, true>(blockIdx.y, n, m, xyz1, xyz2, dist1, idx1, list1, count);
-  else
-    chamfer_dir_body<2, true>(blockIdx.y, m, n, xyz2, xyz1, dist2, idx2, list2, count + b);
-}
-
-int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count,
-                        cudaStream_t s) {
-  const int big = n > m ? n : m;
-  dim3 grid((big + kChThreads * 2 - 1) / (kChThreads * 2), b, 2);
-  chamfer_rest_kernel<<<grid, kChThreads, 0, s>>>(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, list1, list2, count);
-  count_launch();
-  return launch_status();
+  chamfer_dir_body<R, false>(blockIdx.x, blockIdx.y, n, m, xyz, xyz2, dist, idx, nullptr, nullptr);
 }
 
 int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2, float *dist, int *idx,
@@ -135,6 +113,36 @@ int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2,
     }
     count_launch();
   }
+  return launch_status();
+}
+
+// The left-over pass of the grid path, both directions in one launch.  plan[kPlanNRest] lists (direction * b +
+// cloud) whose left-over points are finished here (clouds handed over wholesale to the fused kernels are not
+// listed); a 1-D grid strides over (list, chunk of 2*256 queries) and leaves at once when there is none.
+__global__ void __launch_bounds__(kChThreads)
+chamfer_rest_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                    float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
+                    int *__restrict__ idx2, const int *__restrict__ list1, const int *__restrict__ list2,
+                    const int *__restrict__ count, const int *__restrict__ plan) {
+  const int nrest = __ldg(plan + kPlanNRest);
+  if (nrest == 0) return;
+  const int big = n > m ? n : m;
+  const int chunks = (big + kChThreads * 2 - 1) / (kChThreads * 2);
+  for (long long w = blockIdx.x; w < (long long)nrest * chunks; w += gridDim.x) {
+    const int e = __ldg(plan + kPlanMap + b + (int)(w / chunks)), chunk = (int)(w % chunks);
+    if (e < b)
+      chamfer_dir_body<2, true>(chunk, e, n, m, xyz1, xyz2, dist1, idx1, list1, count);
+    else
+      chamfer_dir_body<2, true>(chunk, e - b, m, n, xyz2, xyz1, dist2, idx2, list2, count + b);
+  }
+}
+
+int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, const int *plan,
+                        cudaStream_t s) {
+  chamfer_rest_kernel<<<kNumSMs * 4, kChThreads, 0, s>>>(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, list1, list2,
+                                                         count, plan);
+  count_launch();
   return launch_status();
 }
 

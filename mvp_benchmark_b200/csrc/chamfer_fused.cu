@@ -123,23 +123,51 @@ struct PairSmem {
   uint64_t bar[2];
 };
 
-// grid: x = row tile, y = column split, z = cloud.  WARPS warps per CTA, TM = kBlk * WARPS rows per tile.
-template <int WARPS>
+// A work item is (row tile, column split, cloud): WARPS warps, TM = kBlk * WARPS rows per tile.
+//   plan == nullptr: grid (row tiles, column splits, b), one item per CTA.
+//   plan != nullptr: the fall-back of the grid path (chamfer_grid.cu).  plan[kPlanNFlag] clouds, listed in
+//     plan + kPlanMap, were handed over to brute force; a 1-D grid of resident CTAs strides over their items and
+//     leaves at once when there are none (the normal case).
+template <int WARPS, bool kPlan>
 __global__ void __launch_bounds__(WARPS * 32, WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4))
-chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *__restrict__ xyz1,
-                    const float *__restrict__ xyz2, u64 *__restrict__ rowkey, u64 *__restrict__ colkey) {
+chamfer_pair_kernel(int n, int m, int tiles_x, int split, int tiles_per_cta, int use_tma,
+                    const float *__restrict__ xyz1, const float *__restrict__ xyz2, u64 *__restrict__ rowkey,
+                    u64 *__restrict__ colkey, const int *__restrict__ plan) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PairSmem<WARPS> &S = *reinterpret_cast<PairSmem<WARPS> *>(smem_raw);
   constexpr int T = WARPS * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.z;
+  const float inf = __int_as_float(0x7f800000);
+  const int per_cloud = tiles_x * split;
+  long long nwork, work, stride;
+  if (kPlan) {
+    nwork = (long long)__ldg(plan + kPlanNFlag) * per_cloud;
+    work = blockIdx.x;
+    stride = gridDim.x;
+    if (work >= nwork) return;
+  } else {
+    work = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    nwork = work + 1;
+    stride = 1;
+  }
+  if (use_tma && tid == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t tt = 0;  // tiles fetched by TMA so far in this CTA: buffer = tt & 1, mbarrier parity = (tt >> 1) & 1
+
+  for (; work < nwork; work += stride) {
+  const int slot = (int)(work / per_cloud), rem = (int)(work % per_cloud);
+  const int b = kPlan ? __ldg(plan + kPlanMap + slot) : slot;
+  const int bx = rem % tiles_x, by = rem / tiles_x;
   const float *A = xyz1 + (size_t)b * n * 3;
   const float *Bc = xyz2 + (size_t)b * m * 3;
-  const int row0 = blockIdx.x * (WARPS * kBlk) + warp * kBlk;  // first row of this warp's kBlk-row block
-  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int row0 = bx * (WARPS * kBlk) + warp * kBlk;  // first row of this warp's kBlk-row block
+  const int tile0 = by * tiles_per_cta;
   const int ntiles_all = (m + kTN - 1) / kTN;
   const int ntiles = min(tiles_per_cta, ntiles_all - tile0);
-  const float inf = __int_as_float(0x7f800000);
 
   // ---- this thread's rows, duplicated into fp32x2 operands
   u64 qx[kRows], qy[kRows], qz[kRows];
@@ -161,20 +189,15 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
     bchunk[r] = 0;
   }
 
-  if (use_tma && tid == 0) {
-    mbar_init(&S.bar[0], 1);
-    mbar_init(&S.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue_tma = [&](int t) {  // thread 0: fetch column tile t (a FULL tile) into raw[t & 1]
-    const int buf = t & 1;
+  // thread 0: fetch column tile t (a FULL tile) into raw[seq & 1], seq = its TMA sequence number in this CTA
+  auto issue_tma = [&](int t, uint32_t seq) {
+    const int buf = seq & 1;
     mbar_expect_tx(&S.bar[buf], kTN * 12);
     tma_load_1d(S.raw[buf], Bc + (size_t)(tile0 + t) * kTN * 3, kTN * 12, &S.bar[buf]);
   };
   // A tile goes through TMA when it is full and 16-byte aligned in global memory; else plain loads.
   auto tile_by_tma = [&](int t) { return use_tma && (tile0 + t + 1) * kTN <= m; };
-  if (ntiles > 0 && tile_by_tma(0) && tid == 0) issue_tma(0);
+  if (ntiles > 0 && tile_by_tma(0) && tid == 0) issue_tma(0, tt);
 
   for (int t = 0; t < ntiles; t++) {
     const int col0 = (tile0 + t) * kTN;
@@ -182,8 +205,9 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
     float *sx = reinterpret_cast<float *>(S.x), *sy = reinterpret_cast<float *>(S.y),
           *sz = reinterpret_cast<float *>(S.z);
     if (tile_by_tma(t)) {
-      mbar_wait(&S.bar[t & 1], (t >> 1) & 1);
-      const float *raw = S.raw[t & 1];
+      mbar_wait(&S.bar[tt & 1], (tt >> 1) & 1);
+      const float *raw = S.raw[tt & 1];
+      tt++;
       for (int j = tid; j < kTN; j += T) {
         sx[j] = raw[j * 3 + 0];
         sy[j] = raw[j * 3 + 1];
@@ -204,7 +228,7 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
       }
     }
     __syncthreads();
-    if (t + 1 < ntiles && tile_by_tma(t + 1) && tid == 0) issue_tma(t + 1);  // overlaps the sweep below
+    if (t + 1 < ntiles && tile_by_tma(t + 1) && tid == 0) issue_tma(t + 1, tt);  // overlaps the sweep below
 
     // ---- sweep: kTN/kBlk chunks of kBlk columns, kCps columns per step
     const int cols_here = min(kTN, m - col0);
@@ -264,7 +288,7 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
       u64 k = ~0ull;
 #pragma unroll
       for (int w = 0; w < WARPS; w++) {
-        const u64 cand = ((u64)S.wmin[w][j] << 32) | (unsigned)((blockIdx.x * WARPS + w));
+        const u64 cand = ((u64)S.wmin[w][j] << 32) | (unsigned)((bx * WARPS + w));
         k = cand < k ? cand : k;
       }
       atomicMin(colkey + (size_t)b * m + col0 + j, k);
@@ -279,57 +303,71 @@ chamfer_pair_kernel(int n, int m, int tiles_per_cta, int use_tma, const float *_
     if (i < n && ntiles > 0)
       atomicMin(rowkey + (size_t)b * n + i, ((u64)__float_as_uint(best[r]) << 32) | (unsigned)bchunk[r]);
   }
+  if (kPlan) __syncthreads();  // the next work item re-stages S.x/y/z and rewrites S.wmin
+  }  // work items
 }
 
-// One warp per point p of cloud P (np points): key = (bits(d) << 32) | block.  The kBlk points of cloud Q in that
-// block are re-evaluated, kBlk/32 consecutive candidates per lane (128-bit loads when the block is whole and
-// 16-byte aligned), and the first one whose distance to p has exactly those bits is the answer.
+// One warp per point p (both directions in one launch: the b*n points of xyz1 against xyz2, then the b*m points of
+// xyz2 against xyz1): key = (bits(d) << 32) | block.  The kBlk points of the other cloud in that block are
+// re-evaluated, kBlk/32 consecutive candidates per lane (128-bit loads when the block is whole and 16-byte
+// aligned), and the first one whose distance to p has exactly those bits is the answer.
+//   grid: x strides over the n + m points of a cloud pair (8 per CTA), y over the clouds.
+//   plan == nullptr: all b clouds.   plan != nullptr: only the clouds listed in the plan (see chamfer_pair_kernel).
 __global__ void __launch_bounds__(256)
-chamfer_resolve_kernel(long long total, int np, int nq, int vec_ok, const float *__restrict__ P,
-                       const float *__restrict__ Q, const u64 *__restrict__ key, float *__restrict__ dist,
-                       int *__restrict__ idx) {
+chamfer_resolve_kernel(int b, int n, int m, int vec1, int vec2, const float *__restrict__ xyz1,
+                       const float *__restrict__ xyz2, const u64 *__restrict__ rowkey, const u64 *__restrict__ colkey,
+                       float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
+                       int *__restrict__ idx2, const int *__restrict__ plan) {
   constexpr int PER = kBlk / 32;  // candidates per lane
-  const int lane = threadIdx.x & 31;
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (wid >= total) return;
-  const long long cloud = wid / np;
-  const u64 k = __ldg(key + wid);
-  const uint32_t bits = (uint32_t)(k >> 32);
-  const int base = (int)(uint32_t)k * kBlk;
-  const float px = __ldg(P + wid * 3 + 0), py = __ldg(P + wid * 3 + 1), pz = __ldg(P + wid * 3 + 2);
-  const float *q = Q + ((size_t)cloud * nq + base + lane * PER) * 3;
-  float c[PER * 3];
-  if (vec_ok && base + kBlk <= nq) {
-    const float4 *q4 = reinterpret_cast<const float4 *>(q);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int clouds = plan ? __ldg(plan + kPlanNFlag) : b;
+  for (int slot = blockIdx.y; slot < clouds; slot += gridDim.y) {
+  const long long cloud = plan ? __ldg(plan + kPlanMap + slot) : slot;
+  for (int i = blockIdx.x * 8 + warp; i < n + m; i += gridDim.x * 8) {
+    const bool first_dir = i < n;
+    const int np = first_dir ? n : m, nq = first_dir ? m : n;
+    const int vec_ok = first_dir ? vec2 : vec1;  // alignment of the cloud the candidates come from
+    const float *P = first_dir ? xyz1 : xyz2, *Q = first_dir ? xyz2 : xyz1;
+    const long long wid = cloud * np + (first_dir ? i : i - n);
+    const u64 k = __ldg((first_dir ? rowkey : colkey) + wid);
+    const uint32_t bits = (uint32_t)(k >> 32);
+    const int base = (int)(uint32_t)k * kBlk;
+    const float px = __ldg(P + wid * 3 + 0), py = __ldg(P + wid * 3 + 1), pz = __ldg(P + wid * 3 + 2);
+    const float *q = Q + ((size_t)cloud * nq + base + lane * PER) * 3;
+    float c[PER * 3];
+    if (vec_ok && base + kBlk <= nq) {
+      const float4 *q4 = reinterpret_cast<const float4 *>(q);
 #pragma unroll
-    for (int v = 0; v < PER * 3 / 4; v++) {
-      const float4 t = __ldg(q4 + v);
-      c[v * 4 + 0] = t.x;
-      c[v * 4 + 1] = t.y;
-      c[v * 4 + 2] = t.z;
-      c[v * 4 + 3] = t.w;
+      for (int v = 0; v < PER * 3 / 4; v++) {
+        const float4 t = __ldg(q4 + v);
+        c[v * 4 + 0] = t.x;
+        c[v * 4 + 1] = t.y;
+        c[v * 4 + 2] = t.z;
+        c[v * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < PER; v++) {
+        const bool ok = base + lane * PER + v < nq;
+        c[v * 3 + 0] = ok ? __ldg(q + v * 3 + 0) : kPadCol;
+        c[v * 3 + 1] = ok ? __ldg(q + v * 3 + 1) : kPadCol;
+        c[v * 3 + 2] = ok ? __ldg(q + v * 3 + 2) : kPadCol;
+      }
     }
-  } else {
+    int first = PER;
 #pragma unroll
-    for (int v = 0; v < PER; v++) {
-      const bool ok = base + lane * PER + v < nq;
-      c[v * 3 + 0] = ok ? __ldg(q + v * 3 + 0) : kPadCol;
-      c[v * 3 + 1] = ok ? __ldg(q + v * 3 + 1) : kPadCol;
-      c[v * 3 + 2] = ok ? __ldg(q + v * 3 + 2) : kPadCol;
+    for (int v = PER - 1; v >= 0; v--) {
+      const float d = sqdist(c[v * 3 + 0] - px, c[v * 3 + 1] - py, c[v * 3 + 2] - pz);
+      if (__float_as_uint(d) == bits) first = v;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, first < PER);
+    const int src = mask ? __ffs(mask) - 1 : 0;
+    const int v = __shfl_sync(0xffffffffu, first, src);
+    if (lane == 0) {
+      (first_dir ? dist1 : dist2)[wid] = __uint_as_float(bits);
+      (first_dir ? idx1 : idx2)[wid] = mask ? base + src * PER + v : base;
     }
   }
-  int first = PER;
-#pragma unroll
-  for (int v = PER - 1; v >= 0; v--) {
-    const float d = sqdist(c[v * 3 + 0] - px, c[v * 3 + 1] - py, c[v * 3 + 2] - pz);
-    if (__float_as_uint(d) == bits) first = v;
-  }
-  const unsigned mask = __ballot_sync(0xffffffffu, first < PER);
-  const int src = mask ? __ffs(mask) - 1 : 0;
-  const int v = __shfl_sync(0xffffffffu, first, src);
-  if (lane == 0) {
-    dist[wid] = __uint_as_float(bits);
-    idx[wid] = mask ? base + src * PER + v : base;
   }
 }
 
@@ -340,59 +378,90 @@ bool chamfer_fused_supported(int b, int n, int m) {
 
 size_t chamfer_fused_workspace_bytes(int b, int n, int m) { return sizeof(u64) * (size_t)b * ((size_t)n + m); }
 
+struct PairShape {
+  int warps, tiles_per_cta, split, tiles_x;
+};
+
+// Tile shape: the largest row tile that still yields >= 4 CTAs per SM worth of tiles, then split the column sweep so
+// that the tail of the last wave is short.
+static PairShape pair_shape(int b, int n, int m) {
+  const int ntiles = (m + kTN - 1) / kTN;
+  auto ctas = [&](int warps, int split) { return (long long)b * ((n + warps * kBlk - 1) / (warps * kBlk)) * split; };
+  PairShape p;
+  p.warps = 8;
+  while (p.warps > 2 && ctas(p.warps, ntiles) < 4LL * kNumSMs) p.warps >>= 1;
+  p.tiles_per_cta = ntiles;
+  while (p.tiles_per_cta > 1 && ctas(p.warps, (ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta) < 12LL * kNumSMs)
+    p.tiles_per_cta = (p.tiles_per_cta + 1) / 2;
+  p.split = (ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.tiles_x = (n + p.warps * kBlk - 1) / (p.warps * kBlk);
+  return p;
+}
+
 template <int WARPS>
-static int pair_launch(int b, int n, int m, int split, int tiles_per_cta, int use_tma, const float *xyz1,
-                       const float *xyz2, u64 *rowkey, u64 *colkey, cudaStream_t s) {
+static int pair_launch(int b, int n, int m, const PairShape &sh, int use_tma, const float *xyz1, const float *xyz2,
+                       u64 *rowkey, u64 *colkey, const int *plan, cudaStream_t s) {
   const size_t smem = sizeof(PairSmem<WARPS>);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid((n + WARPS * kBlk - 1) / (WARPS * kBlk), split, b);
-  chamfer_pair_kernel<WARPS><<<grid, WARPS * 32, smem, s>>>(n, m, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey);
+  // plan-driven: one wave of resident CTAs striding over the handed-over clouds' tiles
+  const int resident = kNumSMs * (WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4));
+  const long long items = (long long)b * sh.tiles_x * sh.split;
+  if (plan)
+    chamfer_pair_kernel<WARPS, true><<<(unsigned)std::min<long long>(items, resident), WARPS * 32, smem, s>>>(
+        n, m, sh.tiles_x, sh.split, sh.tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, plan);
+  else
+    chamfer_pair_kernel<WARPS, false><<<dim3(sh.tiles_x, sh.split, b), WARPS * 32, smem, s>>>(
+        n, m, sh.tiles_x, sh.split, sh.tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, plan);
+  count_launch();
+  return launch_status();
+}
+
+// plan == nullptr: every cloud.  plan != nullptr (device memory, written by chamfer_grid_query_kernel's last CTA):
+// only the clouds it lists; every kernel leaves at once when it lists none.
+int chamfer_fused_launch_plan(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                              int *idx1, int *idx2, void *ws, size_t ws_bytes, const int *plan, cudaStream_t s) {
+  if (ws_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
+  u64 *rowkey = reinterpret_cast<u64 *>(ws);
+  u64 *colkey = rowkey + (size_t)b * n;
+  if (!plan) {  // (plan-driven: chamfer_grid_build_kernel has set the keys)
+    cudaError_t e = cudaMemsetAsync(ws, 0xff, chamfer_fused_workspace_bytes(b, n, m), s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const PairShape sh = pair_shape(b, n, m);
+  // bulk TMA needs 16-byte aligned sources: tiles start at multiples of 1024 points (12 KB), clouds at
+  // multiples of m*12 bytes
+  const int use_tma = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
+  int rc;
+  if (sh.warps == 8) rc = pair_launch<8>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
+  else if (sh.warps == 4) rc = pair_launch<4>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
+  else rc = pair_launch<2>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
+  if (rc) return rc;
+
+  const int vec2 = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
+  const int vec1 = ((reinterpret_cast<uintptr_t>(xyz1) & 15) == 0 && (n % 4) == 0) ? 1 : 0;
+  const long long chunks = ((long long)n + m + 7) / 8;
+  dim3 rgrid((unsigned)std::min<long long>(chunks, 1 << 20), b);
+  if (plan) {  // about one wave of CTAs, leaving at once when nothing was handed over
+    const int gy = std::min(b, 16);
+    rgrid = dim3((unsigned)std::min<long long>(chunks, (kNumSMs * 8 + gy - 1) / gy), gy);
+  }
+  chamfer_resolve_kernel<<<rgrid, 256, 0, s>>>(b, n, m, vec1, vec2, xyz1, xyz2, rowkey, colkey, dist1, dist2, idx1, idx2,
+                                               plan);
   count_launch();
   return launch_status();
 }
 
 int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
                          int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
-  if (ws_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
-  u64 *rowkey = reinterpret_cast<u64 *>(ws);
-  u64 *colkey = rowkey + (size_t)b * n;
-  cudaError_t e = cudaMemsetAsync(ws, 0xff, chamfer_fused_workspace_bytes(b, n, m), s);
-  if (e != cudaSuccess) return (int)e;
-
-  // Tile shape: the largest row tile that still yields >= 4 CTAs per SM worth of tiles, then split the column
-  // sweep so that the tail of the last wave is short.
-  const int ntiles = (m + kTN - 1) / kTN;
-  auto ctas = [&](int warps, int split) { return (long long)b * ((n + warps * kBlk - 1) / (warps * kBlk)) * split; };
-  int warps = 8;
-  while (warps > 2 && ctas(warps, ntiles) < 4LL * kNumSMs) warps >>= 1;
-  int tiles_per_cta = ntiles;
-  while (tiles_per_cta > 1 && ctas(warps, (ntiles + tiles_per_cta - 1) / tiles_per_cta) < 12LL * kNumSMs)
-    tiles_per_cta = (tiles_per_cta + 1) / 2;
-  const int split = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
-  // bulk TMA needs 16-byte aligned sources: tiles start at multiples of 1024 points (12 KB), clouds at
-  // multiples of m*12 bytes
-  const int use_tma = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
-  int rc;
-  if (warps == 8) rc = pair_launch<8>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
-  else if (warps == 4) rc = pair_launch<4>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
-  else rc = pair_launch<2>(b, n, m, split, tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, s);
-  if (rc) return rc;
-
-  const long long t1 = (long long)b * n, t2 = (long long)b * m;
-  const int vec2 = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
-  const int vec1 = ((reinterpret_cast<uintptr_t>(xyz1) & 15) == 0 && (n % 4) == 0) ? 1 : 0;
-  chamfer_resolve_kernel<<<(unsigned)((t1 * 32 + 255) / 256), 256, 0, s>>>(t1, n, m, vec2, xyz1, xyz2, rowkey, dist1,
-                                                                            idx1);
-  chamfer_resolve_kernel<<<(unsigned)((t2 * 32 + 255) / 256), 256, 0, s>>>(t2, m, n, vec1, xyz2, xyz1, colkey, dist2,
-                                                                            idx2);
-  count_launch(2);
-  return launch_status();
+  return chamfer_fused_launch_plan(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, ws, ws_bytes, nullptr, s);
 }
 
 }  // namespace mvp

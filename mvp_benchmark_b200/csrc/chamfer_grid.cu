@@ -23,12 +23,16 @@
 // Degenerate inputs (non-finite coordinates, zero or astronomically large extent) mark the grid invalid; all
 // queries against it go to the left-over list, i.e. the brute-force path and its semantics.
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace mvp {
 
 constexpr int kGridThreads = 1024;   // build CTA
 constexpr int kGridMaxCells = 32768; // shared-memory histogram: 128 KB
-constexpr int kGridQThreads = 128;   // query CTA
+#ifndef MVP_GRID_QTHREADS
+#define MVP_GRID_QTHREADS 128
+#endif
+constexpr int kGridQThreads = MVP_GRID_QTHREADS;  // query CTA
 #ifndef MVP_GRID_PPC
 #define MVP_GRID_PPC 2               // target points per cell
 #endif
@@ -36,26 +40,17 @@ constexpr int kGridQThreads = 128;   // query CTA
 #define MVP_GRID_MAXRING 3
 #endif
 #ifndef MVP_GRID_BUDGET
-#define MVP_GRID_BUDGET 1536         // candidate evaluations per query before it gives up
+#define MVP_GRID_BUDGET 512          // candidate evaluations per query before it gives up
 #endif
-
-struct __align__(16) GridHdr {
-  float lo[3];
-  float inv_s;
-  float s;
-  int g[3];
-  int ncell;
-  int valid;
-  int pad[6];
-};
-static_assert(sizeof(GridHdr) == 64, "GridHdr layout");
 
 struct GridWs {  // carved out of the caller's workspace by grid_plan()
   GridHdr *hdr;        // [2][b]
   int *count;          // [2][b]  left-over list lengths
+  int *plan;           // kPlan* words (common.cuh): ticket, nflag, nrest, b cloud ids, 2b list ids
   int *start[2];       // [b][cap_side + 1]
   float4 *sorted[2];   // [b][n] / [b][m]
   int *list[2];        // [b][n] / [b][m]
+  unsigned long long *key[2];  // the fused kernels' row / column keys: all-ones here, used only on hand-over
   int cap[2];
 };
 
@@ -81,6 +76,7 @@ static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
   t.cap[1] = cap1;
   t.hdr = reinterpret_cast<GridHdr *>(take(sizeof(GridHdr) * 2 * (size_t)b));
   t.count = reinterpret_cast<int *>(take(sizeof(int) * 2 * (size_t)b));
+  t.plan = reinterpret_cast<int *>(take(sizeof(int) * (kPlanMap + 3 * (size_t)b)));
   t.start[0] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap0 + 1)));
   t.start[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap1 + 1)));
   t.sorted[0] = reinterpret_cast<float4 *>(take(sizeof(float4) * (size_t)b * n));
@@ -89,11 +85,6 @@ static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
   t.list[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * m));
   if (w) *w = t;
   return off;
-}
-
-__device__ __forceinline__ int cell_coord(float u, int g) {
-  // floor + clamp in float first: u may be far outside the int range for a query outside the grid
-  return (int)fminf(fmaxf(floorf(u), 0.f), (float)(g - 1));
 }
 
 // ------------------------------------------------------------------------------------------------ build
@@ -151,54 +142,7 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
       }
       fin &= s_fin[w];
     }
-    GridHdr h;
-    float ex[3], emax = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      ex[a] = hi[a] - lo[a];
-      emax = fmaxf(emax, ex[a]);
-      h.lo[a] = lo[a];
-    }
-    h.valid = (fin && emax > 0.f && emax < 1e18f) ? 1 : 0;
-    h.g[0] = h.g[1] = h.g[2] = 1;
-    h.s = 1.f;
-    h.inv_s = 1.f;
-    if (!h.valid) {
-      h.lo[0] = h.lo[1] = h.lo[2] = 0.f;
-    } else {
-      // isotropic cell side: start from the volume heuristic (thin extents padded), grow until <= cap cells
-      float vol = 1.f;
-#pragma unroll
-      for (int a = 0; a < 3; a++) vol *= fmaxf(ex[a], emax * 1e-3f) / emax;  // relative: no overflow
-      float s = emax * cbrtf(vol / (float)cap);
-      for (int it = 0; it < 400; it++) {
-        float cells = 1.f;
-#pragma unroll
-        for (int a = 0; a < 3; a++) cells *= floorf(ex[a] / s) + 1.f;
-        if (cells <= (float)cap) break;
-        s *= 1.04f;
-      }
-      const float inv_s = 1.0f / s;
-      long long cells = 1;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        // one more cell than floor(extent / s): the largest coordinate never needs the clamp by more than rounding
-        float gf = floorf(ex[a] * inv_s) + 1.f;
-        h.g[a] = (int)fminf(gf, (float)cap);
-        cells *= h.g[a];
-      }
-      if (cells > cap || !(inv_s > 0.f) || !(inv_s < 3.0e38f)) {  // pathological rounding: fall back
-        h.valid = 0;
-        h.g[0] = h.g[1] = h.g[2] = 1;
-        h.lo[0] = h.lo[1] = h.lo[2] = 0.f;
-      } else {
-        h.s = s;
-        h.inv_s = inv_s;
-      }
-    }
-    h.ncell = h.g[0] * h.g[1] * h.g[2];
-#pragma unroll
-    for (int a = 0; a < 6; a++) h.pad[a] = 0;
+    const GridHdr h = grid_header(lo, hi, fin, cap);
     s_hdr = h;
     W.hdr[side * b + cloud] = h;
     W.count[side * b + cloud] = 0;
@@ -255,6 +199,10 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
   }
   if (tid == 0) start[ncell] = np;
   __syncthreads();
+  {  // keys of the fused brute-force kernels, in case this cloud pair is handed over to them
+    unsigned long long *key = (side ? W.key[1] : W.key[0]) + (size_t)cloud * np;
+    for (int i = tid; i < np; i += kGridThreads) key[i] = ~0ull;
+  }
 
   // ---- pass 3: scatter (order inside a cell is arbitrary; the query's tie rule is explicit)
   float4 *S = (side ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * np;
@@ -271,7 +219,7 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
                           int *__restrict__ idx1, int *__restrict__ idx2) {
   const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
   const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
-  if (t >= total) return;
+  if (t < total) {
   const int dir = t >= total1 ? 1 : 0;       // 0: points of xyz1 against xyz2's grid; 1: the other way round
   const long long pi = dir ? t - total1 : t;
   const int nq = dir ? m : n, nt = dir ? n : m;
@@ -304,8 +252,15 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
     const float sly = 1e-4f + 1e-6f * (fabsf(uy) + (float)gy);
     const float slz = 1e-4f + 1e-6f * (fabsf(uz) + (float)gz);
     const float s2 = s * s * (1.f - 1e-5f);  // (cells -> squared distance), rounded DOWN generously
-    // a query astronomically far from the grid (or with an overflowing cell coordinate) cannot be pruned
-    int budget = (fabsf(ux) < 1e6f && fabsf(uy) < 1e6f && fabsf(uz) < 1e6f) ? MVP_GRID_BUDGET : -1;
+    // A query more than kMaxRing + 1 cells outside the grid cannot finish: its best distance stays above the
+    // lateral extent of the largest cube (ext below).  Also catches overflowing / non-finite cell coordinates.
+    const float out = fmaxf(fmaxf(fmaxf(-ux, ux - (float)gx), fmaxf(-uy, uy - (float)gy)), fmaxf(-uz, uz - (float)gz));
+    const bool finite = fabsf(ux) + fabsf(uy) + fabsf(uz) < 3.0e38f;  // false for NaN / inf
+#ifdef MVP_GRID_NOBAIL
+    int budget = MVP_GRID_BUDGET;
+#else
+    int budget = (finite && out <= (float)(MVP_GRID_MAXRING + 1)) ? MVP_GRID_BUDGET : -1;
+#endif
 
     // distance (in cells, >= 0, conservative) from coordinate u to the slab of cell c
     auto gap = [](float u, int c, float slack) {
@@ -321,14 +276,16 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
       for (int i = a; i < e; i++) {
         const float4 q = __ldg(T + i);
         const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
-        const int qi = __float_as_int(q.w);
-        if (d < best || (d == best && qi < bi)) {
-          best = d;
-          bi = qi;
+        if (d <= best) {  // rare after the first few candidates
+          const int qi = __float_as_int(q.w);
+          if (d < best || qi < bi) {
+            best = d;
+            bi = qi;
+          }
         }
       }
     };
-    // cells [x0, x1] of row (yy, zz), clipped at both ends by the per-cell bound
+    // cells [x0, x1] of row (yy, zz), clipped at both ends by the per-cell bound (rings >= 2 only)
     auto row = [&](int x0, int x1, int yy, int zz, float lbyz) {
       x0 = max(x0, 0);
       x1 = min(x1, gx - 1);
@@ -346,24 +303,51 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
     };
 
     for (int r = 1; r <= MVP_GRID_MAXRING && !done && budget >= 0; r++) {
-      if (r == 1) row(cx - 1, cx + 1, cy, cz, 0.f);  // the centre row first: a good `best` prunes the rest
-      for (int dz = -r; dz <= r && budget >= 0; dz++) {
-        const int zz = cz + dz;
-        if (zz < 0 || zz >= gz) continue;
-        const float gzz = gap(uz, zz, slz);
-        if (gzz * gzz * s2 > best) continue;
-        for (int dy = -r; dy <= r; dy++) {
-          const int yy = cy + dy;
-          if (yy < 0 || yy >= gy) continue;
-          const float gyy = gap(uy, yy, sly);
-          const float lbyz = fmaf(gyy, gyy, gzz * gzz);
-          if (lbyz * s2 > best) continue;
-          const bool shell = (dz == -r || dz == r || dy == -r || dy == r);
-          if (shell) {
-            row(cx - r, cx + r, yy, zz, lbyz);
-          } else if (r > 1) {  // interior row: only its two new end cells
-            row(cx - r, cx - r, yy, zz, lbyz);
-            row(cx + r, cx + r, yy, zz, lbyz);
+      if (r == 1) {
+        // ---- the 3x3x3 cube, unrolled: per-axis squared gaps of the two outer slabs once (inf = outside the
+        // grid), the centre row first so that a good `best` prunes the other eight
+        float gxs[3], gys[3], gzs[3];
+        gxs[1] = gys[1] = gzs[1] = 0.f;
+        { const float g = gap(ux, cx - 1, slx); gxs[0] = cx > 0 ? g * g : inf; }
+        { const float g = gap(ux, cx + 1, slx); gxs[2] = cx + 1 < gx ? g * g : inf; }
+        { const float g = gap(uy, cy - 1, sly); gys[0] = cy > 0 ? g * g : inf; }
+        { const float g = gap(uy, cy + 1, sly); gys[2] = cy + 1 < gy ? g * g : inf; }
+        { const float g = gap(uz, cz - 1, slz); gzs[0] = cz > 0 ? g * g : inf; }
+        { const float g = gap(uz, cz + 1, slz); gzs[2] = cz + 1 < gz ? g * g : inf; }
+        const int xlo = cx > 0 ? cx - 1 : cx, xhi = cx + 1 < gx ? cx + 1 : cx;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+          // visiting order: centre, the four face neighbours, the four diagonal rows
+          constexpr int oy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+          constexpr int oz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+          const float lbyz = gys[oy[t] + 1] + gzs[oz[t] + 1];
+          if (lbyz * s2 > best) continue;  // also true for rows outside the grid (inf) once best is finite ...
+          const int yy = cy + oy[t], zz = cz + oz[t];
+          if (yy < 0 || yy >= gy || zz < 0 || zz >= gz) continue;  // ... and this covers best == inf
+          const int x0 = (gxs[0] + lbyz) * s2 > best ? cx : xlo;
+          const int x1 = (gxs[2] + lbyz) * s2 > best ? cx : xhi;
+          const int base = (zz * gy + yy) * gx;
+          scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
+          if (budget < 0) break;
+        }
+      } else {
+        for (int dz = -r; dz <= r && budget >= 0; dz++) {
+          const int zz = cz + dz;
+          if (zz < 0 || zz >= gz) continue;
+          const float gzz = gap(uz, zz, slz);
+          if (gzz * gzz * s2 > best) continue;
+          for (int dy = -r; dy <= r; dy++) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= gy) continue;
+            const float gyy = gap(uy, yy, sly);
+            const float lbyz = fmaf(gyy, gyy, gzz * gzz);
+            if (lbyz * s2 > best) continue;
+            if (dz == -r || dz == r || dy == -r || dy == r) {
+              row(cx - r, cx + r, yy, zz, lbyz);
+            } else {  // interior row: only its two new end cells
+              row(cx - r, cx - r, yy, zz, lbyz);
+              row(cx + r, cx + r, yy, zz, lbyz);
+            }
           }
         }
       }
@@ -384,26 +368,71 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
     dist[orig] = best;
     idx[orig] = bi;
   } else {
-    const int pos = atomicAdd(W.count + dir * b + cloud, 1);
+    // append to the left-over list of (direction, cloud): one atomic per group of lanes sharing the list
+    const int li = dir * b + cloud;
+    const unsigned peers = __match_any_sync(__activemask(), li);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int pos = 0;
+    if (lane == leader) pos = atomicAdd(W.count + li, __popc(peers));
+    pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
     ((dir ? W.list[1] : W.list[0]) + (size_t)cloud * nq)[pos] = orig;
+  }
+  }  // t < total
+
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+// Decides who completes the left-over points (one small CTA; a separate launch because finding "the last CTA of
+// the query kernel" needs a device-scope fence per CTA, which measured +100 us on the query kernel).
+__global__ void __launch_bounds__(256)
+chamfer_grid_plan_kernel(int b, int n, int m, GridWs W) {
+  __shared__ int s_nflag, s_nrest;
+  if (threadIdx.x == 0) s_nflag = s_nrest = 0;
+  __syncthreads();
+  // a cloud pair with more than a quarter of its points left over is cheaper in the fused brute-force kernels
+  // (each pair evaluated once for both directions) than in the per-direction left-over pass
+  const int thresh = (int)(((long long)n + m) / 4);
+  for (int c = threadIdx.x; c < b; c += 256) {
+    const int l0 = W.count[c], l1 = W.count[b + c];
+    if (l0 + l1 > thresh) {
+      W.plan[kPlanMap + atomicAdd(&s_nflag, 1)] = c;
+    } else {
+      if (l0) W.plan[kPlanMap + b + atomicAdd(&s_nrest, 1)] = c;
+      if (l1) W.plan[kPlanMap + b + atomicAdd(&s_nrest, 1)] = b + c;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    W.plan[kPlanNFlag] = s_nflag;
+    W.plan[kPlanNRest] = s_nrest;
   }
 }
 
 // chamfer.cu
 int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, cudaStream_t s);
+                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, const int *plan,
+                        cudaStream_t s);
+// chamfer_fused.cu
+size_t chamfer_fused_workspace_bytes(int b, int n, int m);
+int chamfer_fused_launch_plan(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                              int *idx1, int *idx2, void *ws, size_t ws_bytes, const int *plan, cudaStream_t s);
 
 bool chamfer_grid_supported(int b, int n, int m) {
   return b > 0 && b <= 65535 && n >= 512 && m >= 512 && n <= (1 << 20) && m <= (1 << 20) &&
          (long long)b * ((long long)n + m) < (1LL << 31);
 }
 
-size_t chamfer_grid_workspace_bytes(int b, int n, int m) { return grid_plan(b, n, m, nullptr, nullptr); }
+size_t chamfer_grid_workspace_bytes(int b, int n, int m) {
+  return grid_plan(b, n, m, nullptr, nullptr) + chamfer_fused_workspace_bytes(b, n, m);  // + the hand-over's keys
+}
 
 int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
                         int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
   GridWs W;
-  if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
+  const size_t grid_bytes = grid_plan(b, n, m, ws, &W), key_bytes = chamfer_fused_workspace_bytes(b, n, m);
+  if (ws_bytes < grid_bytes + key_bytes) return MVP_ERR_WORKSPACE;
+  W.key[0] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ws) + grid_bytes);
+  W.key[1] = W.key[0] + (size_t)b * n;
   const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
   static bool configured = false;
   if (!configured) {
@@ -416,10 +445,16 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
   const long long total = (long long)b * ((long long)n + m);
   chamfer_grid_query_kernel<<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
       b, n, m, W, dist1, dist2, idx1, idx2);
-  count_launch(2);
+  chamfer_grid_plan_kernel<<<1, 256, 0, s>>>(b, n, m, W);
+  count_launch(3);
   int rc = launch_status();
   if (rc) return rc;
-  return chamfer_rest_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, W.list[0], W.list[1], W.count, s);
+  // hand-over: whole cloud pairs to the fused brute-force kernels, scattered left-over points to the tiled pass;
+  // all of these leave at once when the plan is empty
+  rc = chamfer_fused_launch_plan(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2,
+                                 reinterpret_cast<unsigned char *>(ws) + grid_bytes, key_bytes, W.plan, s);
+  if (rc) return rc;
+  return chamfer_rest_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, W.list[0], W.list[1], W.count, W.plan, s);
 }
 
 }  // namespace mvp

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Tuning aid: builds libmvp_ops variants of the Chamfer pair kernel (macro knobs in csrc/chamfer_fused.cu) into
-gpurun_build/ (here, no GPU needed) and, on the GPU box, times mvp_chamfer_forward of each at B=32 N=M=16384.
+"""Tuning aid: builds libmvp_ops variants of the Chamfer kernels (macro knobs in csrc/chamfer_fused.cu and
+csrc/chamfer_grid.cu) into gpurun_build/ (here, no GPU needed) and, on the GPU box, times mvp_chamfer_forward of
+each at B=32 N=M=16384 (and at the VRCNet size B=64 N=M=2048 for the grid set).
 
-    python tools/pair_variants.py build          # in the build container
-    gpurun -- 'python tools/pair_variants.py run'
+    python tools/pair_variants.py build [pair|grid]         # in the build container
+    gpurun -- 'python tools/pair_variants.py run [pair|grid]'
 """
 import ctypes
 import os
@@ -13,6 +14,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_build")
 CSRC = os.path.join(ROOT, "mvp_benchmark_b200", "csrc")
+GRID_VARIANTS = {
+    "base": [],
+    "noplan": ["-DMVP_GRID_NOPLAN"],
+    "nobail": ["-DMVP_GRID_NOBAIL"],
+    "noplan_nobail": ["-DMVP_GRID_NOPLAN", "-DMVP_GRID_NOBAIL"],
+    "budget1536": ["-DMVP_GRID_BUDGET=1536"],
+    "q256": ["-DMVP_GRID_QTHREADS=256"],
+}
+SETS = {}
 VARIANTS = {
     "base": [],
     "minb3": ["-DMVP_PAIR_MINB=3"],
@@ -25,33 +35,43 @@ VARIANTS = {
 }
 
 
-def build():
+SETS.update({"pair": VARIANTS, "grid": GRID_VARIANTS})
+SYMBOL = {"pair": "chamfer_pair_kernelILi8", "grid": "chamfer_grid_query_kernel"}
+SHAPES = {"pair": [(32, 16384, 16384)], "grid": [(32, 16384, 16384), (64, 2048, 2048)]}
+
+
+def build(which):
     os.makedirs(OUT, exist_ok=True)
-    for name, flags in VARIANTS.items():
-        lib = os.path.join(OUT, f"libvar_{name}.so")
+    for name, flags in SETS[which].items():
+        lib = os.path.join(OUT, f"libvar_{which}_{name}.so")
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
                "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-shared", "-Xptxas", "-v"] + flags + \
-              [os.path.join(CSRC, f) for f in ("capi.cu", "chamfer.cu", "chamfer_fused.cu")] + ["-o", lib]
+              [os.path.join(CSRC, f) for f in ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu")] + ["-o", lib]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             print(name, "FAILED\n", r.stderr[-2000:])
             continue
         lines = (r.stdout + r.stderr).splitlines()
         for i, l in enumerate(lines):
-            if "chamfer_pair_kernelILi8" in l:
+            if SYMBOL[which] in l and "Compiling" in l:
                 print(name, "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
 
 
-def run():
+def run(which):
+    for shape in SHAPES[which]:
+        print("shape", shape, flush=True)
+        run_shape(which, *shape)
+
+
+def run_shape(which, b, n, m):
     import torch
     dev = torch.device("cuda:0")
-    b, n, m = 32, 16384, 16384
     g = torch.Generator(device=dev)
     g.manual_seed(0)
     x1, x2 = torch.rand(b, n, 3, device=dev, generator=g), torch.rand(b, m, 3, device=dev, generator=g)
     ref = None
-    for name in VARIANTS:
-        path = os.path.join(OUT, f"libvar_{name}.so")
+    for name in SETS[which]:
+        path = os.path.join(OUT, f"libvar_{which}_{name}.so")
         if not os.path.isfile(path):
             continue
         L = ctypes.CDLL(path)
@@ -87,4 +107,5 @@ def run():
 
 
 if __name__ == "__main__":
-    build() if sys.argv[1:] == ["build"] else run()
+    which = sys.argv[2] if len(sys.argv) > 2 else "pair"
+    build(which) if sys.argv[1] == "build" else run(which)
