@@ -17,10 +17,15 @@ Numbers on the JSON line:
   e2e        the same metric through the reference-facing Python API (metrics.cd() autograd Function)
              with HOST buffers: per step pinned-host -> device copies of both clouds, forward,
              backward, and device -> pinned-host copies of dist1/dist2/idx1/idx2/gradxyz1/gradxyz2.
-  roofline   the dominant kernel (Chamfer forward), algorithmic bytes 20*B*(N+M) per forward
-              / its average duration (CUDA events inside the timed region) against the
-             measured HBM copy peak in MEASURED_PEAKS.json.  Brute-force Chamfer is FP32-issue bound,
-             not HBM bound: `roofline_fp32` reports the binding roofline.
+  roofline   the Chamfer forward (grid build + query + the hand-over kernels, which normally leave at
+             once; profiles/ holds the ncu launch list with each kernel's share), algorithmic bytes
+             20*B*(N+M) per forward / its average duration (CUDA events inside the timed
+             region) against the measured HBM copy peak in MEASURED_PEAKS.json.
+  brute_force  the same step with mvp_chamfer_forward_algo(MVP_CHAMFER_BRUTE): every one of the B*N*M
+             pairs evaluated (the north_star's tiled pairwise argmin).  That path is FP32-issue bound,
+             not HBM bound: its `roofline_fp32` reports the binding roofline.  The
+             default path is the grid-pruned exact search, bit-identical in its outputs; point-pairs/s
+             counts B*N*M per step for both, as the reference's metric does, not pairs evaluated.
   cpu_baseline  the CPU oracle (oracle/oracle.c, a port of the reference kernels' arithmetic, OpenMP
              over all host cores) on a bounded sample of the same workload.
 --impl reference: the same metric for the reference's algorithm on the host CPU cores (the oracle
@@ -39,6 +44,9 @@ if ROOT not in sys.path:
 
 B, N, M = 32, 16384, 16384
 L2_BYTES = 126 << 20
+# dram__bytes_read.sum + dram__bytes_write.sum of the forward's kernels from the ncu --set full capture summarised in
+# profiles/ (per forward, B=32 N=M=16384); None until a capture of the current kernels is committed
+TRAFFIC_BYTES = None
 METRIC = "chamfer_fwd_bwd_point_pairs_per_s"
 UNIT = "point-pairs/s"
 WORKLOAD = "chamfer_distance_fwd_bwd B=32 N=M=16384 fp32 uniform[0,1)^3 (PCN/C2 fine-output CD size)"
@@ -239,6 +247,12 @@ def run_ours(args):
                    "mvp_chamfer_forward")
         return a, c
 
+    def step_brute(k):
+        a, c = X1[k % nsets], X2[k % nsets]
+        _lib.check(L.mvp_chamfer_forward_algo(1, b, n, m, P(a), P(c), P(d1), P(d2), P(i1), P(i2), P(ws), ws.numel(),
+                                              stream), "mvp_chamfer_forward_algo(brute)")
+        return a, c
+
     def step_bwd(a, c):
         _lib.check(L.mvp_chamfer_backward(b, n, m, P(a), P(c), P(G1), P(G2), P(i1), P(i2), P(gx1), P(gx2), stream),
                    "mvp_chamfer_backward")
@@ -270,6 +284,22 @@ def run_ours(args):
     total_ms = mdist.max_over_ranks(total_ms, dev)
     ms_per_step = total_ms / steps
     value = world * pairs / (ms_per_step * 1e-3)
+
+    # ---- the same step with the brute-force forward (every pair evaluated), for the FP32-issue roofline
+    bsteps = max(3, min(steps, 20))
+    for k in range(3):
+        step_bwd(*step_brute(k))
+    bev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(bsteps)]
+    torch.cuda.synchronize()
+    for k in range(bsteps):
+        bev[k][0].record()
+        a, c = step_brute(3 + k)
+        bev[k][1].record()
+        step_bwd(a, c)
+        bev[k][2].record()
+    torch.cuda.synchronize()
+    brute_fwd_ms = sum(e[0].elapsed_time(e[1]) for e in bev) / bsteps
+    brute_ms = bev[0][0].elapsed_time(bev[-1][2]) / bsteps
 
     # ---- e2e: reference-facing Python API, host buffers in, host buffers out
     cd = metrics.cd()
@@ -316,7 +346,7 @@ def run_ours(args):
     # FP32 issue roofline: a brute-force pair costs >= 3.5 issue slots with packed fp32x2 math
     # (3 sub + 1 mul + 2 fma per TWO pairs, + 1 min per pair) on 148 SMs x 4 schedulers x 32 lanes.
     lanes_per_s = 148 * 128 * f_mhz * 1e6
-    fp32 = {"bound": "fp32_issue", "unit": "pair-evaluations/s", "achieved": pairs / (fwd_ms * 1e-3),
+    fp32 = {"bound": "fp32_issue", "unit": "pair-evaluations/s", "achieved": pairs / (brute_fwd_ms * 1e-3),
             "peak": lanes_per_s / 3.5, "peak_model": "148 SM x 128 lanes x sampled SM clock / 3.5 issue slots per pair "
             "(packed f32x2 sub/mul/fma + one min per pair; each pair evaluated once for both directions)",
             "sm_mhz_used": f_mhz}
@@ -332,12 +362,19 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "metrics.cd()(xyz1, xyz2) + autograd backward, pinned host in/out"},
         "gpu_launches": int(launches),
+        "algorithm": "forward = exact grid-pruned nearest neighbour (chamfer_grid.cu), outputs bit-identical to brute "
+                     "force; point-pairs counts B*N*M per step as the reference's metric does, not pairs evaluated",
         "kernel_ms": {"chamfer_forward": fwd_ms, "chamfer_backward": bwd_ms, "wall_ms_per_step": 1e3 * t_wall / steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": None, "kernel": "chamfer forward (both directions)", "algorithmic_bytes": fwd_bytes,
-                     "peak_source": peak_src,
-                     "note": "brute-force Chamfer is FP32-issue bound (2200 instr/byte); see roofline_fp32"},
-        "roofline_fp32": fp32,
+                     "traffic": TRAFFIC_BYTES, "kernel": "chamfer forward, both directions (chamfer_grid_build_kernel + "
+                     "chamfer_grid_query_kernel + plan + 3 hand-over kernels that leave at once; shares in "
+                     "profiles/r1_launches_bench.md)", "algorithmic_bytes": fwd_bytes, "peak_source": peak_src,
+                     "note": "latency/issue bound, not HBM bound: ~1M independent searches of ~30 candidates each; "
+                             "the working set (21 MB of sorted points) is L2-resident"},
+        "brute_force": {"value": world * pairs / (brute_ms * 1e-3), "unit": UNIT, "ms_per_step": brute_ms,
+                        "chamfer_forward_ms": brute_fwd_ms, "steps": bsteps, "roofline_fp32": fp32,
+                        "note": "mvp_chamfer_forward_algo(MVP_CHAMFER_BRUTE): all B*N*M pairs evaluated, each once for "
+                                "both directions; FP32-issue bound (2200 instr/byte)"},
         "clocks": clocks,
     }
 

@@ -91,6 +91,18 @@ int mvp_emd_forward(int b, int n, int m, const float *xyz1, const float *xyz2, f
                     float *dist, int *assignment, void *workspace, size_t workspace_bytes,
                     mvp_stream_t stream);
 
+/* The same operator with the Bid search named explicitly (tests and benchmarks; results are bit-identical):
+ *   MVP_EMD_AUTO   what mvp_emd_forward does: GRID when n <= 8192, else BRUTE;
+ *   MVP_EMD_BRUTE  every unassigned source scans all n targets each round (as the reference's Bid kernel does);
+ *   MVP_EMD_GRID   sources search a uniform grid over the targets outwards and stop when no unvisited target can
+ *                  reach their second-best value (n <= 8192; MVP_ERR_INVALID_ARGUMENT otherwise). */
+#define MVP_EMD_AUTO 0
+#define MVP_EMD_BRUTE 1
+#define MVP_EMD_GRID 2
+int mvp_emd_forward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2, float eps,
+                         int iters, float *dist, int *assignment, void *workspace, size_t workspace_bytes,
+                         mvp_stream_t stream);
+
 /* Replaces emd.backward -> emd_cuda_backward (emd.cpp:18-21, emd_cuda.cu:302-316, kernel :284-300).
  * gradxyz1 (b,n,3) is fully written (no pre-zeroing needed).  The reference returns zeros for xyz2
  * (emd_module.py:78-81); that tensor is the Python layer's business. */

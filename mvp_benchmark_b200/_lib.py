@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvp_ops.so")
+# MVP_OPS_LIB: tuning / debugging aid (tools/pair_variants.py builds alternative libraries with other macro knobs)
+LIB_PATH = os.environ.get("MVP_OPS_LIB") or os.path.join(_HERE, "libmvp_ops.so")
 
 _c_int = ctypes.c_int
 _c_float = ctypes.c_float
@@ -38,6 +39,7 @@ def _load():
         "mvp_chamfer_backward": (_c_int, [_c_int] * 3 + [_p] * 8 + [_p]),
         "mvp_emd_forward_workspace_bytes": (_c_size_t, [_c_int] * 2),
         "mvp_emd_forward": (_c_int, [_c_int] * 3 + [_p, _p, _c_float, _c_int, _p, _p, _p, _c_size_t, _p]),
+        "mvp_emd_forward_algo": (_c_int, [_c_int] * 4 + [_p, _p, _c_float, _c_int, _p, _p, _p, _c_size_t, _p]),
         "mvp_emd_backward": (_c_int, [_c_int] * 2 + [_p] * 5 + [_p]),
         "mvp_furthest_point_sampling": (_c_int, [_c_int] * 3 + [_p] * 3 + [_p]),
         "mvp_furthest_point_sampling_with_dist": (_c_int, [_c_int] * 3 + [_p] * 3 + [_p]),

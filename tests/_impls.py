@@ -128,15 +128,22 @@ class CudaImpl:
                                            self.S()), "mvp_chamfer_backward")
         return self.N(gx1, gx2)
 
-    def emd_forward(self, x1, x2, eps, iters):
+    EMD_ALGOS = {"auto": 0, "brute": 1, "grid": 2}
+
+    def emd_forward(self, x1, x2, eps, iters, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr
         a, c = self.T(x1), self.T(x2)
         b, n, _ = a.shape
         d, asg = self.E((b, n), t.float32), self.E((b, n), t.int32)
         ws = L.workspace(L.lib.mvp_emd_forward_workspace_bytes(b, n), self.dev)
         ws.fill_(0xA5)
-        L.check(L.lib.mvp_emd_forward(b, n, c.shape[1], p(a), p(c), float(eps), int(iters), p(d), p(asg), p(ws),
-                                      ws.numel(), self.S()), "mvp_emd_forward")
+        if algo == "auto":
+            rc = L.lib.mvp_emd_forward(b, n, c.shape[1], p(a), p(c), float(eps), int(iters), p(d), p(asg), p(ws),
+                                       ws.numel(), self.S())
+        else:
+            rc = L.lib.mvp_emd_forward_algo(self.EMD_ALGOS[algo], b, n, c.shape[1], p(a), p(c), float(eps), int(iters),
+                                            p(d), p(asg), p(ws), ws.numel(), self.S())
+        L.check(rc, "mvp_emd_forward")
         return self.N(d, asg)
 
     def emd_backward(self, x1, x2, g, asg):

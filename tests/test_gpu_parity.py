@@ -207,14 +207,35 @@ def test_chamfer_vs_reference_cuda_live(gpu, ref, cuda, kind, b, n, m):
                                                 ("uniform", 1, 3072, 0.005, 30), ("uniform", 2, 1024, 0.002, 1),
                                                 ("duplicates", 2, 1024, 0.005, 20), ("lattice", 1, 1024, 0.01, 40),
                                                 ("uniform", 1, 4096, 0.004, 400)])
-def test_emd_vs_oracle(gpu, cpu, kind, b, n, eps, iters):
+@pytest.mark.parametrize("algo", ["brute", "grid"])
+def test_emd_vs_oracle(gpu, cpu, kind, b, n, eps, iters, algo):
     x1, x2 = _data.cloud(kind, b, n, 31), _data.cloud(kind, b, n, 32)
-    d, a = gpu.emd_forward(x1, x2, eps, iters)
+    d, a = gpu.emd_forward(x1, x2, eps, iters, algo=algo)
     wd, wa = cpu.emd_forward(x1, x2, eps, iters)
     _cases.eq(a, wa, f"emd {kind} assignment")
     _cases.eq(d, wd, f"emd {kind} dist")
     g = np.random.default_rng(3).random((b, n), dtype=np.float32)
     _cases.eq(gpu.emd_backward(x1, x2, g, a), cpu.emd_backward(x1, x2, g, a), "emd gradxyz1")
+
+
+@pytest.mark.parametrize("kind1,kind2,b,n,eps,iters", [
+    ("uniform", "uniform", 3, 8192, 0.005, 50), ("sphere", "uniform", 2, 4096, 0.005, 60),
+    ("clustered", "uniform", 2, 2048, 0.005, 50), ("uniform", "clustered", 2, 2048, 0.005, 50),
+    ("planar", "planar", 2, 2048, 0.005, 50), ("shifted", "shifted", 2, 1024, 0.005, 30),
+    ("outliers", "uniform", 2, 2048, 0.005, 40), ("constant", "uniform", 2, 1024, 0.005, 20),
+    ("uniform", "constant", 2, 1024, 0.005, 20), ("tiny", "tiny", 1, 1024, 0.005, 20),
+    ("uniform", "uniform", 70, 1024, 0.005, 50), ("uniform", "uniform", 150, 1024, 0.002, 25),
+    ("uniform", "uniform", 2, 2048, -0.001, 10), ("lattice", "duplicates", 2, 2048, 0.01, 40)])
+def test_emd_grid_is_bit_identical_to_full_scan(gpu, kind1, kind2, b, n, eps, iters):
+    """The grid-pruned Bid search (default for n <= 8192) against the full scan, on benign and hostile
+    distributions, several cluster sizes (b = 3 -> 8 CTAs per cloud ... b = 150 -> 1) and a negative eps
+    (prices fall, so the price bound is negative)."""
+    x1, x2 = _data.cloud(kind1, b, n, 61), _data.cloud(kind2, b, n, 62)
+    wd, wa = gpu.emd_forward(x1, x2, eps, iters, algo="brute")
+    for algo in ("grid", "auto"):
+        d, a = gpu.emd_forward(x1, x2, eps, iters, algo=algo)
+        _cases.eq(a, wa, f"emd {algo} vs full scan, {kind1}/{kind2} assignment")
+        _cases.eq(d, wd, f"emd {algo} vs full scan, {kind1}/{kind2} dist")
 
 
 def test_emd_c5_shape_properties_and_reference(gpu, ref, cuda):

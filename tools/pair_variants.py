@@ -22,6 +22,15 @@ GRID_VARIANTS = {
     "budget1536": ["-DMVP_GRID_BUDGET=1536"],
     "q256": ["-DMVP_GRID_QTHREADS=256"],
 }
+EMD_VARIANTS = {
+    "base": [],
+    "fs0": ["-DMVP_EMD_FULLSCAN_EVALS=0"],
+    "fs16": ["-DMVP_EMD_FULLSCAN_EVALS=16"],
+    "fs128": ["-DMVP_EMD_FULLSCAN_EVALS=128"],
+    "fs512": ["-DMVP_EMD_FULLSCAN_EVALS=512"],
+    "ppc2": ["-DMVP_EMD_GRID_PPC=2"],
+    "ppc8": ["-DMVP_EMD_GRID_PPC=8"],
+}
 SETS = {}
 VARIANTS = {
     "base": [],
@@ -35,8 +44,8 @@ VARIANTS = {
 }
 
 
-SETS.update({"pair": VARIANTS, "grid": GRID_VARIANTS})
-SYMBOL = {"pair": "chamfer_pair_kernelILi8", "grid": "chamfer_grid_query_kernel"}
+SETS.update({"pair": VARIANTS, "grid": GRID_VARIANTS, "emd": EMD_VARIANTS})
+SYMBOL = {"pair": "chamfer_pair_kernelILi8", "grid": "chamfer_grid_query_kernel", "emd": "emd_auction_grid_kernel"}
 SHAPES = {"pair": [(32, 16384, 16384)], "grid": [(32, 16384, 16384), (64, 2048, 2048)]}
 
 
@@ -46,7 +55,8 @@ def build(which):
         lib = os.path.join(OUT, f"libvar_{which}_{name}.so")
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
                "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-shared", "-Xptxas", "-v"] + flags + \
-              [os.path.join(CSRC, f) for f in ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu")] + ["-o", lib]
+              [os.path.join(CSRC, f) for f in (("capi.cu", "emd.cu") if which == "emd" else
+                                               ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu"))] + ["-o", lib]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             print(name, "FAILED\n", r.stderr[-2000:])
@@ -57,7 +67,47 @@ def build(which):
                 print(name, "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
 
 
+def run_emd():
+    """mvp_emd_forward of every variant at (b, n, iters) points that stress the first rounds, the tail, and both."""
+    import torch
+    dev = torch.device("cuda:0")
+    ref = {}
+    for b, n, iters in [(64, 8192, 50), (32, 2048, 50), (16, 8192, 3000), (32, 2048, 3000), (64, 8192, 5)]:
+        print("shape", (b, n, iters), flush=True)
+        g = torch.Generator(device=dev)
+        g.manual_seed(0)
+        x1, x2 = torch.rand(b, n, 3, device=dev, generator=g), torch.rand(b, n, 3, device=dev, generator=g)
+        for name in SETS["emd"]:
+            path = os.path.join(OUT, f"libvar_emd_{name}.so")
+            if not os.path.isfile(path):
+                continue
+            L = ctypes.CDLL(path)
+            L.mvp_emd_forward_workspace_bytes.restype = ctypes.c_size_t
+            ws = torch.empty(L.mvp_emd_forward_workspace_bytes(b, n), dtype=torch.uint8, device=dev)
+            d, a = torch.empty(b, n, device=dev), torch.empty(b, n, device=dev, dtype=torch.int32)
+            P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+            def call():
+                rc = L.mvp_emd_forward(b, n, n, P(x1), P(x2), ctypes.c_float(0.005), iters, P(d), P(a), P(ws),
+                                       ctypes.c_size_t(ws.numel()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, rc
+            call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                call()
+            e1.record()
+            e1.synchronize()
+            key = (b, n, iters)
+            if key not in ref:
+                ref[key] = a.clone()
+            print(f"{name:10s} {e0.elapsed_time(e1) / 3:9.3f} ms  same_as_base={torch.equal(a, ref[key])}", flush=True)
+
+
 def run(which):
+    if which == "emd":
+        return run_emd()
     for shape in SHAPES[which]:
         print("shape", shape, flush=True)
         run_shape(which, *shape)
