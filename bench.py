@@ -45,8 +45,8 @@ if ROOT not in sys.path:
 B, N, M = 32, 16384, 16384
 L2_BYTES = 126 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of the forward's kernels from the ncu --set full capture summarised in
-# profiles/ (per forward, B=32 N=M=16384); None until a capture of the current kernels is committed
-TRAFFIC_BYTES = None
+# profiles/ (per forward, B=32 N=M=16384)
+TRAFFIC_BYTES = 36.9e6  # build 15.3 + 2.7 MB, query 18.9 + 0.0 MB (profiles/r1_chamfer_grid_full.md)
 METRIC = "chamfer_fwd_bwd_point_pairs_per_s"
 UNIT = "point-pairs/s"
 WORKLOAD = "chamfer_distance_fwd_bwd B=32 N=M=16384 fp32 uniform[0,1)^3 (PCN/C2 fine-output CD size)"

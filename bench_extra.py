@@ -94,6 +94,10 @@ def run(dev, hbm_gbs=None):
     entry("emd_forward_64x8192_iters50", _time(lambda: emd(e1, e2, 0.005, 50), 3, 1),
           _time(lambda: ref_cuda.emd_forward(e1, e2, 0.005, 50), 3, 1) if have_ref else None,
           64.0 * 8192 * 8192, "point-pairs/s", 32.0 * 64 * 8192)
+    e1l, e2l = e1[:16].contiguous(), e2[:16].contiguous()
+    entry("emd_forward_16x8192_iters3000", _time(lambda: emd(e1l, e2l, 0.005, 3000), 2, 1),
+          _time(lambda: ref_cuda.emd_forward(e1l, e2l, 0.005, 3000), 2, 1) if have_ref else None,
+          16.0 * 8192 * 8192, "point-pairs/s", 32.0 * 16 * 8192)
     e1s, e2s = R(32, 2048, 3), R(32, 2048, 3)
     entry("emd_forward_32x2048_iters50", _time(lambda: emd(e1s, e2s, 0.005, 50), 5, 2),
           _time(lambda: ref_cuda.emd_forward(e1s, e2s, 0.005, 50), 5, 2) if have_ref else None,

@@ -30,7 +30,9 @@ KEY_METRICS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-    "sm__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_active.avg",
     "smsp__inst_executed.sum",
@@ -43,17 +45,17 @@ KEY_METRICS = [
     "launch__block_size",
     "launch__cluster_size",
     "launch__waves_per_multiprocessor",
-    "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio",
-    "smsp__average_warp_latency_issue_stalled_barrier.ratio",
-    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
-    "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
-    "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
-    "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
-    "smsp__average_warp_latency_issue_stalled_wait.ratio",
-    "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
-    "smsp__average_warp_latency_issue_stalled_membar.ratio",
-    "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
-    "smsp__average_warp_latency_issue_stalled_branch_resolving.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
 ]
 
 
