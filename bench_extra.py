@@ -110,34 +110,52 @@ def run(dev, hbm_gbs=None):
               _time(lambda: ref_cuda.furthest_point_sample(x, mm_), 5) if have_ref else None,
               float(bb) * mm_, "selected points/s", 12.0 * bb * nn + 4.0 * bb * mm_)
 
-    # ---- bandwidth ops
-    bb, c, nn, mp = 64, 64, 3072, 15360
-    feat = torch.randn(bb, c, nn, device=dev, generator=g)
-    idx = torch.randint(0, nn, (bb, mp), device=dev, generator=g, dtype=torch.int32)
-    entry("gather_points_64x64x3072_to_15360", _time(lambda: mm.gather_points(feat, idx)),
-          _time(lambda: ref_cuda.gather_points(feat, idx)) if have_ref else None,
-          float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1))
-    go = torch.randn(bb, c, mp, device=dev, generator=g)
+    # ---- bandwidth ops: timed through the C ABI with preallocated outputs (the Python layer adds ~30 us of host
+    # work per call, which is not what a roofline fraction should measure); sizes are VRCNet's
     from mvp_benchmark_b200 import _lib
-    gp = torch.empty(bb, c, nn, device=dev)
+    L, P, S = _lib.lib, _lib.ptr, _lib.stream_of
 
-    def ours_gg():
-        _lib.check(_lib.lib.mvp_gather_points_grad(bb, c, nn, mp, _lib.ptr(go), _lib.ptr(idx), _lib.ptr(gp),
-                                                   _lib.stream_of(go)), "gather grad")
+    def gather_case(tag, bb, c, nn, mp):
+        feat = torch.randn(bb, c, nn, device=dev, generator=g)
+        idx = torch.randint(0, nn, (bb, mp), device=dev, generator=g, dtype=torch.int32)
+        out = torch.empty(bb, c, mp, device=dev)
+        go = torch.randn(bb, c, mp, device=dev, generator=g)
+        gp = torch.empty(bb, c, nn, device=dev)
+        fwd = lambda: _lib.check(L.mvp_gather_points(bb, c, nn, mp, P(feat), P(idx), P(out), S(feat)), "gather")  # noqa: E731
+        bwd = lambda: _lib.check(L.mvp_gather_points_grad(bb, c, nn, mp, P(go), P(idx), P(gp), S(go)), "gather grad")  # noqa: E731
+        entry(f"gather_points_{tag}", _time(fwd), _time(lambda: ref_cuda.gather_points(feat, idx)) if have_ref else None,
+              float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1))
+        entry(f"gather_points_grad_{tag}", _time(bwd),
+              _time(lambda: ref_cuda.gather_points_grad(go, idx, nn)) if have_ref else None,
+              float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1) + 4.0 * bb * c * nn)
 
-    entry("gather_points_grad_64x64x3072_from_15360", _time(ours_gg),
-          _time(lambda: ref_cuda.gather_points_grad(go, idx, nn)) if have_ref else None,
-          float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1) + 4.0 * bb * c * nn)
+    gather_case("64x64x3072_to_15360", 64, 64, 3072, 15360)
+    gather_case("64x128x1536_to_7680", 64, 128, 1536, 7680)
+    gather_case("64x256x768_to_3840", 64, 256, 768, 3840)
+
+    def interp_case(tag, bb, c, m_, n_):
+        f = torch.randn(bb, c, m_, device=dev, generator=g)
+        i3 = torch.randint(0, m_, (bb, n_, 3), device=dev, generator=g, dtype=torch.int32)
+        w = R(bb, n_, 3)
+        out = torch.empty(bb, c, n_, device=dev)
+        go = torch.randn(bb, c, n_, device=dev, generator=g)
+        gp = torch.empty(bb, c, m_, device=dev)
+        fwd = lambda: _lib.check(L.mvp_three_interpolate(bb, c, m_, n_, P(f), P(i3), P(w), P(out), S(f)), "interp")  # noqa: E731
+        bwd = lambda: _lib.check(L.mvp_three_interpolate_grad(bb, c, n_, m_, P(go), P(i3), P(w), P(gp), S(go)), "interp grad")  # noqa: E731
+        entry(f"three_interpolate_{tag}", _time(fwd),
+              _time(lambda: ref_cuda.three_interpolate(f, i3, w)) if have_ref else None, float(bb) * c * n_, "elements/s",
+              4.0 * bb * n_ * (2 * c + 6))
+        entry(f"three_interpolate_grad_{tag}", _time(bwd),
+              _time(lambda: ref_cuda.three_interpolate_grad(go, i3, w, m_)) if have_ref else None, float(bb) * c * n_, "elements/s",
+              4.0 * bb * n_ * (2 * c + 6) + 4.0 * bb * c * m_)
+
+    interp_case("64x128x1536_to_3072", 64, 128, 1536, 3072)
+    interp_case("64x256x768_to_1536", 64, 256, 768, 1536)
+    interp_case("64x512x384_to_768", 64, 512, 384, 768)
     u, k = R(64, 3072, 3), R(64, 1536, 3)
     entry("three_nn_64x3072_from_1536", _time(lambda: mm.three_nn(u, k)),
           _time(lambda: ref_cuda.three_nn(u, k)) if have_ref else None, 64.0 * 3072 * 1536, "point-pairs/s",
           12.0 * 64 * (3072 + 1536) + 24.0 * 64 * 3072)
-    f = torch.randn(64, 128, 1536, device=dev, generator=g)
-    i3 = torch.randint(0, 1536, (64, 3072, 3), device=dev, generator=g, dtype=torch.int32)
-    w = R(64, 3072, 3)
-    entry("three_interpolate_64x128x1536_to_3072", _time(lambda: mm.three_interpolate(f, i3, w)),
-          _time(lambda: ref_cuda.three_interpolate(f, i3, w)) if have_ref else None, 64.0 * 128 * 3072, "elements/s",
-          4.0 * 64 * 3072 * (2 * 128 + 6))
     xyz, ctr = R(32, 2048, 3), R(32, 102, 3)
     entry("ball_query_32x2048_102centres_ns12", _time(lambda: mm.ball_query(0, 0.0774596669, 12, xyz, ctr)),
           _time(lambda: ref_cuda.ball_query(0, 0.0774596669, 12, xyz, ctr)) if have_ref else None, 32.0 * 102,

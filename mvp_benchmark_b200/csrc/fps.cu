@@ -17,6 +17,10 @@
 
 #include "common.cuh"
 
+#ifndef MVP_FPS_PMAX
+#define MVP_FPS_PMAX 8  // tuning knob (tools/pair_variants.py): points per thread before more warps are used
+#endif
+
 namespace mvp {
 
 __device__ __forceinline__ uint32_t fps_key(int k, int log2T) {
@@ -36,33 +40,80 @@ __device__ __forceinline__ int redux_max_s32(int v) {
   return r;
 }
 
+typedef unsigned long long fps_u64;
+__device__ __forceinline__ fps_u64 fps_pack2(float lo, float hi) {
+  fps_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fps_unpack2(fps_u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// squared distances of two points (packed) to one point (duplicated): the reference's contraction
+// fma(dz,dz, fma(dx,dx, dy*dy)) lane by lane, in 6 packed fp32x2 issue slots instead of 12
+__device__ __forceinline__ fps_u64 fps_dist2(fps_u64 X, fps_u64 Y, fps_u64 Z, fps_u64 qx, fps_u64 qy, fps_u64 qz) {
+  fps_u64 dx, dy, dz, t;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(X), "l"(qx));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(Y), "l"(qy));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(Z), "l"(qz));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  return t;
+}
+__device__ __forceinline__ float fps_max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // TB threads, P points per thread (k = tid + i*TB).  WITH_DIST: `data` is the (n,n) distance matrix.
-template <int TB, int P, bool WITH_DIST>
+// SMEM_PTS: the cloud also lives in shared memory as float4, so the coordinates of the point just selected — the
+// head of every iteration's dependency chain — cost one LDS.128 instead of three global loads.
+template <int TB, int P, bool WITH_DIST, bool SMEM_PTS>
 __global__ void __launch_bounds__(TB)
 fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
            int *__restrict__ idxs) {
+  static_assert(P % 2 == 0, "points are processed in packed pairs");
   constexpr int NW = TB / 32;
+  extern __shared__ __align__(16) float4 s_pts[];
   __shared__ int s_val[2][32];
   __shared__ uint32_t s_key[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *dataset = data + (size_t)blockIdx.x * (WITH_DIST ? (size_t)n * n : (size_t)n * 3);
   idxs += (size_t)blockIdx.x * m;
 
-  float px[P], py[P], pz[P], td[P];
+  fps_u64 PX[P / 2], PY[P / 2], PZ[P / 2];  // points 2h and 2h+1 of this thread, packed
+  float td[P];
 #pragma unroll
-  for (int i = 0; i < P; i++) {
-    const int k = tid + i * TB;
-    if (k < n) {
-      if (!WITH_DIST) {
-        px[i] = __ldg(dataset + k * 3 + 0);
-        py[i] = __ldg(dataset + k * 3 + 1);
-        pz[i] = __ldg(dataset + k * 3 + 2);
+  for (int h = 0; h < P / 2; h++) {
+    float x[2] = {0.f, 0.f}, y[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = 2 * h + e, k = tid + i * TB;
+      if (k < n) {
+        if (!WITH_DIST) {
+          x[e] = __ldg(dataset + k * 3 + 0);
+          y[e] = __ldg(dataset + k * 3 + 1);
+          z[e] = __ldg(dataset + k * 3 + 2);
+          if (SMEM_PTS) s_pts[k] = make_float4(x[e], y[e], z[e], 0.f);
+        }
+        td[i] = 1e10f;  // furthest_point_sample.py:30
+      } else {
+        td[i] = -1.f;  // never selected: compares below every real distance as a signed int
       }
-      td[i] = 1e10f;  // furthest_point_sample.py:30
-    } else {
-      px[i] = py[i] = pz[i] = 0.f;
-      td[i] = -1.f;  // never selected: compares below every real distance as a signed int
     }
+    PX[h] = fps_pack2(x[0], x[1]);
+    PY[h] = fps_pack2(y[0], y[1]);
+    PZ[h] = fps_pack2(z[0], z[1]);
+  }
+  // tie-break keys of this thread's points, once (they sit on every iteration's critical path otherwise); for the
+  // register-starved 32-points-per-thread shape they are recomputed on demand
+  constexpr bool kKeys = P <= 16;
+  uint32_t pkey[kKeys ? P : 1];
+  if (kKeys) {
+#pragma unroll
+    for (int i = 0; i < P; i++) pkey[i] = (tid + i * TB < n) ? fps_key(tid + i * TB, log2T) : 0xffffffffu;
   }
   if (warp == 0) {
     s_val[0][lane] = s_val[1][lane] = (int)0x80000000;
@@ -83,14 +134,23 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
         vmax = fmaxf(vmax, td[i]);
       }
     } else {
-      const float x1 = __ldg(dataset + old * 3 + 0);
-      const float y1 = __ldg(dataset + old * 3 + 1);
-      const float z1 = __ldg(dataset + old * 3 + 2);
+      float x1, y1, z1;
+      if (SMEM_PTS) {
+        const float4 o = s_pts[old];
+        x1 = o.x, y1 = o.y, z1 = o.z;
+      } else {
+        x1 = __ldg(dataset + old * 3 + 0);
+        y1 = __ldg(dataset + old * 3 + 1);
+        z1 = __ldg(dataset + old * 3 + 2);
+      }
+      const fps_u64 qx = fps_pack2(x1, x1), qy = fps_pack2(y1, y1), qz = fps_pack2(z1, z1);
 #pragma unroll
-      for (int i = 0; i < P; i++) {
-        const float d = sqdist(px[i] - x1, py[i] - y1, pz[i] - z1);  // point - old (:65-66)
-        td[i] = fminf(d, td[i]);
-        vmax = fmaxf(vmax, td[i]);
+      for (int h = 0; h < P / 2; h++) {
+        float d0, d1;
+        fps_unpack2(fps_dist2(PX[h], PY[h], PZ[h], qx, qy, qz), d0, d1);  // point - old (:65-66)
+        td[2 * h] = fminf(d0, td[2 * h]);
+        td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+        vmax = fps_max3(vmax, td[2 * h], td[2 * h + 1]);
       }
     }
     const int vbits = __float_as_int(vmax);
@@ -100,7 +160,11 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
 #pragma unroll
       for (int i = 0; i < P; i++) {
         const int k = tid + i * TB;
-        if (k < n && __float_as_int(td[i]) == wbits) key = min(key, fps_key(k, log2T));
+        if (kKeys) {
+          if (__float_as_int(td[i]) == wbits) key = min(key, pkey[i]);  // padding: td = -1 never equals a maximum
+        } else if (k < n && __float_as_int(td[i]) == wbits) {
+          key = min(key, fps_key(k, log2T));
+        }
       }
     }
     const uint32_t wkey = redux_min_u32(key);
@@ -198,7 +262,19 @@ static int ref_block_size(int work_size) {
 template <bool WD, int TB, int P>
 static void fps_launch_one(int b, int n, int m, int log2T, const float *data, float *temp, int *idx,
                            cudaStream_t s) {
-  fps_kernel<TB, P, WD><<<b, TB, 0, s>>>(n, m, log2T, data, temp, idx);
+  // the shared-memory copy of the cloud: 16 B per point, for clouds up to 8192 points (128 KB)
+  constexpr bool kSmem = !WD && TB * P <= 8192;
+  const size_t smem = kSmem ? (size_t)n * sizeof(float4) : 0;
+  if (smem > 40 * 1024) {
+    static size_t granted = 0;
+    if (smem > granted) {
+      if (cudaFuncSetAttribute(fps_kernel<TB, P, WD, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(TB * P * sizeof(float4))) != cudaSuccess)
+        return;  // launch_status() reports it
+      granted = TB * P * sizeof(float4);
+    }
+  }
+  fps_kernel<TB, P, WD, kSmem><<<b, TB, smem, s>>>(n, m, log2T, data, temp, idx);
 }
 
 template <bool WD>
@@ -209,13 +285,30 @@ static int fps_dispatch(int b, int n, int m, const float *data, float *temp, int
   const int T = ref_block_size(n);
   int log2T = 0;
   while ((1 << log2T) < T) log2T++;
-  // Fewest warps that keep <= 16 points per thread; then grow P.  (TB, P) with TB*P >= n.
+  // (TB, P) with TB*P >= n: at most MVP_FPS_PMAX points per thread while warps are left, then grow P.
+  if (n > 4096 && n <= 512 * 16) fps_launch_one<WD, 512, 16>(b, n, m, log2T, data, temp, idx, s);  // measured best
+  else
+#if MVP_FPS_PMAX >= 16
   if (n <= 128 * 4) fps_launch_one<WD, 128, 4>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 128 * 8) fps_launch_one<WD, 128, 8>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 128 * 16) fps_launch_one<WD, 128, 16>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 256 * 12) fps_launch_one<WD, 256, 12>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 256 * 16) fps_launch_one<WD, 256, 16>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 512 * 16) fps_launch_one<WD, 512, 16>(b, n, m, log2T, data, temp, idx, s);
+#elif MVP_FPS_PMAX >= 8
+  if (n <= 128 * 4) fps_launch_one<WD, 128, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 128 * 8) fps_launch_one<WD, 128, 8>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 256 * 8) fps_launch_one<WD, 256, 8>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 512 * 6) fps_launch_one<WD, 512, 6>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 512 * 8) fps_launch_one<WD, 512, 8>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 1024 * 8) fps_launch_one<WD, 1024, 8>(b, n, m, log2T, data, temp, idx, s);
+#else
+  if (n <= 128 * 4) fps_launch_one<WD, 128, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 256 * 4) fps_launch_one<WD, 256, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 512 * 4) fps_launch_one<WD, 512, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 1024 * 4) fps_launch_one<WD, 1024, 4>(b, n, m, log2T, data, temp, idx, s);
+  else if (n <= 1024 * 8) fps_launch_one<WD, 1024, 8>(b, n, m, log2T, data, temp, idx, s);
+#endif
   else if (n <= 1024 * 16) fps_launch_one<WD, 1024, 16>(b, n, m, log2T, data, temp, idx, s);
   else if (n <= 1024 * 32) fps_launch_one<WD, 1024, 32>(b, n, m, log2T, data, temp, idx, s);
   else {

@@ -303,11 +303,24 @@ static int channel_slices(int b, int c, int cols) {
 
 static bool bad_dims(int b, int c, int n, int mpts) { return b < 0 || c < 0 || n < 0 || mpts < 0; }
 
+// pointnet2_staged.cu: the shared-memory staged variants, taken when there are about as many gathered columns as
+// source columns (every call of the completion models)
+bool staged_applicable(int b, int c, int rows, int cols);
+int gather_staged_launch(int b, int c, int n, int mpts, const float *points, const int *idx, float *out,
+                         cudaStream_t s);
+int gather_grad_staged_launch(int b, int c, int n, int mpts, const float *grad_out, const int *idx, float *grad_points,
+                              cudaStream_t s);
+int three_interpolate_staged_launch(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                                    float *out, cudaStream_t s);
+int three_interpolate_grad_staged_launch(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                         const float *weight, float *grad_points, cudaStream_t s);
+
 static int gather_launch(int b, int c, int n, int mpts, const float *points, const int *idx, float *out,
                          cudaStream_t s) {
   if (bad_dims(b, c, n, mpts)) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || c == 0 || mpts == 0) return MVP_OK;
   if (n == 0 || !points || !idx || !out) return MVP_ERR_INVALID_ARGUMENT;
+  if (staged_applicable(b, c, n, mpts)) return gather_staged_launch(b, c, n, mpts, points, idx, out, s);
   const int split = channel_slices(b, c, mpts);
   const int cper = (c + split - 1) / split;
   for (int b0 = 0; b0 < b; b0 += 65535) {
@@ -325,6 +338,8 @@ static int gather_grad_launch(int b, int c, int n, int mpts, const float *grad_o
   if (bad_dims(b, c, n, mpts)) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || c == 0 || n == 0) return MVP_OK;
   if (!grad_points) return MVP_ERR_INVALID_ARGUMENT;
+  if (mpts > 0 && grad_out && idx && staged_applicable(b, c, n, mpts))  // writes every element: no memset
+    return gather_grad_staged_launch(b, c, n, mpts, grad_out, idx, grad_points, s);
   cudaError_t e = cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * c * n, s);
   if (e != cudaSuccess) return (int)e;
   if (mpts == 0) return MVP_OK;
@@ -431,6 +446,7 @@ MVP_API int mvp_three_interpolate(int b, int c, int m, int n, const float *point
   if (b == 0 || c == 0 || n == 0) return MVP_OK;
   if (m == 0 || !points || !idx || !weight || !out) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
+  if (staged_applicable(b, c, m, n)) return three_interpolate_staged_launch(b, c, m, n, points, idx, weight, out, s);
   const int split = channel_slices(b, c, n);
   const int cper = (c + split - 1) / split;
   for (int b0 = 0; b0 < b; b0 += 65535) {
@@ -450,6 +466,8 @@ MVP_API int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *
   if (b == 0 || c == 0 || m == 0) return MVP_OK;
   if (!grad_points) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
+  if (n > 0 && grad_out && idx && weight && staged_applicable(b, c, m, n))  // writes every element: no memset
+    return three_interpolate_grad_staged_launch(b, c, n, m, grad_out, idx, weight, grad_points, s);
   cudaError_t e = cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * c * m, s);
   if (e != cudaSuccess) return (int)e;
   if (n == 0) return MVP_OK;

@@ -320,7 +320,11 @@ def test_knn_vs_oracle(gpu, cpu, kind, b, n, p, k):
 
 
 # ---------------------------------------------------------------------------------------------- gathers
-@pytest.mark.parametrize("b,c,n,m", [(64, 3, 2048, 2048), (8, 64, 3072, 15360), (2, 256, 768, 3840), (2, 1, 5, 1), (3, 7, 100, 1000)])
+# staged path (M >= N/2: TMA-staged rows, shared-memory atomics in the backward) and direct path (M << N, rows that do
+# not fit shared memory), aligned and unaligned rows, channel counts that do not divide the group size
+@pytest.mark.parametrize("b,c,n,m", [(64, 3, 2048, 2048), (8, 64, 3072, 15360), (2, 256, 768, 3840), (2, 1, 5, 1), (3, 7, 100, 1000),
+                                     (2, 64, 4096, 256), (3, 13, 101, 333), (2, 5, 20000, 30000), (1, 3, 60000, 70000),
+                                     (2, 9, 3071, 4001), (70, 2, 64, 64)])
 def test_gather_vs_oracle(gpu, cpu, b, c, n, m):
     rng = np.random.default_rng(91)
     pts = rng.standard_normal((b, c, n)).astype(np.float32)
@@ -340,7 +344,8 @@ def test_group_vs_oracle(gpu, cpu, b, c, n, p, s):
     _cases.close(gpu.group_grad(go, idx, n), cpu.group_grad(go, idx, n), "group grad", atol=1e-5)
 
 
-@pytest.mark.parametrize("b,c,m,n", [(8, 512, 384, 768), (4, 256, 768, 1536), (2, 128, 1536, 3072), (1, 3, 4, 5)])
+@pytest.mark.parametrize("b,c,m,n", [(8, 512, 384, 768), (4, 256, 768, 1536), (2, 128, 1536, 3072), (1, 3, 4, 5),
+                                     (2, 11, 1001, 777), (2, 6, 4096, 100), (1, 2, 60000, 61000), (3, 5, 18000, 9000)])
 def test_three_interpolate_vs_oracle(gpu, cpu, b, c, m, n):
     rng = np.random.default_rng(93)
     pts = rng.standard_normal((b, c, m)).astype(np.float32)

@@ -31,6 +31,7 @@ EMD_VARIANTS = {
     "ppc2": ["-DMVP_EMD_GRID_PPC=2"],
     "ppc8": ["-DMVP_EMD_GRID_PPC=8"],
 }
+FPS_VARIANTS = {"base": [], "pmax8": ["-DMVP_FPS_PMAX=8"], "pmax4": ["-DMVP_FPS_PMAX=4"]}
 SETS = {}
 VARIANTS = {
     "base": [],
@@ -44,8 +45,9 @@ VARIANTS = {
 }
 
 
-SETS.update({"pair": VARIANTS, "grid": GRID_VARIANTS, "emd": EMD_VARIANTS})
-SYMBOL = {"pair": "chamfer_pair_kernelILi8", "grid": "chamfer_grid_query_kernel", "emd": "emd_auction_grid_kernel"}
+SETS.update({"pair": VARIANTS, "grid": GRID_VARIANTS, "emd": EMD_VARIANTS, "fps": FPS_VARIANTS})
+SYMBOL = {"pair": "chamfer_pair_kernelILi8", "grid": "chamfer_grid_query_kernel", "emd": "emd_auction_grid_kernel",
+          "fps": "fps_kernelILi256"}
 SHAPES = {"pair": [(32, 16384, 16384)], "grid": [(32, 16384, 16384), (64, 2048, 2048)]}
 
 
@@ -55,7 +57,7 @@ def build(which):
         lib = os.path.join(OUT, f"libvar_{which}_{name}.so")
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
                "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-shared", "-Xptxas", "-v"] + flags + \
-              [os.path.join(CSRC, f) for f in (("capi.cu", "emd.cu") if which == "emd" else
+              [os.path.join(CSRC, f) for f in (("capi.cu", "emd.cu") if which == "emd" else ("capi.cu", "fps.cu") if which == "fps" else
                                                ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu"))] + ["-o", lib]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
@@ -105,9 +107,48 @@ def run_emd():
             print(f"{name:10s} {e0.elapsed_time(e1) / 3:9.3f} ms  same_as_base={torch.equal(a, ref[key])}", flush=True)
 
 
+def run_fps():
+    import torch
+    dev = torch.device("cuda:0")
+    ref = {}
+    for b, n, m in [(32, 2048, 2048), (64, 3072, 2048), (64, 3072, 1536), (64, 1536, 768), (64, 768, 384), (8, 8192, 1024),
+                    (4, 16384, 512)]:
+        print("shape", (b, n, m), flush=True)
+        g = torch.Generator(device=dev)
+        g.manual_seed(0)
+        x = torch.rand(b, n, 3, device=dev, generator=g)
+        for name in SETS["fps"]:
+            path = os.path.join(OUT, f"libvar_fps_{name}.so")
+            if not os.path.isfile(path):
+                continue
+            L = ctypes.CDLL(path)
+            idx = torch.empty(b, m, device=dev, dtype=torch.int32)
+            P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+            def call():
+                rc = L.mvp_furthest_point_sampling(b, n, m, P(x), ctypes.c_void_p(0), P(idx),
+                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, rc
+            call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                call()
+            e1.record()
+            e1.synchronize()
+            key = (b, n, m)
+            if key not in ref:
+                ref[key] = idx.clone()
+            print(f"{name:10s} {e0.elapsed_time(e1) / 5:9.4f} ms  {e0.elapsed_time(e1) / 5 / m * 1e6:7.1f} ns/pick  "
+                  f"same_as_base={torch.equal(idx, ref[key])}", flush=True)
+
+
 def run(which):
     if which == "emd":
         return run_emd()
+    if which == "fps":
+        return run_fps()
     for shape in SHAPES[which]:
         print("shape", shape, flush=True)
         run_shape(which, *shape)
