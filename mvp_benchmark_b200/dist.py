@@ -21,7 +21,10 @@ def init_from_env(backend=None):
     if backend == "nccl":
         torch.cuda.set_device(local)
     if not dist.is_initialized():
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)  # binds the communicator to this rank's GPU up front
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
 

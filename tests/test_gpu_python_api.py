@@ -140,3 +140,50 @@ def test_ops_follow_the_current_stream(ops, cuda):
         got = metrics.cd()(a, c)[0]
     s.synchronize()
     assert torch.equal(got, want)
+
+
+def test_ops_are_cuda_graph_capturable(ops, cuda):
+    """No op synchronises the host or allocates behind torch's back: a forward+backward through Chamfer (grid
+    path and the small-cloud path), EMD, FPS, gather and three_interpolate is captured once and replayed on new
+    inputs; the replay must reproduce the eager results bit for bit (gradients: same accumulation class, 1e-5)."""
+    metrics, mm = ops
+    g = torch.Generator(device=cuda)
+    g.manual_seed(3)
+    R = lambda *s: torch.rand(*s, device=cuda, generator=g)  # noqa: E731
+    x1, x2, small = R(2, 2048, 3), R(2, 1536, 3), R(2, 100, 3)
+    e1, e2 = R(2, 1024, 3), R(2, 1024, 3)
+    feat = R(2, 16, 2048)
+    i3 = torch.randint(0, 2048, (2, 1536, 3), device=cuda, generator=g, dtype=torch.int32)
+    w3 = R(2, 1536, 3)
+    cd, emd = metrics.cd(), metrics.emd()
+
+    def step():
+        a, f = x1.detach().requires_grad_(True), feat.detach().requires_grad_(True)
+        d1, d2, j1, j2 = cd(a, x2)
+        s1, s2, _, _ = cd(small, a)
+        ed, ea = emd(e1, e2, 0.005, 20)
+        fi = mm.furthest_point_sample(a.detach(), 512)
+        gathered = mm.gather_points(f, fi)
+        interp = mm.three_interpolate(f, i3, w3)
+        (d1.sum() + d2.sum() + s2.sum() + gathered.sum() + (interp * w3[..., 0].unsqueeze(1)).sum()).backward()
+        return [d1.detach(), d2.detach(), j1, j2, s1.detach(), ed, ea, fi, gathered.detach(), interp.detach()], [a.grad, f.grad]
+
+    side = torch.cuda.Stream(cuda)
+    side.wait_stream(torch.cuda.current_stream(cuda))
+    with torch.cuda.stream(side):
+        step()  # warm-up outside capture (lazy kernel-attribute setup, allocator pools)
+    torch.cuda.current_stream(cuda).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs, grads = step()
+    for t in (x1, x2, small, e1, e2, feat, w3):  # new inputs, same buffers
+        t.copy_(torch.rand(t.shape, device=cuda, generator=g))
+    graph.replay()
+    torch.cuda.synchronize(cuda)
+    got = [t.clone() for t in outs], [t.clone() for t in grads]
+    want = step()
+    torch.cuda.synchronize(cuda)
+    for a, b in zip(got[0], want[0]):
+        assert torch.equal(a, b)
+    for a, b in zip(got[1], want[1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
