@@ -72,8 +72,9 @@ int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, c
                              size_t workspace_bytes, mvp_stream_t stream);
 
 /* Replaces chamfer_3D.backward -> chamfer_cuda_backward (chamfer_cuda.cpp:22-26, chamfer3D.cu:176-195,
- * kernel :155-174).  gradxyz1 (b,n,3) and gradxyz2 (b,m,3) are zero-filled inside
- * (dist_chamfer_3D.py:56-57 does it in the reference) and then accumulated with fp32 atomics. */
+ * kernel :155-174).  gradxyz1 (b,n,3) and gradxyz2 (b,m,3) need no zero-fill (dist_chamfer_3D.py:56-57 does
+ * it in the reference): each point's own half is written with a plain store, the scattered halves are
+ * accumulated with fp32 atomics. */
 int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
                          const float *graddist1, const float *graddist2, const int *idx1,
                          const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream);

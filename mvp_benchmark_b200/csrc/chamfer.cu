@@ -146,8 +146,13 @@ int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz
   return launch_status();
 }
 
-// Backward: both directions in one launch.  Thread i < b*n handles point i of xyz1 (direction 1),
-// the rest handle points of xyz2 (direction 2).  chamfer3D.cu:155-174: g = grad*2; six accumulations.
+// Backward (chamfer3D.cu:155-174: g = grad*2; six float atomics per point into pre-zeroed gradients).  Point i of
+// one cloud contributes  v = g (p_i - q_nn(i))  to its OWN gradient row and -v to its neighbour's row in the OTHER
+// cloud.  Every row receives exactly one own contribution, so pass 1 WRITES it with a plain coalesced store (which
+// is also what zero-fills the gradients) and pass 2 adds the scattered halves with red.global.add.f32: half the
+// atomics of the reference and no memset.  One launch each for both directions: thread i < b*n handles point i of
+// xyz1, the rest handle points of xyz2.
+template <bool kScatter>
 __global__ void __launch_bounds__(256)
 chamfer_grad_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                     const float *__restrict__ gd1, const float *__restrict__ gd2,
@@ -169,12 +174,15 @@ chamfer_grad_kernel(int b, int n, int m, const float *__restrict__ xyz1, const f
     const long long o = (cloud * nb + j2) * 3;
     const float x2 = __ldg(Bp + o + 0), y2 = __ldg(Bp + o + 1), z2 = __ldg(Bp + o + 2);
     const float vx = g * (x1 - x2), vy = g * (y1 - y2), vz = g * (z1 - z2);
-    atomicAdd(GA + p * 3 + 0, vx);
-    atomicAdd(GA + p * 3 + 1, vy);
-    atomicAdd(GA + p * 3 + 2, vz);
-    atomicAdd(GB + o + 0, -vx);
-    atomicAdd(GB + o + 1, -vy);
-    atomicAdd(GB + o + 2, -vz);
+    if (!kScatter) {
+      GA[p * 3 + 0] = vx;
+      GA[p * 3 + 1] = vy;
+      GA[p * 3 + 2] = vz;
+    } else {
+      atomicAdd(GB + o + 0, -vx);
+      atomicAdd(GB + o + 1, -vy);
+      atomicAdd(GB + o + 2, -vz);
+    }
   }
 }
 
@@ -244,18 +252,13 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
   if (!xyz1 || !xyz2 || !graddist1 || !graddist2 || !idx1 || !idx2 || !gradxyz1 || !gradxyz2)
     return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e;
-  const size_t b1 = sizeof(float) * (size_t)b * n * 3, b2 = sizeof(float) * (size_t)b * m * 3;
-  if ((char *)gradxyz1 + b1 == (char *)gradxyz2) {  // one contiguous allocation: one memset
-    if ((e = cudaMemsetAsync(gradxyz1, 0, b1 + b2, s)) != cudaSuccess) return (int)e;
-  } else {
-    if ((e = cudaMemsetAsync(gradxyz1, 0, b1, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(gradxyz2, 0, b2, s)) != cudaSuccess) return (int)e;
-  }
   const long long total = (long long)b * (n + m);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-  chamfer_grad_kernel<<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2,
-                                           gradxyz1, gradxyz2);
+  chamfer_grad_kernel<false><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                  gradxyz2);
+  chamfer_grad_kernel<true><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                 gradxyz2);
+  count_launch(2);
   count_launch();
   return launch_status();
 }

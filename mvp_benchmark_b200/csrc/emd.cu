@@ -306,6 +306,10 @@ constexpr int kEmdGridMaxN = 8192;
 #ifndef MVP_EMD_FULLSCAN_EVALS
 #define MVP_EMD_FULLSCAN_EVALS 48
 #endif
+#ifndef MVP_EMD_TAIL_MAX
+#define MVP_EMD_TAIL_MAX 512
+#endif
+constexpr int kEmdTailMax = MVP_EMD_TAIL_MAX;  // unassigned sources (whole cloud) at which one CTA takes over; <= 512
 constexpr int kEmdFullScanEvals = MVP_EMD_FULLSCAN_EVALS;  // per-thread evaluations up to which a full scan is used
 
 __global__ void __launch_bounds__(kEmdThreads, 1)
@@ -324,7 +328,7 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
   int *orig = reinterpret_cast<int *>(smem_raw + (size_t)n * 16);        // n: original index of a sorted target
   int *T = orig + n;                                                     // cap + 1 (padded to 4): cell starts
   int *list = T + ((cap + 1 + 3) & ~3);                                  // n / C: unassigned sources of this CTA
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_cnt2;
   __shared__ int s_total;  // read by the other CTAs of the cluster through DSMEM
   __shared__ float s_red[6][32];
   __shared__ int s_int[32];
@@ -457,7 +461,239 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
 
   const float s2 = h.s * h.s * (1.f - 1e-5f);  // cells^2 -> squared distance, rounded down generously
 
-  for (int it = 0; it < iters; it++) {
+  // ---- the pieces of a round that the cluster-wide rounds and the single-CTA tail rounds share
+  // current prices (global, indexed by original target) into the sorted copy; their minimum bounds every
+  // unvisited target's value.  from_global = false: the copy is authoritative (tail rounds), only the minimum.
+  auto refresh_prices = [&](bool from_global) {
+  {
+    float pm = inf;
+    for (int pos = tid; pos < n; pos += kEmdThreads) {
+      const float p = from_global ? __ldcg(st.price + orig[pos]) : tgt[pos].w;
+      tgt[pos].w = p;
+      pm = fminf(pm, p);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) pm = fminf(pm, __shfl_xor_sync(0xffffffffu, pm, off));
+    if (lane == 0) s_red[0][warp] = pm;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kEmdThreads / 32; w++) pm = fminf(pm, s_red[0][w]);
+      s_pmin = pm;
+    }
+    __syncthreads();
+  }
+  };
+  auto bid_phase = [&](const int ucnt, const KeyParams kp) {
+  const float vmax = 3.0f - s_pmin;  // no target's value exceeds this (up to rounding, covered by the margins)
+  // squared distance beyond which a target cannot reach `better`; negative = nothing can
+  auto reach2 = [&](float better) {
+    const float t = (vmax - better) * (1.f + 1e-5f) + 1e-5f;
+    return t < 0.f ? -1.f : t * t;
+  };
+
+  // ---- Bid
+  // Few unassigned sources (the long tail of an auction): spreading a full scan of the shared-memory targets over
+  // all 1024 threads costs n * ucnt / 1024 evaluations per thread and no search overhead — cheaper than a grid
+  // search by one warp per source once that is a few dozen.
+  if ((long long)ucnt * n <= (long long)kEmdThreads * kEmdFullScanEvals) {
+    int tpp = 1;  // threads per source: largest power of two <= kEmdThreads / ucnt
+    while (ucnt > 0 && tpp * 2 * ucnt <= kEmdThreads) tpp *= 2;
+    const int pi = tid / tpp, g = tid % tpp;
+    const bool valid = pi < ucnt;
+    int src = -1;
+    float x1 = 0, y1 = 0, z1 = 0;
+    if (valid) {
+      src = list[pi];
+      x1 = __ldg(xyz1 + src * 3 + 0);
+      y1 = __ldg(xyz1 + src * 3 + 1);
+      z1 = __ldg(xyz1 + src * 3 + 2);
+    }
+    BidTop top;
+    top.best = -1e9f;
+    top.better = -1e9f;
+    top.bi = -1;
+    if (valid) {
+      for (int pos = g; pos < n; pos += tpp) {
+        const float4 q = tgt[pos];
+        const float s = sqdist(q.x - x1, q.y - y1, q.z - z1);
+        const float d = (float)(3.0 - (double)__fsqrt_rn(s) - (double)q.w);
+        if (d > top.best) {
+          top.better = top.best;
+          top.best = d;
+          top.bi = orig[pos];
+        } else if (d == top.best) {
+          top.better = d;
+          const int k = orig[pos];
+          if (scans_before(k, top.bi, kp)) top.bi = k;
+        } else if (d > top.better) {
+          top.better = d;
+        }
+      }
+    }
+    const int wspan = tpp < 32 ? tpp : 32;
+    for (int off = 1; off < wspan; off <<= 1) {
+      BidTop o;
+      o.best = __shfl_xor_sync(0xffffffffu, top.best, off);
+      o.better = __shfl_xor_sync(0xffffffffu, top.better, off);
+      o.bi = __shfl_xor_sync(0xffffffffu, top.bi, off);
+      merge_top(top, o, kp);
+    }
+    if (tpp > 32) {  // one source spans tpp/32 whole warps
+      if (lane == 0) s_merge[warp] = top;
+      __syncthreads();
+      const int wpp = tpp / 32;
+      if (lane == 0 && (warp % wpp) == 0)
+        for (int w = warp + 1; w < warp + wpp; w++) merge_top(top, s_merge[w], kp);
+    }
+    if (valid && g == 0) {
+      const float inc = top.best - top.better + eps;
+      st.bid[src] = top.bi;
+      st.bid_inc[src] = inc;
+      atomic_max_float(st.max_inc + top.bi, inc);
+    }
+  } else {
+  int tpp = 1;  // lanes per source: largest power of two <= min(32, kEmdThreads / ucnt)
+  while (ucnt > 0 && tpp < 32 && tpp * 2 * ucnt <= kEmdThreads) tpp *= 2;
+  const int ppp = kEmdThreads / tpp;  // sources per pass
+  const int passes = (ucnt + ppp - 1) / ppp;
+  for (int pass = 0; pass < passes; pass++) {
+    const int pi = pass * ppp + tid / tpp;
+    const int g = tid % tpp;
+    const bool valid = pi < ucnt;
+    int src = -1;
+    float x1 = 0, y1 = 0, z1 = 0;
+    if (valid) {
+      src = list[pi];
+      x1 = __ldg(xyz1 + src * 3 + 0);
+      y1 = __ldg(xyz1 + src * 3 + 1);
+      z1 = __ldg(xyz1 + src * 3 + 2);
+    }
+    BidTop top;
+    top.best = -1e9f;
+    top.better = -1e9f;
+    top.bi = -1;
+    const float ux = (x1 - h.lo[0]) * h.inv_s, uy = (y1 - h.lo[1]) * h.inv_s, uz = (z1 - h.lo[2]) * h.inv_s;
+    const int cx = cell_coord(ux, gx), cy = cell_coord(uy, gy), cz = cell_coord(uz, gz);
+    const float slx = 1e-4f + 1e-6f * (fabsf(ux) + (float)gx);
+    const float sly = 1e-4f + 1e-6f * (fabsf(uy) + (float)gy);
+    const float slz = 1e-4f + 1e-6f * (fabsf(uz) + (float)gz);
+    // a source whose cell coordinates are not finite cannot prune: it scans the whole grid ring by ring
+    const bool prunable = h.valid && (fabsf(ux) + fabsf(uy) + fabsf(uz) < 1e30f);
+
+    // Lane g of a source's group owns the sorted positions == g (mod tpp), whatever range it is handed: the lanes
+    // clip their ranges independently (each with its own, conservative, `better`), so the split must not depend
+    // on where a lane's range starts.
+    auto scan = [&](int a, int e) {
+      for (int pos = a + ((g - a) & (tpp - 1)); pos < e; pos += tpp) {
+        const float4 q = tgt[pos];
+        const float s = sqdist(q.x - x1, q.y - y1, q.z - z1);
+        const float d = (float)(3.0 - (double)__fsqrt_rn(s) - (double)q.w);
+        if (d > top.best) {
+          top.better = top.best;
+          top.best = d;
+          top.bi = orig[pos];
+        } else if (d == top.best) {
+          top.better = d;
+          const int k = orig[pos];
+          if (scans_before(k, top.bi, kp)) top.bi = k;
+        } else if (d > top.better) {
+          top.better = d;
+        }
+      }
+    };
+
+    BidTop merged = top;
+    float known = -1e9f;   // a lower bound of the group's `better` (merged at the end of the previous ring)
+    bool finished = !valid;
+    int r = 0;
+    while (__any_sync(0xffffffffu, !finished)) {
+      if (!finished) {
+        for (int dz = -r; dz <= r; dz++) {
+          const int zz = cz + dz;
+          if (zz < 0 || zz >= gz) continue;
+          const float gzz = prunable ? cell_gap(uz, zz, slz) : 0.f;
+          for (int dy = -r; dy <= r; dy++) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= gy) continue;
+            const float gyy = prunable ? cell_gap(uy, yy, sly) : 0.f;
+            const float lbyz = fmaf(gyy, gyy, gzz * gzz);
+#ifdef MVP_EMD_DEBUG_NOPRUNE
+            const float lim = 3e38f;
+#else
+            const float lim = reach2(fmaxf(known, top.better));
+#endif
+            if (lbyz * s2 > lim) continue;
+            const int base = (zz * gy + yy) * gx;
+            const bool shell = (dz == -r || dz == r || dy == -r || dy == r);
+            if (shell) {
+              int x0 = max(cx - r, 0), x1c = min(cx + r, gx - 1);
+              if (prunable) {
+                while (x0 <= x1c) {
+                  const float gg = cell_gap(ux, x0, slx);
+                  if (fmaf(gg, gg, lbyz) * s2 > lim) x0++; else break;
+                }
+                while (x1c >= x0) {
+                  const float gg = cell_gap(ux, x1c, slx);
+                  if (fmaf(gg, gg, lbyz) * s2 > lim) x1c--; else break;
+                }
+              }
+              if (x0 <= x1c) scan(T[base + x0], T[base + x1c + 1]);
+            } else {  // interior row: only its two new end cells
+              if (cx - r >= 0) {
+                const float gg = prunable ? cell_gap(ux, cx - r, slx) : 0.f;
+                if (!(fmaf(gg, gg, lbyz) * s2 > lim)) scan(T[base + cx - r], T[base + cx - r + 1]);
+              }
+              if (cx + r < gx) {
+                const float gg = prunable ? cell_gap(ux, cx + r, slx) : 0.f;
+                if (!(fmaf(gg, gg, lbyz) * s2 > lim)) scan(T[base + cx + r], T[base + cx + r + 1]);
+              }
+            }
+          }
+        }
+      }
+      // merge the partial results of the tpp lanes of each source (all lanes of the warp take part)
+      merged = top;
+      for (int off = 1; off < tpp; off <<= 1) {
+        BidTop o;
+        o.best = __shfl_xor_sync(0xffffffffu, merged.best, off);
+        o.better = __shfl_xor_sync(0xffffffffu, merged.better, off);
+        o.bi = __shfl_xor_sync(0xffffffffu, merged.bi, off);
+        merge_top(merged, o, kp);
+      }
+      if (!finished) {
+        known = merged.better;
+        // everything outside the cube of radius r is at least `ext` cells away
+        float ext = inf;
+        if (cx - r > 0) ext = fminf(ext, ux - (float)(cx - r) - slx);
+        if (cx + r + 1 < gx) ext = fminf(ext, (float)(cx + r + 1) - ux - slx);
+        if (cy - r > 0) ext = fminf(ext, uy - (float)(cy - r) - sly);
+        if (cy + r + 1 < gy) ext = fminf(ext, (float)(cy + r + 1) - uy - sly);
+        if (cz - r > 0) ext = fminf(ext, uz - (float)(cz - r) - slz);
+        if (cz + r + 1 < gz) ext = fminf(ext, (float)(cz + r + 1) - uz - slz);
+        const bool covered = (cx - r <= 0) && (cx + r + 1 >= gx) && (cy - r <= 0) && (cy + r + 1 >= gy) &&
+                             (cz - r <= 0) && (cz + r + 1 >= gz);
+        ext = fmaxf(ext, 0.f);
+#ifdef MVP_EMD_DEBUG_NOTERM
+        if (covered) finished = true;
+#else
+        if (covered || (prunable && ext * ext * s2 > reach2(known))) finished = true;
+#endif
+        r++;
+      }
+    }
+    if (valid && g == 0) {
+      const float inc = merged.best - merged.better + eps;
+      st.bid[src] = merged.bi;
+      st.bid_inc[src] = inc;
+      atomic_max_float(st.max_inc + merged.bi, inc);
+    }
+  }
+  }  // grid search
+  };
+
+  int it = 0;
+  bool tail = false;
+  for (; it < iters; it++) {
     const bool last = (it == iters - 1);
     // ---- list the unassigned sources of the own slice (order is irrelevant, as in calc_unass_idx :85-93)
     if (tid == 0) s_cnt = 0;
@@ -480,6 +716,10 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
     int total = 0;
     for (int r = 0; r < C; r++) total += *cluster.map_shared_rank(&s_total, r);
     if (total == 0) break;  // converged: every later round is a no-op
+    if (total <= kEmdTailMax) {  // the long tail: one CTA finishes the auction alone (below)
+      tail = true;
+      break;
+    }
     KeyParams kp;
     kp.n = n;
     {
@@ -488,229 +728,8 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
       kp.tpu = 1024 / unass_per_block;
     }
 
-    // ---- current prices into the sorted copy; their minimum bounds every unvisited target's value
-    {
-      float pm = inf;
-      for (int pos = tid; pos < n; pos += kEmdThreads) {
-        const float p = __ldcg(st.price + orig[pos]);
-        tgt[pos].w = p;
-        pm = fminf(pm, p);
-      }
-#pragma unroll
-      for (int off = 16; off; off >>= 1) pm = fminf(pm, __shfl_xor_sync(0xffffffffu, pm, off));
-      if (lane == 0) s_red[0][warp] = pm;
-      __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < kEmdThreads / 32; w++) pm = fminf(pm, s_red[0][w]);
-        s_pmin = pm;
-      }
-      __syncthreads();
-    }
-    const float vmax = 3.0f - s_pmin;  // no target's value exceeds this (up to rounding, covered by the margins)
-    // squared distance beyond which a target cannot reach `better`; negative = nothing can
-    auto reach2 = [&](float better) {
-      const float t = (vmax - better) * (1.f + 1e-5f) + 1e-5f;
-      return t < 0.f ? -1.f : t * t;
-    };
-
-    // ---- Bid
-    // Few unassigned sources (the long tail of an auction): spreading a full scan of the shared-memory targets over
-    // all 1024 threads costs n * ucnt / 1024 evaluations per thread and no search overhead — cheaper than a grid
-    // search by one warp per source once that is a few dozen.
-    if ((long long)ucnt * n <= (long long)kEmdThreads * kEmdFullScanEvals) {
-      int tpp = 1;  // threads per source: largest power of two <= kEmdThreads / ucnt
-      while (ucnt > 0 && tpp * 2 * ucnt <= kEmdThreads) tpp *= 2;
-      const int pi = tid / tpp, g = tid % tpp;
-      const bool valid = pi < ucnt;
-      int src = -1;
-      float x1 = 0, y1 = 0, z1 = 0;
-      if (valid) {
-        src = list[pi];
-        x1 = __ldg(xyz1 + src * 3 + 0);
-        y1 = __ldg(xyz1 + src * 3 + 1);
-        z1 = __ldg(xyz1 + src * 3 + 2);
-      }
-      BidTop top;
-      top.best = -1e9f;
-      top.better = -1e9f;
-      top.bi = -1;
-      if (valid) {
-        for (int pos = g; pos < n; pos += tpp) {
-          const float4 q = tgt[pos];
-          const float s = sqdist(q.x - x1, q.y - y1, q.z - z1);
-          const float d = (float)(3.0 - (double)__fsqrt_rn(s) - (double)q.w);
-          if (d > top.best) {
-            top.better = top.best;
-            top.best = d;
-            top.bi = orig[pos];
-          } else if (d == top.best) {
-            top.better = d;
-            const int k = orig[pos];
-            if (scans_before(k, top.bi, kp)) top.bi = k;
-          } else if (d > top.better) {
-            top.better = d;
-          }
-        }
-      }
-      const int wspan = tpp < 32 ? tpp : 32;
-      for (int off = 1; off < wspan; off <<= 1) {
-        BidTop o;
-        o.best = __shfl_xor_sync(0xffffffffu, top.best, off);
-        o.better = __shfl_xor_sync(0xffffffffu, top.better, off);
-        o.bi = __shfl_xor_sync(0xffffffffu, top.bi, off);
-        merge_top(top, o, kp);
-      }
-      if (tpp > 32) {  // one source spans tpp/32 whole warps
-        if (lane == 0) s_merge[warp] = top;
-        __syncthreads();
-        const int wpp = tpp / 32;
-        if (lane == 0 && (warp % wpp) == 0)
-          for (int w = warp + 1; w < warp + wpp; w++) merge_top(top, s_merge[w], kp);
-      }
-      if (valid && g == 0) {
-        const float inc = top.best - top.better + eps;
-        st.bid[src] = top.bi;
-        st.bid_inc[src] = inc;
-        atomic_max_float(st.max_inc + top.bi, inc);
-      }
-    } else {
-    int tpp = 1;  // lanes per source: largest power of two <= min(32, kEmdThreads / ucnt)
-    while (ucnt > 0 && tpp < 32 && tpp * 2 * ucnt <= kEmdThreads) tpp *= 2;
-    const int ppp = kEmdThreads / tpp;  // sources per pass
-    const int passes = (ucnt + ppp - 1) / ppp;
-    for (int pass = 0; pass < passes; pass++) {
-      const int pi = pass * ppp + tid / tpp;
-      const int g = tid % tpp;
-      const bool valid = pi < ucnt;
-      int src = -1;
-      float x1 = 0, y1 = 0, z1 = 0;
-      if (valid) {
-        src = list[pi];
-        x1 = __ldg(xyz1 + src * 3 + 0);
-        y1 = __ldg(xyz1 + src * 3 + 1);
-        z1 = __ldg(xyz1 + src * 3 + 2);
-      }
-      BidTop top;
-      top.best = -1e9f;
-      top.better = -1e9f;
-      top.bi = -1;
-      const float ux = (x1 - h.lo[0]) * h.inv_s, uy = (y1 - h.lo[1]) * h.inv_s, uz = (z1 - h.lo[2]) * h.inv_s;
-      const int cx = cell_coord(ux, gx), cy = cell_coord(uy, gy), cz = cell_coord(uz, gz);
-      const float slx = 1e-4f + 1e-6f * (fabsf(ux) + (float)gx);
-      const float sly = 1e-4f + 1e-6f * (fabsf(uy) + (float)gy);
-      const float slz = 1e-4f + 1e-6f * (fabsf(uz) + (float)gz);
-      // a source whose cell coordinates are not finite cannot prune: it scans the whole grid ring by ring
-      const bool prunable = h.valid && (fabsf(ux) + fabsf(uy) + fabsf(uz) < 1e30f);
-
-      // Lane g of a source's group owns the sorted positions == g (mod tpp), whatever range it is handed: the lanes
-      // clip their ranges independently (each with its own, conservative, `better`), so the split must not depend
-      // on where a lane's range starts.
-      auto scan = [&](int a, int e) {
-        for (int pos = a + ((g - a) & (tpp - 1)); pos < e; pos += tpp) {
-          const float4 q = tgt[pos];
-          const float s = sqdist(q.x - x1, q.y - y1, q.z - z1);
-          const float d = (float)(3.0 - (double)__fsqrt_rn(s) - (double)q.w);
-          if (d > top.best) {
-            top.better = top.best;
-            top.best = d;
-            top.bi = orig[pos];
-          } else if (d == top.best) {
-            top.better = d;
-            const int k = orig[pos];
-            if (scans_before(k, top.bi, kp)) top.bi = k;
-          } else if (d > top.better) {
-            top.better = d;
-          }
-        }
-      };
-
-      BidTop merged = top;
-      float known = -1e9f;   // a lower bound of the group's `better` (merged at the end of the previous ring)
-      bool finished = !valid;
-      int r = 0;
-      while (__any_sync(0xffffffffu, !finished)) {
-        if (!finished) {
-          for (int dz = -r; dz <= r; dz++) {
-            const int zz = cz + dz;
-            if (zz < 0 || zz >= gz) continue;
-            const float gzz = prunable ? cell_gap(uz, zz, slz) : 0.f;
-            for (int dy = -r; dy <= r; dy++) {
-              const int yy = cy + dy;
-              if (yy < 0 || yy >= gy) continue;
-              const float gyy = prunable ? cell_gap(uy, yy, sly) : 0.f;
-              const float lbyz = fmaf(gyy, gyy, gzz * gzz);
-#ifdef MVP_EMD_DEBUG_NOPRUNE
-              const float lim = 3e38f;
-#else
-              const float lim = reach2(fmaxf(known, top.better));
-#endif
-              if (lbyz * s2 > lim) continue;
-              const int base = (zz * gy + yy) * gx;
-              const bool shell = (dz == -r || dz == r || dy == -r || dy == r);
-              if (shell) {
-                int x0 = max(cx - r, 0), x1c = min(cx + r, gx - 1);
-                if (prunable) {
-                  while (x0 <= x1c) {
-                    const float gg = cell_gap(ux, x0, slx);
-                    if (fmaf(gg, gg, lbyz) * s2 > lim) x0++; else break;
-                  }
-                  while (x1c >= x0) {
-                    const float gg = cell_gap(ux, x1c, slx);
-                    if (fmaf(gg, gg, lbyz) * s2 > lim) x1c--; else break;
-                  }
-                }
-                if (x0 <= x1c) scan(T[base + x0], T[base + x1c + 1]);
-              } else {  // interior row: only its two new end cells
-                if (cx - r >= 0) {
-                  const float gg = prunable ? cell_gap(ux, cx - r, slx) : 0.f;
-                  if (!(fmaf(gg, gg, lbyz) * s2 > lim)) scan(T[base + cx - r], T[base + cx - r + 1]);
-                }
-                if (cx + r < gx) {
-                  const float gg = prunable ? cell_gap(ux, cx + r, slx) : 0.f;
-                  if (!(fmaf(gg, gg, lbyz) * s2 > lim)) scan(T[base + cx + r], T[base + cx + r + 1]);
-                }
-              }
-            }
-          }
-        }
-        // merge the partial results of the tpp lanes of each source (all lanes of the warp take part)
-        merged = top;
-        for (int off = 1; off < tpp; off <<= 1) {
-          BidTop o;
-          o.best = __shfl_xor_sync(0xffffffffu, merged.best, off);
-          o.better = __shfl_xor_sync(0xffffffffu, merged.better, off);
-          o.bi = __shfl_xor_sync(0xffffffffu, merged.bi, off);
-          merge_top(merged, o, kp);
-        }
-        if (!finished) {
-          known = merged.better;
-          // everything outside the cube of radius r is at least `ext` cells away
-          float ext = inf;
-          if (cx - r > 0) ext = fminf(ext, ux - (float)(cx - r) - slx);
-          if (cx + r + 1 < gx) ext = fminf(ext, (float)(cx + r + 1) - ux - slx);
-          if (cy - r > 0) ext = fminf(ext, uy - (float)(cy - r) - sly);
-          if (cy + r + 1 < gy) ext = fminf(ext, (float)(cy + r + 1) - uy - sly);
-          if (cz - r > 0) ext = fminf(ext, uz - (float)(cz - r) - slz);
-          if (cz + r + 1 < gz) ext = fminf(ext, (float)(cz + r + 1) - uz - slz);
-          const bool covered = (cx - r <= 0) && (cx + r + 1 >= gx) && (cy - r <= 0) && (cy + r + 1 >= gy) &&
-                               (cz - r <= 0) && (cz + r + 1 >= gz);
-          ext = fmaxf(ext, 0.f);
-#ifdef MVP_EMD_DEBUG_NOTERM
-          if (covered) finished = true;
-#else
-          if (covered || (prunable && ext * ext * s2 > reach2(known))) finished = true;
-#endif
-          r++;
-        }
-      }
-      if (valid && g == 0) {
-        const float inc = merged.best - merged.better + eps;
-        st.bid[src] = merged.bi;
-        st.bid_inc[src] = inc;
-        atomic_max_float(st.max_inc + merged.bi, inc);
-      }
-    }
-    }  // grid search
+    refresh_prices(true);
+    bid_phase(ucnt, kp);
     cluster.sync();
 
     // ---- GetMax: bidders within +-1e-6 of the target's maximum; highest source index wins
@@ -739,6 +758,90 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
         assignment[j] = bid_id;
         st.price[bid_id] = __ldcg(st.price + bid_id) + bid_inc;
         st.max_inc[bid_id] = -1e9f;
+      }
+    }
+    cluster.sync();
+  }
+
+  // ---- Tail rounds.  With a few hundred sources left, a round is all latency: five cluster barriers, the price
+  // refresh and the list scan cost more than the bids.  Rank 0 finishes the auction alone: CTA barriers only, the
+  // unassigned list kept in shared memory and updated in place (a winner's slot goes to the source it evicted), the
+  // shared-memory prices authoritative.  Same arithmetic, same tie rules, same global state arrays.
+  if (tail) {
+    if (rank == 0) {
+      int *cur = list, *nxt = list + kEmdTailMax;  // n / C >= 1024 = 2 * kEmdTailMax entries
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int j0 = 0; j0 < n; j0 += kEmdThreads) {
+        const int j = j0 + tid;
+        const bool un = __ldcg(assignment + j) == -1;
+        const unsigned mask = __ballot_sync(0xffffffffu, un);
+        if (mask) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_cnt, __popc(mask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (un) cur[base + __popc(mask & ((1u << lane) - 1u))] = j;
+        }
+      }
+      __syncthreads();
+      refresh_prices(true);
+      for (; it < iters; it++) {
+        const bool last = (it == iters - 1);
+        const int ucnt = s_cnt;
+        if (ucnt == 0) break;
+        KeyParams kp;
+        kp.n = n;
+        {
+          const int block_cnt = n / 1024;
+          const int unass_per_block = (ucnt + block_cnt - 1) / block_cnt;
+          kp.tpu = 1024 / unass_per_block;
+        }
+        if ((long long)ucnt * n > (long long)kEmdThreads * kEmdFullScanEvals) refresh_prices(false);  // grid search: pmin
+        list = cur;  // bid_phase reads the sources from `list`
+        bid_phase(ucnt, kp);
+        __syncthreads();
+        const unsigned long long round_tag = (unsigned long long)(it + 1) << 32;
+        for (int u = tid; u < ucnt; u += kEmdThreads) {  // GetMax
+          const int j = cur[u];
+          const int bid_id = __ldcg(st.bid + j);
+          const float bid_inc = __ldcg(st.bid_inc + j);
+          const float max_inc = __ldcg(st.max_inc + bid_id);
+          if ((double)bid_inc - 1e-6 <= (double)max_inc && (double)max_inc <= (double)bid_inc + 1e-6)
+            atomicMax(st.max_idx + bid_id, round_tag | (unsigned)j);
+        }
+        if (tid == 0) s_cnt2 = 0;
+        __syncthreads();
+        for (int u = tid; u < ucnt; u += kEmdThreads) {  // Assign, and the next round's list
+          const int j = cur[u];
+          const int bid_id = __ldcg(st.bid + j);
+          if (last) {
+            assignment[j] = bid_id;
+          } else if (__ldcg(st.max_idx + bid_id) == (round_tag | (unsigned)j)) {
+            const float bid_inc = __ldcg(st.bid_inc + j);
+            const int ass_inv = __ldcg(st.assignment_inv + bid_id);
+            if (ass_inv != -1) {
+              assignment[ass_inv] = -1;
+              nxt[atomicAdd(&s_cnt2, 1)] = ass_inv;
+            }
+            st.assignment_inv[bid_id] = j;
+            assignment[j] = bid_id;
+            const float newp = __ldcg(st.price + bid_id) + bid_inc;
+            st.price[bid_id] = newp;
+            st.max_inc[bid_id] = -1e9f;
+            // the same price into the sorted copy: the target sits somewhere in its cell's range
+            const int c = cell_of(__ldg(xyz2 + bid_id * 3 + 0), __ldg(xyz2 + bid_id * 3 + 1), __ldg(xyz2 + bid_id * 3 + 2));
+            for (int pos = T[c]; pos < T[c + 1]; pos++)
+              if (orig[pos] == bid_id) tgt[pos].w = newp;
+          } else {
+            nxt[atomicAdd(&s_cnt2, 1)] = j;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt = s_cnt2;
+        int *t = cur;
+        cur = nxt;
+        nxt = t;
+        __syncthreads();
       }
     }
     cluster.sync();

@@ -141,6 +141,174 @@ three_interpolate_grad_staged_kernel(int c, int n, int m, int G, const float *__
   for (int i = threadIdx.x; i < gcount * m; i += kStThreads) gp[i] = rows[i];
 }
 
+// ---- backward through a transposed index (CSR) ---------------------------------------------------------------------
+// grad_points[b,c,j] = sum over the gathered columns p with idx[b,p] == j of grad_out[b,c,p].  The index is shared by
+// all channels of a cloud, so a CTA transposes it ONCE in shared memory (counting sort of the columns by destination:
+// integer shared-memory atomics, which are native — fp32 ones are a CAS loop) and then, channel after channel, brings
+// the grad_out row in by bulk TMA (double-buffered) and lets each thread SUM the columns of its destinations and write
+// the result with a coalesced store.  No floating-point atomics at all, no memset.
+__device__ __forceinline__ void csr_tma_issue(float *dst, const float *src, int count, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count * 4) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   st_smem_u32(dst)),
+               "l"(src), "r"(count * 4), "r"(st_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void csr_bar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(st_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Exclusive scan of start[1 .. rows] in place (start[0] = 0 is kept): start[j + 1] := number of entries with
+// destination < j + 1 ... i.e. after the call start[j] is the first slot of destination j and start[rows] the total.
+// Done in two steps so that start[j + 1] can serve as destination j's fill cursor: see the callers.
+__device__ __forceinline__ void csr_scan(int *start, int rows, int *s_warp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = (rows + kStThreads - 1) / kStThreads;
+  const int c0 = min(tid * chunk, rows), c1 = min(c0 + chunk, rows);
+  int sum = 0;
+  for (int c = c0; c < c1; c++) sum += start[c + 1];
+  int incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < kStThreads / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+  for (int c = c0; c < c1; c++) {  // start[c + 1] := first slot of destination c (its cursor during the fill)
+    const int cnt = start[c + 1];
+    start[c + 1] = run;
+    run += cnt;
+  }
+  __syncthreads();
+}
+
+// grid (channel groups, 1, clouds).  Shared memory: start[n + 1 (+pad)] | perm[mpts] | two row buffers of mpts floats.
+__global__ void __launch_bounds__(kStThreads)
+gather_grad_csr_kernel(int c, int n, int mpts, int G, const float *__restrict__ grad_out, const int *__restrict__ idx,
+                       float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int s_warp[32];
+  const int mp4 = (mpts + 3) & ~3;
+  float *const row0 = reinterpret_cast<float *>(smem_raw), *const row1 = row0 + mp4;
+  int *perm = reinterpret_cast<int *>(smem_raw) + 2 * mp4;
+  int *start = perm + mp4;  // n + 1
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
+  const int *id = idx + (size_t)b * mpts;
+  const float *go = grad_out + ((size_t)b * c + c0) * mpts;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(go) & 15) == 0) && (mpts % 4 == 0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (bulk) csr_tma_issue(row0, go, mpts, &bar[0]);  // the first row streams in while the index is transposed
+  }
+  for (int j = tid; j <= n; j += kStThreads) start[j] = 0;
+  __syncthreads();
+  for (int p = tid; p < mpts; p += kStThreads) atomicAdd(&start[__ldg(id + p) + 1], 1);
+  __syncthreads();
+  csr_scan(start, n, s_warp);
+  for (int p = tid; p < mpts; p += kStThreads) perm[atomicAdd(&start[__ldg(id + p) + 1], 1)] = p;
+  __syncthreads();  // start[j] = first slot of destination j, start[n] = mpts
+
+  float *gp = grad_points + ((size_t)b * c + c0) * n;
+  for (int g = 0; g < gcount; g++) {
+    float *r = (g & 1) ? row1 : row0;
+    if (bulk) {
+      csr_bar_wait(&bar[g & 1], (g >> 1) & 1);
+      if (tid == 0 && g + 1 < gcount) csr_tma_issue((g & 1) ? row0 : row1, go + (size_t)(g + 1) * mpts, mpts, &bar[(g + 1) & 1]);
+    } else {
+      for (int p = tid; p < mpts; p += kStThreads) r[p] = __ldg(go + (size_t)g * mpts + p);
+      __syncthreads();
+    }
+    for (int j = tid; j < n; j += kStThreads) {
+      float acc = 0.f;
+      for (int q = start[j]; q < start[j + 1]; q++) acc = __fadd_rn(acc, r[perm[q]]);
+      gp[(size_t)g * n + j] = acc;
+    }
+    __syncthreads();  // everybody is done with row[g & 1] before it is refilled two iterations later
+  }
+}
+
+// three_interpolate backward: grad_points[b,c,j] = sum over (p,k) with idx[b,p,k] == j of grad_out[b,c,p] * w[b,p,k]
+// (products rounded before the sum, as three_interpolate_cuda.cu:81-83 adds them).
+// Shared memory: two row buffers of n floats | permp[3n] | permw[3n] | start[m + 1].
+__global__ void __launch_bounds__(kStThreads)
+three_interpolate_grad_csr_kernel(int c, int n, int m, int G, const float *__restrict__ grad_out,
+                                  const int *__restrict__ idx, const float *__restrict__ weight,
+                                  float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int s_warp[32];
+  const int n4 = (n + 3) & ~3;
+  float *const row0 = reinterpret_cast<float *>(smem_raw), *const row1 = row0 + n4;
+  int *permp = reinterpret_cast<int *>(smem_raw) + 2 * n4;
+  float *permw = reinterpret_cast<float *>(permp + 3 * n);
+  int *start = reinterpret_cast<int *>(permw + 3 * n);  // m + 1
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
+  const int *id = idx + (size_t)b * n * 3;
+  const float *w = weight + (size_t)b * n * 3;
+  const float *go = grad_out + ((size_t)b * c + c0) * n;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(go) & 15) == 0) && (n % 4 == 0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (bulk) csr_tma_issue(row0, go, n, &bar[0]);
+  }
+  for (int j = tid; j <= m; j += kStThreads) start[j] = 0;
+  __syncthreads();
+  for (int e = tid; e < 3 * n; e += kStThreads) atomicAdd(&start[__ldg(id + e) + 1], 1);
+  __syncthreads();
+  csr_scan(start, m, s_warp);
+  for (int e = tid; e < 3 * n; e += kStThreads) {
+    const int slot = atomicAdd(&start[__ldg(id + e) + 1], 1);
+    permp[slot] = e / 3;
+    permw[slot] = __ldg(w + e);
+  }
+  __syncthreads();
+
+  float *gp = grad_points + ((size_t)b * c + c0) * m;
+  for (int g = 0; g < gcount; g++) {
+    float *r = (g & 1) ? row1 : row0;
+    if (bulk) {
+      csr_bar_wait(&bar[g & 1], (g >> 1) & 1);
+      if (tid == 0 && g + 1 < gcount) csr_tma_issue((g & 1) ? row0 : row1, go + (size_t)(g + 1) * n, n, &bar[(g + 1) & 1]);
+    } else {
+      for (int p = tid; p < n; p += kStThreads) r[p] = __ldg(go + (size_t)g * n + p);
+      __syncthreads();
+    }
+    for (int j = tid; j < m; j += kStThreads) {
+      float acc = 0.f;
+      for (int q = start[j]; q < start[j + 1]; q++) acc = __fadd_rn(acc, __fmul_rn(r[permp[q]], permw[q]));
+      gp[(size_t)g * m + j] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- launch plans --------------------------------------------------------------------------------------------------
 // rows: source columns per channel (n for gather, m for interpolate); cols: gathered columns per channel
 bool staged_applicable(int b, int c, int rows, int cols) {
@@ -184,8 +352,25 @@ int gather_staged_launch(int b, int c, int n, int mpts, const float *points, con
   return launch_status();
 }
 
+// channels per CTA of the CSR kernels: amortise the transposition over several rows, but keep >= ~2 waves of CTAs
+static int csr_group(int b, int c, int ctas_per_sm) {
+  int G = 16;
+  while (G > 2 && (long long)b * ((c + G - 1) / G) < 2LL * ctas_per_sm * kNumSMs) G >>= 1;
+  return std::min(G, c);
+}
+
 int gather_grad_staged_launch(int b, int c, int n, int mpts, const float *grad_out, const int *idx, float *grad_points,
                               cudaStream_t s) {
+  const size_t csr_smem = sizeof(float) * (3 * (size_t)((mpts + 3) & ~3) + n + 1);
+  if (csr_smem <= 200 * 1024) {
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / csr_smem));
+    const int G = csr_group(b, c, per_sm);
+    if (int rc = set_smem<4>(gather_grad_csr_kernel, csr_smem)) return rc;
+    gather_grad_csr_kernel<<<dim3((c + G - 1) / G, 1, b), kStThreads, csr_smem, s>>>(c, n, mpts, G, grad_out, idx,
+                                                                                    grad_points);
+    count_launch();
+    return launch_status();
+  }
   const int G = group_size(c, n), groups = (c + G - 1) / G;
   const size_t smem = (size_t)G * n * 4;
   if (int rc = set_smem<1>(gather_grad_staged_kernel, smem)) return rc;
@@ -208,6 +393,16 @@ int three_interpolate_staged_launch(int b, int c, int m, int n, const float *poi
 
 int three_interpolate_grad_staged_launch(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                          const float *weight, float *grad_points, cudaStream_t s) {
+  const size_t csr_smem = sizeof(float) * (2 * (size_t)((n + 3) & ~3) + 6 * (size_t)n + m + 1);
+  if (csr_smem <= 200 * 1024) {
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / csr_smem));
+    const int G = csr_group(b, c, per_sm);
+    if (int rc = set_smem<5>(three_interpolate_grad_csr_kernel, csr_smem)) return rc;
+    three_interpolate_grad_csr_kernel<<<dim3((c + G - 1) / G, 1, b), kStThreads, csr_smem, s>>>(c, n, m, G, grad_out, idx,
+                                                                                               weight, grad_points);
+    count_launch();
+    return launch_status();
+  }
   const int G = group_size(c, m), groups = (c + G - 1) / G;
   const size_t smem = (size_t)G * m * 4;
   if (int rc = set_smem<3>(three_interpolate_grad_staged_kernel, smem)) return rc;

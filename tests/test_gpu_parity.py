@@ -225,7 +225,9 @@ def test_emd_vs_oracle(gpu, cpu, kind, b, n, eps, iters, algo):
     ("outliers", "uniform", 2, 2048, 0.005, 40), ("constant", "uniform", 2, 1024, 0.005, 20),
     ("uniform", "constant", 2, 1024, 0.005, 20), ("tiny", "tiny", 1, 1024, 0.005, 20),
     ("uniform", "uniform", 70, 1024, 0.005, 50), ("uniform", "uniform", 150, 1024, 0.002, 25),
-    ("uniform", "uniform", 2, 2048, -0.001, 10), ("lattice", "duplicates", 2, 2048, 0.01, 40)])
+    ("uniform", "uniform", 2, 2048, -0.001, 10), ("lattice", "duplicates", 2, 2048, 0.01, 40),
+    ("uniform", "uniform", 4, 2048, 0.005, 3000), ("sphere", "sphere", 2, 8192, 0.005, 600),
+    ("uniform", "uniform", 2, 1024, 0.02, 3000)])
 def test_emd_grid_is_bit_identical_to_full_scan(gpu, kind1, kind2, b, n, eps, iters):
     """The grid-pruned Bid search (default for n <= 8192) against the full scan, on benign and hostile
     distributions, several cluster sizes (b = 3 -> 8 CTAs per cloud ... b = 150 -> 1) and a negative eps
