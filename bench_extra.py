@@ -22,6 +22,136 @@ def _time(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
+def vrcnet_census(dev, g, have_ref):
+    """Every call into the operator library that one VRCNet training step makes (forward + backward), at the
+    shapes of cfgs/vrcnet.yaml with B=32 (the ops see 2B=64 after vrcnet.py:452-454) — SURVEY.md §3.1 / §A3:
+    5 FPS, 9 gathers, 3 groupings, 3 three_nn, 3 three_interpolate, 4 Chamfer forward+backward, and the backward
+    scatters of the feature gathers / groupings / interpolations.  The dense layers between them (cuDNN / cuBLAS
+    through PyTorch) are outside the operator boundary and not part of this number.  Ours through the C ABI with
+    preallocated outputs; the reference's kernels through oracle/ref_cuda (which allocates its outputs the way the
+    reference's Python does)."""
+    import mm3d_pn2 as mm  # noqa: F401  (ensures the package is importable from the mirror)
+    from mvp_benchmark_b200 import _lib
+    from oracle import ref_cuda
+    L, P = _lib.lib, _lib.ptr
+    R = lambda *s: torch.rand(*s, device=dev, generator=g)  # noqa: E731
+    N = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
+    I = lambda hi, *s: torch.randint(0, hi, s, device=dev, generator=g, dtype=torch.int32)  # noqa: E731
+    E = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+    EI = lambda *s: torch.empty(*s, device=dev, dtype=torch.int32)  # noqa: E731
+    S = _lib.stream_of(R(1))
+    ours, ref, kinds, rkinds = [], [], [], []
+
+    class _Tagged(list):  # list whose append also records the op class of the entry
+        def __init__(self, tags):
+            super().__init__()
+            self.tags, self.tag = tags, None
+
+        def append(self, fn):
+            super().append(fn)
+            self.tags.append(self.tag)
+
+    ours, ref = _Tagged(kinds), _Tagged(rkinds)
+
+    def tag(name):
+        ours.tag = ref.tag = name
+
+    def fps(b, n, m):
+        tag("fps")
+        x, o = R(b, n, 3), EI(b, m)
+        ours.append(lambda: L.mvp_furthest_point_sampling(b, n, m, P(x), None, P(o), S))
+        ref.append(lambda: ref_cuda.furthest_point_sample(x, m))
+
+    def gather(b, c, n, m, grad):
+        tag("gather_points fwd+bwd")
+        f, i, o = N(b, c, n), I(n, b, m), E(b, c, m)
+        ours.append(lambda: L.mvp_gather_points(b, c, n, m, P(f), P(i), P(o), S))
+        ref.append(lambda: ref_cuda.gather_points(f, i))
+        if grad:
+            go, gp = N(b, c, m), E(b, c, n)
+            ws = _lib.workspace(L.mvp_scatter_workspace_bytes(b, n, m), dev)
+            ours.append(lambda: L.mvp_gather_points_grad_ws(b, c, n, m, P(go), P(i), P(gp), P(ws), ws.numel(), S))
+            ref.append(lambda: ref_cuda.gather_points_grad(go, i, n))
+
+    def group(b, c, n, p, s_):
+        tag("grouping_operation fwd+bwd")
+        f, i, o = N(b, c, n), I(n, b, p, s_), E(b, c, p, s_)
+        go, gp = N(b, c, p, s_), E(b, c, n)
+        ours.append(lambda: L.mvp_group_points(b, c, n, p, s_, P(f), P(i), P(o), S))
+        ws = _lib.workspace(L.mvp_scatter_workspace_bytes(b, n, p * s_), dev)
+        ours.append(lambda: L.mvp_group_points_grad_ws(b, c, n, p, s_, P(go), P(i), P(gp), P(ws), ws.numel(), S))
+        ref.append(lambda: ref_cuda.group_points(f, i))
+        ref.append(lambda: ref_cuda.group_points_grad(go, i, n))
+
+    def unpool(b, c, m, n):  # three_nn (n targets from m sources) + three_interpolate forward / backward
+        tag("three_nn + three_interpolate fwd+bwd")
+        u, k, d, i = R(b, n, 3), R(b, m, 3), E(b, n, 3), EI(b, n, 3)
+        f, w, o, go, gp = N(b, c, m), R(b, n, 3), E(b, c, n), N(b, c, n), E(b, c, m)
+        i3 = I(m, b, n, 3)
+        ours.append(lambda: L.mvp_three_nn(b, n, m, P(u), P(k), P(d), P(i), S))
+        ours.append(lambda: L.mvp_three_interpolate(b, c, m, n, P(f), P(i3), P(w), P(o), S))
+        ws = _lib.workspace(L.mvp_scatter_workspace_bytes(b, m, 3 * n), dev)
+        ours.append(lambda: L.mvp_three_interpolate_grad_ws(b, c, n, m, P(go), P(i3), P(w), P(gp), P(ws), ws.numel(), S))
+        ref.append(lambda: ref_cuda.three_nn(u, k))
+        ref.append(lambda: ref_cuda.three_interpolate(f, i3, w))
+        ref.append(lambda: ref_cuda.three_interpolate_grad(go, i3, w, m))
+
+    def chamfer(b, n, m):
+        tag("chamfer fwd+bwd")
+        a, c_ = R(b, n, 3), R(b, m, 3)
+        d1, d2, i1, i2 = E(b, n), E(b, m), EI(b, n), EI(b, m)
+        g1, g2, gx = R(b, n), R(b, m), E(b * (n + m) * 3)
+        ws = _lib.workspace(L.mvp_chamfer_forward_workspace_bytes(b, n, m), dev)
+        ours.append(lambda: L.mvp_chamfer_forward(b, n, m, P(a), P(c_), P(d1), P(d2), P(i1), P(i2), P(ws), ws.numel(), S))
+        ours.append(lambda: L.mvp_chamfer_backward(b, n, m, P(a), P(c_), P(g1), P(g2), P(i1), P(i2), P(gx[:b * n * 3]),
+                                                   P(gx[b * n * 3:]), S))
+
+        def ref_cd():
+            o1, o2, j1, j2 = ref_cuda.chamfer_forward(a, c_)
+            ref_cuda.chamfer_backward(a, c_, g1, g2, j1, j2)
+        ref.append(ref_cd)
+
+    fps(32, 2048, 2048), gather(32, 3, 2048, 2048, False)                         # vrcnet.py:451
+    for n, c in ((3072, 64), (1536, 128), (768, 256)):                            # vrcnet.py:255-273, model_utils.py:88-110
+        fps(64, n, n // 2), gather(64, 3, n, n // 2, False), gather(64, c, n, 10 * (n // 2), True), group(64, c, n, n // 2, 1)
+    for c, m in ((512, 384), (256, 768), (128, 1536)):                            # vrcnet.py:288-292
+        unpool(64, c, m, 2 * m)
+    fps(64, 3072, 2048), gather(64, 3, 3072, 2048, False), gather(64, 64, 3072, 2048, True)   # vrcnet.py:380-383
+    for m in (1024, 3072, 2048, 2048):                                            # vrcnet.py:509-512
+        chamfer(64, 2048, m)
+
+    def run_all(fns):
+        for f in fns:
+            rc = f()
+            if isinstance(rc, int) and rc != 0:
+                raise RuntimeError(f"operator call failed with code {rc}")
+
+    res = {"calls": len(ours), "ours_ms": _time(lambda: run_all(ours), 5, 2)}
+    if have_ref:
+        res["ref_cuda_ms"] = _time(lambda: run_all(ref), 5, 2)
+        res["speedup_vs_ref_cuda"] = res["ref_cuda_ms"] / res["ours_ms"]
+    by = {}
+    for fns, tags, col in ((ours, kinds, "ours_ms"),) + (((ref, rkinds, "ref_cuda_ms"),) if have_ref else ()):
+        for name in dict.fromkeys(tags):
+            sel = [f for f, t in zip(fns, tags) if t == name]
+            by.setdefault(name, {})[col] = round(_time(lambda: run_all(sel), 5, 2), 4)
+    res["by_operator"] = by
+    # the same calls replayed from one CUDA graph: device time without per-call host work
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        S2 = _lib.stream_of(R(1))
+        S.value = S2.value
+        run_all(ours)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            run_all(ours)
+    torch.cuda.synchronize()
+    res["ours_cuda_graph_ms"] = _time(graph.replay, 5, 2)
+    return res
+
+
 def run(dev, hbm_gbs=None):
     import json
     import os
@@ -122,7 +252,9 @@ def run(dev, hbm_gbs=None):
         go = torch.randn(bb, c, mp, device=dev, generator=g)
         gp = torch.empty(bb, c, nn, device=dev)
         fwd = lambda: _lib.check(L.mvp_gather_points(bb, c, nn, mp, P(feat), P(idx), P(out), S(feat)), "gather")  # noqa: E731
-        bwd = lambda: _lib.check(L.mvp_gather_points_grad(bb, c, nn, mp, P(go), P(idx), P(gp), S(go)), "gather grad")  # noqa: E731
+        ws = _lib.workspace(L.mvp_scatter_workspace_bytes(bb, nn, mp), dev)
+        bwd = lambda: _lib.check(L.mvp_gather_points_grad_ws(bb, c, nn, mp, P(go), P(idx), P(gp), P(ws), ws.numel(), S(go)),  # noqa: E731
+                                 "gather grad")
         entry(f"gather_points_{tag}", _time(fwd), _time(lambda: ref_cuda.gather_points(feat, idx)) if have_ref else None,
               float(bb) * c * mp, "elements/s", 4.0 * bb * mp * (2 * c + 1))
         entry(f"gather_points_grad_{tag}", _time(bwd),
@@ -141,7 +273,9 @@ def run(dev, hbm_gbs=None):
         go = torch.randn(bb, c, n_, device=dev, generator=g)
         gp = torch.empty(bb, c, m_, device=dev)
         fwd = lambda: _lib.check(L.mvp_three_interpolate(bb, c, m_, n_, P(f), P(i3), P(w), P(out), S(f)), "interp")  # noqa: E731
-        bwd = lambda: _lib.check(L.mvp_three_interpolate_grad(bb, c, n_, m_, P(go), P(i3), P(w), P(gp), S(go)), "interp grad")  # noqa: E731
+        ws = _lib.workspace(L.mvp_scatter_workspace_bytes(bb, m_, 3 * n_), dev)
+        bwd = lambda: _lib.check(L.mvp_three_interpolate_grad_ws(bb, c, n_, m_, P(go), P(i3), P(w), P(gp), P(ws), ws.numel(),  # noqa: E731
+                                                                 S(go)), "interp grad")
         entry(f"three_interpolate_{tag}", _time(fwd),
               _time(lambda: ref_cuda.three_interpolate(f, i3, w)) if have_ref else None, float(bb) * c * n_, "elements/s",
               4.0 * bb * n_ * (2 * c + 6))
@@ -156,6 +290,7 @@ def run(dev, hbm_gbs=None):
     entry("three_nn_64x3072_from_1536", _time(lambda: mm.three_nn(u, k)),
           _time(lambda: ref_cuda.three_nn(u, k)) if have_ref else None, 64.0 * 3072 * 1536, "point-pairs/s",
           12.0 * 64 * (3072 + 1536) + 24.0 * 64 * 3072)
+    out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
     xyz, ctr = R(32, 2048, 3), R(32, 102, 3)
     entry("ball_query_32x2048_102centres_ns12", _time(lambda: mm.ball_query(0, 0.0774596669, 12, xyz, ctr)),
           _time(lambda: ref_cuda.ball_query(0, 0.0774596669, 12, xyz, ctr)) if have_ref else None, 32.0 * 102,

@@ -168,6 +168,27 @@ int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
             float *dist2, mvp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The backward scatters again, with a caller-provided workspace (same results, faster): the index is
+ * transposed once per cloud into the workspace (start[rows + 1] | perm[entries]) and every gradient
+ * element is then SUMMED by one thread and written once — no floating-point atomics, no memset.
+ *   rows    = destination columns per channel (n of gather / group, m of three_interpolate)
+ *   entries = index entries per cloud (npoints, npoints*nsample, 3*n of three_interpolate)
+ * mvp_scatter_workspace_bytes(b, rows, entries) bytes, 16-byte aligned.  Shapes for which this path
+ * is not the faster one (rows of grad_out above 32 KB, fewer entries than destinations, rows > 49152)
+ * and a missing / short workspace fall back to the functions above.
+ * ------------------------------------------------------------------------------------------- */
+size_t mvp_scatter_workspace_bytes(int b, int rows, int entries);
+int mvp_gather_points_grad_ws(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                              float *grad_points, void *workspace, size_t workspace_bytes,
+                              mvp_stream_t stream);
+int mvp_group_points_grad_ws(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                             const int *idx, float *grad_points, void *workspace,
+                             size_t workspace_bytes, mvp_stream_t stream);
+int mvp_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                  const float *weight, float *grad_points, void *workspace,
+                                  size_t workspace_bytes, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ def _load():
         "mvp_three_nn": (_c_int, [_c_int] * 3 + [_p] * 4 + [_p]),
         "mvp_three_interpolate": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
         "mvp_three_interpolate_grad": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
+        "mvp_scatter_workspace_bytes": (_c_size_t, [_c_int] * 3),
+        "mvp_gather_points_grad_ws": (_c_int, [_c_int] * 4 + [_p] * 4 + [_c_size_t, _p]),
+        "mvp_group_points_grad_ws": (_c_int, [_c_int] * 5 + [_p] * 4 + [_c_size_t, _p]),
+        "mvp_three_interpolate_grad_ws": (_c_int, [_c_int] * 4 + [_p] * 5 + [_c_size_t, _p]),
         "mvp_knn": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
     }
     for name, (res, args) in sig.items():

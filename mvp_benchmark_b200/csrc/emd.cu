@@ -306,10 +306,6 @@ constexpr int kEmdGridMaxN = 8192;
 #ifndef MVP_EMD_FULLSCAN_EVALS
 #define MVP_EMD_FULLSCAN_EVALS 48
 #endif
-#ifndef MVP_EMD_TAIL_MAX
-#define MVP_EMD_TAIL_MAX 512
-#endif
-constexpr int kEmdTailMax = MVP_EMD_TAIL_MAX;  // unassigned sources (whole cloud) at which one CTA takes over; <= 512
 constexpr int kEmdFullScanEvals = MVP_EMD_FULLSCAN_EVALS;  // per-thread evaluations up to which a full scan is used
 
 __global__ void __launch_bounds__(kEmdThreads, 1)
@@ -328,7 +324,7 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
   int *orig = reinterpret_cast<int *>(smem_raw + (size_t)n * 16);        // n: original index of a sorted target
   int *T = orig + n;                                                     // cap + 1 (padded to 4): cell starts
   int *list = T + ((cap + 1 + 3) & ~3);                                  // n / C: unassigned sources of this CTA
-  __shared__ int s_cnt, s_cnt2;
+  __shared__ int s_cnt;
   __shared__ int s_total;  // read by the other CTAs of the cluster through DSMEM
   __shared__ float s_red[6][32];
   __shared__ int s_int[32];
@@ -461,14 +457,13 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
 
   const float s2 = h.s * h.s * (1.f - 1e-5f);  // cells^2 -> squared distance, rounded down generously
 
-  // ---- the pieces of a round that the cluster-wide rounds and the single-CTA tail rounds share
-  // current prices (global, indexed by original target) into the sorted copy; their minimum bounds every
-  // unvisited target's value.  from_global = false: the copy is authoritative (tail rounds), only the minimum.
-  auto refresh_prices = [&](bool from_global) {
+  // current prices (global, indexed by original target) into the sorted copy; their minimum bounds every unvisited
+  // target's value
+  auto refresh_prices = [&]() {
   {
     float pm = inf;
     for (int pos = tid; pos < n; pos += kEmdThreads) {
-      const float p = from_global ? __ldcg(st.price + orig[pos]) : tgt[pos].w;
+      const float p = __ldcg(st.price + orig[pos]);
       tgt[pos].w = p;
       pm = fminf(pm, p);
     }
@@ -691,9 +686,7 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
   }  // grid search
   };
 
-  int it = 0;
-  bool tail = false;
-  for (; it < iters; it++) {
+  for (int it = 0; it < iters; it++) {
     const bool last = (it == iters - 1);
     // ---- list the unassigned sources of the own slice (order is irrelevant, as in calc_unass_idx :85-93)
     if (tid == 0) s_cnt = 0;
@@ -716,10 +709,6 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
     int total = 0;
     for (int r = 0; r < C; r++) total += *cluster.map_shared_rank(&s_total, r);
     if (total == 0) break;  // converged: every later round is a no-op
-    if (total <= kEmdTailMax) {  // the long tail: one CTA finishes the auction alone (below)
-      tail = true;
-      break;
-    }
     KeyParams kp;
     kp.n = n;
     {
@@ -728,7 +717,7 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
       kp.tpu = 1024 / unass_per_block;
     }
 
-    refresh_prices(true);
+    refresh_prices();
     bid_phase(ucnt, kp);
     cluster.sync();
 
@@ -758,90 +747,6 @@ emd_auction_grid_kernel(int n, int cap, float eps, int iters, const float *__res
         assignment[j] = bid_id;
         st.price[bid_id] = __ldcg(st.price + bid_id) + bid_inc;
         st.max_inc[bid_id] = -1e9f;
-      }
-    }
-    cluster.sync();
-  }
-
-  // ---- Tail rounds.  With a few hundred sources left, a round is all latency: five cluster barriers, the price
-  // refresh and the list scan cost more than the bids.  Rank 0 finishes the auction alone: CTA barriers only, the
-  // unassigned list kept in shared memory and updated in place (a winner's slot goes to the source it evicted), the
-  // shared-memory prices authoritative.  Same arithmetic, same tie rules, same global state arrays.
-  if (tail) {
-    if (rank == 0) {
-      int *cur = list, *nxt = list + kEmdTailMax;  // n / C >= 1024 = 2 * kEmdTailMax entries
-      if (tid == 0) s_cnt = 0;
-      __syncthreads();
-      for (int j0 = 0; j0 < n; j0 += kEmdThreads) {
-        const int j = j0 + tid;
-        const bool un = __ldcg(assignment + j) == -1;
-        const unsigned mask = __ballot_sync(0xffffffffu, un);
-        if (mask) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_cnt, __popc(mask));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (un) cur[base + __popc(mask & ((1u << lane) - 1u))] = j;
-        }
-      }
-      __syncthreads();
-      refresh_prices(true);
-      for (; it < iters; it++) {
-        const bool last = (it == iters - 1);
-        const int ucnt = s_cnt;
-        if (ucnt == 0) break;
-        KeyParams kp;
-        kp.n = n;
-        {
-          const int block_cnt = n / 1024;
-          const int unass_per_block = (ucnt + block_cnt - 1) / block_cnt;
-          kp.tpu = 1024 / unass_per_block;
-        }
-        if ((long long)ucnt * n > (long long)kEmdThreads * kEmdFullScanEvals) refresh_prices(false);  // grid search: pmin
-        list = cur;  // bid_phase reads the sources from `list`
-        bid_phase(ucnt, kp);
-        __syncthreads();
-        const unsigned long long round_tag = (unsigned long long)(it + 1) << 32;
-        for (int u = tid; u < ucnt; u += kEmdThreads) {  // GetMax
-          const int j = cur[u];
-          const int bid_id = __ldcg(st.bid + j);
-          const float bid_inc = __ldcg(st.bid_inc + j);
-          const float max_inc = __ldcg(st.max_inc + bid_id);
-          if ((double)bid_inc - 1e-6 <= (double)max_inc && (double)max_inc <= (double)bid_inc + 1e-6)
-            atomicMax(st.max_idx + bid_id, round_tag | (unsigned)j);
-        }
-        if (tid == 0) s_cnt2 = 0;
-        __syncthreads();
-        for (int u = tid; u < ucnt; u += kEmdThreads) {  // Assign, and the next round's list
-          const int j = cur[u];
-          const int bid_id = __ldcg(st.bid + j);
-          if (last) {
-            assignment[j] = bid_id;
-          } else if (__ldcg(st.max_idx + bid_id) == (round_tag | (unsigned)j)) {
-            const float bid_inc = __ldcg(st.bid_inc + j);
-            const int ass_inv = __ldcg(st.assignment_inv + bid_id);
-            if (ass_inv != -1) {
-              assignment[ass_inv] = -1;
-              nxt[atomicAdd(&s_cnt2, 1)] = ass_inv;
-            }
-            st.assignment_inv[bid_id] = j;
-            assignment[j] = bid_id;
-            const float newp = __ldcg(st.price + bid_id) + bid_inc;
-            st.price[bid_id] = newp;
-            st.max_inc[bid_id] = -1e9f;
-            // the same price into the sorted copy: the target sits somewhere in its cell's range
-            const int c = cell_of(__ldg(xyz2 + bid_id * 3 + 0), __ldg(xyz2 + bid_id * 3 + 1), __ldg(xyz2 + bid_id * 3 + 2));
-            for (int pos = T[c]; pos < T[c + 1]; pos++)
-              if (orig[pos] == bid_id) tgt[pos].w = newp;
-          } else {
-            nxt[atomicAdd(&s_cnt2, 1)] = j;
-          }
-        }
-        __syncthreads();
-        if (tid == 0) s_cnt = s_cnt2;
-        int *t = cur;
-        cur = nxt;
-        nxt = t;
-        __syncthreads();
       }
     }
     cluster.sync();

@@ -314,6 +314,9 @@ int three_interpolate_staged_launch(int b, int c, int m, int n, const float *poi
                                     float *out, cudaStream_t s);
 int three_interpolate_grad_staged_launch(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                          const float *weight, float *grad_points, cudaStream_t s);
+size_t scatter_csr_workspace_bytes(int b, int rows, int entries);
+int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const float *grad_out, const int *idx,
+                       const float *weight, float *grad_points, void *workspace, size_t workspace_bytes, cudaStream_t s);
 
 static int gather_launch(int b, int c, int n, int mpts, const float *points, const int *idx, float *out,
                          cudaStream_t s) {
@@ -426,6 +429,37 @@ MVP_API int mvp_gather_points_grad(int b, int c, int n, int npoints, const float
   return gather_grad_launch(b, c, n, npoints, grad_out, idx, grad_points, (cudaStream_t)stream);
 }
 
+MVP_API size_t mvp_scatter_workspace_bytes(int b, int rows, int entries) {
+  return scatter_csr_workspace_bytes(b, rows, entries);
+}
+
+// With a workspace the backward scatters go through a transposed index (pointnet2_staged.cu); shapes that path does
+// not cover fall back to the workspace-free kernels.
+static int gather_grad_ws(int b, int c, int n, int mpts, const float *grad_out, const int *idx, float *grad_points,
+                          void *workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (bad_dims(b, c, n, mpts)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b > 0 && c > 0 && n > 0 && mpts > 0 && grad_out && idx && grad_points) {
+    const int rc = scatter_csr_launch(false, b, c, n, mpts, grad_out, idx, nullptr, grad_points, workspace,
+                                      workspace_bytes, s);
+    if (rc != -100) return rc;
+  }
+  return gather_grad_launch(b, c, n, mpts, grad_out, idx, grad_points, s);
+}
+
+MVP_API int mvp_gather_points_grad_ws(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                      float *grad_points, void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+  return gather_grad_ws(b, c, n, npoints, grad_out, idx, grad_points, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+MVP_API int mvp_group_points_grad_ws(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                     const int *idx, float *grad_points, void *workspace, size_t workspace_bytes,
+                                     mvp_stream_t stream) {
+  if (npoints < 0 || nsample < 0 || (long long)npoints * nsample > 0x7fffffffLL)
+    return MVP_ERR_INVALID_ARGUMENT;
+  return gather_grad_ws(b, c, n, npoints * nsample, grad_out, idx, grad_points, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
 MVP_API int mvp_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                              const int *idx, float *out, mvp_stream_t stream) {
   if (npoints < 0 || nsample < 0 || (long long)npoints * nsample > 0x7fffffffLL)
@@ -458,6 +492,21 @@ MVP_API int mvp_three_interpolate(int b, int c, int m, int n, const float *point
     count_launch();
   }
   return launch_status();
+}
+
+MVP_API int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                       const float *weight, float *grad_points, mvp_stream_t stream);
+
+MVP_API int mvp_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                          const float *weight, float *grad_points, void *workspace,
+                                          size_t workspace_bytes, mvp_stream_t stream) {
+  if (bad_dims(b, c, m, n)) return MVP_ERR_INVALID_ARGUMENT;
+  if (b > 0 && c > 0 && m > 0 && n > 0 && (long long)n * 3 <= 0x7fffffffLL && grad_out && idx && weight && grad_points) {
+    const int rc = scatter_csr_launch(true, b, c, m, n, grad_out, idx, weight, grad_points, workspace, workspace_bytes,
+                                      (cudaStream_t)stream);
+    if (rc != -100) return rc;
+  }
+  return mvp_three_interpolate_grad(b, c, n, m, grad_out, idx, weight, grad_points, stream);
 }
 
 MVP_API int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,

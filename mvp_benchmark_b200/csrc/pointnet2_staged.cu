@@ -20,6 +20,17 @@ namespace mvp {
 constexpr int kStThreads = 512;
 constexpr size_t kStRowBytes = 64 * 1024;  // shared-memory budget for the staged rows of a CTA (3 CTAs / SM)
 
+// opt in to > 48 KB of dynamic shared memory, once per kernel (TAG names the kernel: one high-water mark each) and size
+template <int TAG, typename K>
+static int set_smem(K kernel, size_t bytes) {
+  static size_t granted = 40 * 1024;  // static + dynamic share the default 48 KB: opt in a little below it
+  if (bytes <= granted) return MVP_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  granted = bytes;
+  return MVP_OK;
+}
+
 __device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // rows[0 .. count) <- src[0 .. count): bulk TMA when 16-byte aligned, else plain loads.  Ends with a CTA barrier.
@@ -69,7 +80,10 @@ gather_staged_kernel(int c, int n, int mpts, int G, int chunk, const float *__re
   }
 }
 
-// grid (channel groups, 1, clouds): a CTA produces G complete gradient rows
+// grid (channel groups, 1, clouds): a CTA produces G complete gradient rows.  kVec: four consecutive columns per
+// thread and 128-bit loads of idx / grad_out (rows 16-byte aligned, mpts % 4 == 0) — the loads of a warp are what keeps
+// HBM busy while its lanes spin in the shared-memory CAS loops, so each one should carry as many bytes as possible.
+template <bool kVec>
 __global__ void __launch_bounds__(kStThreads)
 gather_grad_staged_kernel(int c, int n, int mpts, int G, const float *__restrict__ grad_out,
                           const int *__restrict__ idx, float *__restrict__ grad_points) {
@@ -79,10 +93,25 @@ gather_grad_staged_kernel(int c, int n, int mpts, int G, const float *__restrict
   __syncthreads();
   const int *id = idx + (size_t)b * mpts;
   const float *go = grad_out + ((size_t)b * c + c0) * mpts;
-  for (int p = threadIdx.x; p < mpts; p += kStThreads) {
-    const int dst = __ldg(id + p);
+  if (kVec) {
+    for (int p = threadIdx.x * 4; p < mpts; p += kStThreads * 4) {
+      const int4 dst = __ldg(reinterpret_cast<const int4 *>(id + p));
+#pragma unroll 2
+      for (int g = 0; g < gcount; g++) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(go + (size_t)g * mpts + p));
+        float *r = rows + g * n;
+        atomicAdd(r + dst.x, v.x);
+        atomicAdd(r + dst.y, v.y);
+        atomicAdd(r + dst.z, v.z);
+        atomicAdd(r + dst.w, v.w);
+      }
+    }
+  } else {
+    for (int p = threadIdx.x; p < mpts; p += kStThreads) {
+      const int dst = __ldg(id + p);
 #pragma unroll 4
-    for (int g = 0; g < gcount; g++) atomicAdd(&rows[g * n + dst], __ldg(go + (size_t)g * mpts + p));
+      for (int g = 0; g < gcount; g++) atomicAdd(&rows[g * n + dst], __ldg(go + (size_t)g * mpts + p));
+    }
   }
   __syncthreads();
   float *gp = grad_points + ((size_t)b * c + c0) * n;
@@ -113,6 +142,9 @@ three_interpolate_staged_kernel(int c, int m, int n, int G, int chunk, const flo
   }
 }
 
+// kVec: four consecutive targets per thread — grad_out read as float4, their 12 indices and 12 weights as 3 + 3
+// 128-bit loads (n % 4 == 0, 16-byte aligned rows).
+template <bool kVec>
 __global__ void __launch_bounds__(kStThreads)
 three_interpolate_grad_staged_kernel(int c, int n, int m, int G, const float *__restrict__ grad_out,
                                      const int *__restrict__ idx, const float *__restrict__ weight,
@@ -122,18 +154,41 @@ three_interpolate_grad_staged_kernel(int c, int n, int m, int G, const float *__
   for (int i = threadIdx.x; i < gcount * m; i += kStThreads) rows[i] = 0.f;
   __syncthreads();
   const float *go = grad_out + ((size_t)b * c + c0) * n;
-  for (int p = threadIdx.x; p < n; p += kStThreads) {
-    const int *id = idx + ((size_t)b * n + p) * 3;
-    const float *w = weight + ((size_t)b * n + p) * 3;
-    const int i0 = __ldg(id + 0), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
-    const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  if (kVec) {
+    for (int p = threadIdx.x * 4; p < n; p += kStThreads * 4) {
+      int id[12];
+      float w[12];
+      const int4 *ip = reinterpret_cast<const int4 *>(idx + ((size_t)b * n + p) * 3);
+      const float4 *wp = reinterpret_cast<const float4 *>(weight + ((size_t)b * n + p) * 3);
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        const int4 a = __ldg(ip + v);
+        const float4 f = __ldg(wp + v);
+        id[4 * v + 0] = a.x, id[4 * v + 1] = a.y, id[4 * v + 2] = a.z, id[4 * v + 3] = a.w;
+        w[4 * v + 0] = f.x, w[4 * v + 1] = f.y, w[4 * v + 2] = f.z, w[4 * v + 3] = f.w;
+      }
+      for (int g = 0; g < gcount; g++) {
+        const float4 gr4 = __ldg(reinterpret_cast<const float4 *>(go + (size_t)g * n + p));
+        const float gr[4] = {gr4.x, gr4.y, gr4.z, gr4.w};
+        float *r = rows + g * m;
+#pragma unroll
+        for (int e = 0; e < 12; e++) atomicAdd(r + id[e], __fmul_rn(gr[e / 3], w[e]));
+      }
+    }
+  } else {
+    for (int p = threadIdx.x; p < n; p += kStThreads) {
+      const int *id = idx + ((size_t)b * n + p) * 3;
+      const float *w = weight + ((size_t)b * n + p) * 3;
+      const int i0 = __ldg(id + 0), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+      const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
 #pragma unroll 4
-    for (int g = 0; g < gcount; g++) {
-      const float gr = __ldg(go + (size_t)g * n + p);
-      float *r = rows + g * m;
-      atomicAdd(r + i0, __fmul_rn(gr, w0));
-      atomicAdd(r + i1, __fmul_rn(gr, w1));
-      atomicAdd(r + i2, __fmul_rn(gr, w2));
+      for (int g = 0; g < gcount; g++) {
+        const float gr = __ldg(go + (size_t)g * n + p);
+        float *r = rows + g * m;
+        atomicAdd(r + i0, __fmul_rn(gr, w0));
+        atomicAdd(r + i1, __fmul_rn(gr, w1));
+        atomicAdd(r + i2, __fmul_rn(gr, w2));
+      }
     }
   }
   __syncthreads();
@@ -141,37 +196,34 @@ three_interpolate_grad_staged_kernel(int c, int n, int m, int G, const float *__
   for (int i = threadIdx.x; i < gcount * m; i += kStThreads) gp[i] = rows[i];
 }
 
-// ---- backward through a transposed index (CSR) ---------------------------------------------------------------------
-// grad_points[b,c,j] = sum over the gathered columns p with idx[b,p] == j of grad_out[b,c,p].  The index is shared by
-// all channels of a cloud, so a CTA transposes it ONCE in shared memory (counting sort of the columns by destination:
-// integer shared-memory atomics, which are native — fp32 ones are a CAS loop) and then, channel after channel, brings
-// the grad_out row in by bulk TMA (double-buffered) and lets each thread SUM the columns of its destinations and write
-// the result with a coalesced store.  No floating-point atomics at all, no memset.
-__device__ __forceinline__ void csr_tma_issue(float *dst, const float *src, int count, uint64_t *bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count * 4) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   st_smem_u32(dst)),
-               "l"(src), "r"(count * 4), "r"(st_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void csr_bar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(st_smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
+// ---- backward through a transposed index (CSR in a caller-provided workspace) -----------------------------------------
+// grad_points[b,c,j] = sum over the gathered columns p with idx[b,p] == j of grad_out[b,c,p] (times a weight for
+// three_interpolate).  The index is shared by all channels of a cloud, so it is transposed ONCE per cloud
+// (scatter_csr_build_kernel: counting sort of the entries by destination with integer shared-memory atomics, which are
+// native — fp32 ones are a CAS loop) into the workspace:  start[rows + 1] | perm[entries]  per cloud.  The consumers
+// then bring G grad_out rows into shared memory with one bulk TMA copy and let every thread SUM the entries of its
+// destinations and write the result with a coalesced store: no floating-point atomics, no memset, three CTAs per SM
+// overlapping each other's copies.
+constexpr int kCsrThreads = 1024;
+constexpr int kCsrMaxRows = 48 * 1024;  // start[] lives in shared memory during the build (192 KB)
 
-// Exclusive scan of start[1 .. rows] in place (start[0] = 0 is kept): start[j + 1] := number of entries with
-// destination < j + 1 ... i.e. after the call start[j] is the first slot of destination j and start[rows] the total.
-// Done in two steps so that start[j + 1] can serve as destination j's fill cursor: see the callers.
-__device__ __forceinline__ void csr_scan(int *start, int rows, int *s_warp) {
+static size_t csr_cloud_ints(int rows, int entries) { return ((size_t)rows + 1 + entries + 3) & ~(size_t)3; }
+
+// grid (clouds).  idx: `entries` destinations per cloud (entry e of gather: column e; of interpolate: (target e/3, k = e%3)).
+__global__ void __launch_bounds__(kCsrThreads, 1)
+scatter_csr_build_kernel(int rows, int entries, size_t cloud_ints, const int *__restrict__ idx, int *__restrict__ ws) {
+  extern __shared__ int start[];  // rows + 1
+  __shared__ int s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = (rows + kStThreads - 1) / kStThreads;
+  const int *id = idx + (size_t)blockIdx.x * entries;
+  int *out_start = ws + (size_t)blockIdx.x * cloud_ints, *perm = out_start + rows + 1;
+  for (int j = tid; j <= rows; j += kCsrThreads) start[j] = 0;
+  __syncthreads();
+  for (int e = tid; e < entries; e += kCsrThreads) atomicAdd(&start[__ldg(id + e) + 1], 1);
+  __syncthreads();
+  // exclusive scan of the counts: start[j + 1] := first slot of destination j (its cursor during the fill, after which
+  // it has advanced to the first slot of destination j + 1); start[0] stays 0
+  const int chunk = (rows + kCsrThreads - 1) / kCsrThreads;
   const int c0 = min(tid * chunk, rows), c1 = min(c0 + chunk, rows);
   int sum = 0;
   for (int c = c0; c < c1; c++) sum += start[c + 1];
@@ -184,7 +236,7 @@ __device__ __forceinline__ void csr_scan(int *start, int rows, int *s_warp) {
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int v = lane < kStThreads / 32 ? s_warp[lane] : 0;
+    int v = s_warp[lane];
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const int u = __shfl_up_sync(0xffffffffu, v, off);
@@ -194,119 +246,104 @@ __device__ __forceinline__ void csr_scan(int *start, int rows, int *s_warp) {
   }
   __syncthreads();
   int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
-  for (int c = c0; c < c1; c++) {  // start[c + 1] := first slot of destination c (its cursor during the fill)
+  for (int c = c0; c < c1; c++) {
     const int cnt = start[c + 1];
     start[c + 1] = run;
     run += cnt;
   }
   __syncthreads();
+  for (int e = tid; e < entries; e += kCsrThreads) perm[atomicAdd(&start[__ldg(id + e) + 1], 1)] = e;
+  __syncthreads();
+  for (int j = tid; j <= rows; j += kCsrThreads) out_start[j] = start[j];
 }
 
-// grid (channel groups, 1, clouds).  Shared memory: start[n + 1 (+pad)] | perm[mpts] | two row buffers of mpts floats.
+// grid (channel groups, 1, clouds); dynamic shared memory: G rows of `cols` floats.
+// kInterp: entry e = 3 * target + k carries the weight weight[b, e]; the row is indexed by the target.
+template <bool kInterp, int G>
 __global__ void __launch_bounds__(kStThreads)
-gather_grad_csr_kernel(int c, int n, int mpts, int G, const float *__restrict__ grad_out, const int *__restrict__ idx,
-                       float *__restrict__ grad_points) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ int s_warp[32];
-  const int mp4 = (mpts + 3) & ~3;
-  float *const row0 = reinterpret_cast<float *>(smem_raw), *const row1 = row0 + mp4;
-  int *perm = reinterpret_cast<int *>(smem_raw) + 2 * mp4;
-  int *start = perm + mp4;  // n + 1
-  const int tid = threadIdx.x;
+scatter_csr_apply_kernel(int c, int rows, int cols, size_t cloud_ints, const float *__restrict__ grad_out,
+                         const float *__restrict__ weight, const int *__restrict__ ws, float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) float rowbuf[];
+  __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
-  const int *id = idx + (size_t)b * mpts;
-  const float *go = grad_out + ((size_t)b * c + c0) * mpts;
-  const bool bulk = ((reinterpret_cast<uintptr_t>(go) & 15) == 0) && (mpts % 4 == 0);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (bulk) csr_tma_issue(row0, go, mpts, &bar[0]);  // the first row streams in while the index is transposed
-  }
-  for (int j = tid; j <= n; j += kStThreads) start[j] = 0;
-  __syncthreads();
-  for (int p = tid; p < mpts; p += kStThreads) atomicAdd(&start[__ldg(id + p) + 1], 1);
-  __syncthreads();
-  csr_scan(start, n, s_warp);
-  for (int p = tid; p < mpts; p += kStThreads) perm[atomicAdd(&start[__ldg(id + p) + 1], 1)] = p;
-  __syncthreads();  // start[j] = first slot of destination j, start[n] = mpts
-
-  float *gp = grad_points + ((size_t)b * c + c0) * n;
-  for (int g = 0; g < gcount; g++) {
-    float *r = (g & 1) ? row1 : row0;
-    if (bulk) {
-      csr_bar_wait(&bar[g & 1], (g >> 1) & 1);
-      if (tid == 0 && g + 1 < gcount) csr_tma_issue((g & 1) ? row0 : row1, go + (size_t)(g + 1) * mpts, mpts, &bar[(g + 1) & 1]);
-    } else {
-      for (int p = tid; p < mpts; p += kStThreads) r[p] = __ldg(go + (size_t)g * mpts + p);
-      __syncthreads();
+  stage_rows(rowbuf, grad_out + ((size_t)b * c + c0) * cols, gcount * cols, &bar);
+  const int *start = ws + (size_t)b * cloud_ints, *perm = start + rows + 1;
+  const float *w = kInterp ? weight + (size_t)b * cols * 3 : nullptr;
+  float *gp = grad_points + ((size_t)b * c + c0) * rows;
+  for (int j = threadIdx.x; j < rows; j += kStThreads) {
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = 0.f;
+    const int q1 = __ldg(start + j + 1);
+    for (int q = __ldg(start + j); q < q1; q++) {
+      const int e = __ldg(perm + q);
+      const int p = kInterp ? e / 3 : e;
+      const float wt = kInterp ? __ldg(w + e) : 1.f;
+#pragma unroll
+      for (int g = 0; g < G; g++)
+        if (g < gcount) {
+          const float v = rowbuf[g * cols + p];
+          acc[g] = __fadd_rn(acc[g], kInterp ? __fmul_rn(v, wt) : v);  // product rounded first, as the atomics add it
+        }
     }
-    for (int j = tid; j < n; j += kStThreads) {
-      float acc = 0.f;
-      for (int q = start[j]; q < start[j + 1]; q++) acc = __fadd_rn(acc, r[perm[q]]);
-      gp[(size_t)g * n + j] = acc;
-    }
-    __syncthreads();  // everybody is done with row[g & 1] before it is refilled two iterations later
+#pragma unroll
+    for (int g = 0; g < G; g++)
+      if (g < gcount) gp[(size_t)g * rows + j] = acc[g];
   }
 }
 
-// three_interpolate backward: grad_points[b,c,j] = sum over (p,k) with idx[b,p,k] == j of grad_out[b,c,p] * w[b,p,k]
-// (products rounded before the sum, as three_interpolate_cuda.cu:81-83 adds them).
-// Shared memory: two row buffers of n floats | permp[3n] | permw[3n] | start[m + 1].
-__global__ void __launch_bounds__(kStThreads)
-three_interpolate_grad_csr_kernel(int c, int n, int m, int G, const float *__restrict__ grad_out,
-                                  const int *__restrict__ idx, const float *__restrict__ weight,
-                                  float *__restrict__ grad_points) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ int s_warp[32];
-  const int n4 = (n + 3) & ~3;
-  float *const row0 = reinterpret_cast<float *>(smem_raw), *const row1 = row0 + n4;
-  int *permp = reinterpret_cast<int *>(smem_raw) + 2 * n4;
-  float *permw = reinterpret_cast<float *>(permp + 3 * n);
-  int *start = reinterpret_cast<int *>(permw + 3 * n);  // m + 1
-  const int tid = threadIdx.x;
-  const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
-  const int *id = idx + (size_t)b * n * 3;
-  const float *w = weight + (size_t)b * n * 3;
-  const float *go = grad_out + ((size_t)b * c + c0) * n;
-  const bool bulk = ((reinterpret_cast<uintptr_t>(go) & 15) == 0) && (n % 4 == 0);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (bulk) csr_tma_issue(row0, go, n, &bar[0]);
-  }
-  for (int j = tid; j <= m; j += kStThreads) start[j] = 0;
-  __syncthreads();
-  for (int e = tid; e < 3 * n; e += kStThreads) atomicAdd(&start[__ldg(id + e) + 1], 1);
-  __syncthreads();
-  csr_scan(start, m, s_warp);
-  for (int e = tid; e < 3 * n; e += kStThreads) {
-    const int slot = atomicAdd(&start[__ldg(id + e) + 1], 1);
-    permp[slot] = e / 3;
-    permw[slot] = __ldg(w + e);
-  }
-  __syncthreads();
+size_t scatter_csr_workspace_bytes(int b, int rows, int entries) {
+  if (b <= 0 || rows <= 0 || entries <= 0 || rows > kCsrMaxRows) return 16;
+  return sizeof(int) * (size_t)b * csr_cloud_ints(rows, entries);
+}
 
-  float *gp = grad_points + ((size_t)b * c + c0) * m;
-  for (int g = 0; g < gcount; g++) {
-    float *r = (g & 1) ? row1 : row0;
-    if (bulk) {
-      csr_bar_wait(&bar[g & 1], (g >> 1) & 1);
-      if (tid == 0 && g + 1 < gcount) csr_tma_issue((g & 1) ? row0 : row1, go + (size_t)(g + 1) * n, n, &bar[(g + 1) & 1]);
-    } else {
-      for (int p = tid; p < n; p += kStThreads) r[p] = __ldg(go + (size_t)g * n + p);
-      __syncthreads();
-    }
-    for (int j = tid; j < m; j += kStThreads) {
-      float acc = 0.f;
-      for (int q = start[j]; q < start[j + 1]; q++) acc = __fadd_rn(acc, __fmul_rn(r[permp[q]], permw[q]));
-      gp[(size_t)g * m + j] = acc;
-    }
-    __syncthreads();
+// grad_points (b, c, rows) from grad_out (b, c, cols) through idx (b, entries): entries = cols (gather / group) or
+// 3 * cols with weights (three_interpolate).  Returns -100 when this path does not apply (the caller falls back).
+int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const float *grad_out, const int *idx,
+                       const float *weight, float *grad_points, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+  const int entries = interp ? 3 * cols : cols;
+  if (b > 65535 || rows > kCsrMaxRows) return -100;
+  // Measured (tools/scatter_variants.py): the transposed index pays off when at least two grad_out rows fit the
+  // shared-memory budget of a CTA (its index reads are then shared between channels) and most destinations receive
+  // something; long rows and sparse scatters are faster in the workspace-free kernels.
+  if ((size_t)cols * 4 * 2 > kStRowBytes || entries < rows) return -100;
+  if (!workspace || workspace_bytes < scatter_csr_workspace_bytes(b, rows, entries)) return -100;
+  const size_t cloud_ints = csr_cloud_ints(rows, entries);
+  const size_t bsmem = sizeof(int) * ((size_t)rows + 1);
+  static size_t granted = 40 * 1024;
+  if (bsmem > granted) {
+    cudaError_t e = cudaFuncSetAttribute(scatter_csr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * (kCsrMaxRows + 1)));
+    if (e != cudaSuccess) return (int)e;
+    granted = sizeof(int) * (kCsrMaxRows + 1);
   }
+  scatter_csr_build_kernel<<<b, kCsrThreads, bsmem, s>>>(rows, entries, cloud_ints, idx, (int *)workspace);
+  // channels per CTA: as many as keep the staged rows within ~64 KB (three CTAs per SM)
+  int G = 4;  // one of the instantiated values 4, 2, 1
+  while (G > 1 && ((size_t)G * cols * 4 > kStRowBytes || G > c)) G >>= 1;
+  const size_t smem = (size_t)G * cols * 4;
+  dim3 grid((c + G - 1) / G, 1, b);
+  int rc = MVP_OK;
+#define MVP_CSR_APPLY(I, GG, TAG)                                                                                   \
+  do {                                                                                                              \
+    rc = set_smem<TAG>(scatter_csr_apply_kernel<I, GG>, smem);                                                      \
+    if (!rc)                                                                                                        \
+      scatter_csr_apply_kernel<I, GG><<<grid, kStThreads, smem, s>>>(c, rows, cols, cloud_ints, grad_out, weight,    \
+                                                                      (const int *)workspace, grad_points);         \
+  } while (0)
+  if (interp) {
+    if (G >= 4) MVP_CSR_APPLY(true, 4, 10);
+    else if (G >= 2) MVP_CSR_APPLY(true, 2, 11);
+    else MVP_CSR_APPLY(true, 1, 12);
+  } else {
+    if (G >= 4) MVP_CSR_APPLY(false, 4, 13);
+    else if (G >= 2) MVP_CSR_APPLY(false, 2, 14);
+    else MVP_CSR_APPLY(false, 1, 15);
+  }
+#undef MVP_CSR_APPLY
+  if (rc) return rc;
+  count_launch(2);
+  return launch_status();
 }
 
 // ---- launch plans --------------------------------------------------------------------------------------------------
@@ -329,17 +366,6 @@ static int column_chunk(int b, int groups, int rows, int cols) {
   return (chunk + kStThreads - 1) / kStThreads * kStThreads;
 }
 
-// opt in to > 48 KB of dynamic shared memory, once per kernel (TAG names the kernel: one high-water mark each) and size
-template <int TAG, typename K>
-static int set_smem(K kernel, size_t bytes) {
-  static size_t granted = 40 * 1024;  // static + dynamic share the default 48 KB: opt in a little below it
-  if (bytes <= granted) return MVP_OK;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return (int)e;
-  granted = bytes;
-  return MVP_OK;
-}
-
 int gather_staged_launch(int b, int c, int n, int mpts, const float *points, const int *idx, float *out,
                          cudaStream_t s) {
   const int G = group_size(c, n), groups = (c + G - 1) / G;
@@ -352,29 +378,18 @@ int gather_staged_launch(int b, int c, int n, int mpts, const float *points, con
   return launch_status();
 }
 
-// channels per CTA of the CSR kernels: amortise the transposition over several rows, but keep >= ~2 waves of CTAs
-static int csr_group(int b, int c, int ctas_per_sm) {
-  int G = 16;
-  while (G > 2 && (long long)b * ((c + G - 1) / G) < 2LL * ctas_per_sm * kNumSMs) G >>= 1;
-  return std::min(G, c);
-}
-
 int gather_grad_staged_launch(int b, int c, int n, int mpts, const float *grad_out, const int *idx, float *grad_points,
                               cudaStream_t s) {
-  const size_t csr_smem = sizeof(float) * (3 * (size_t)((mpts + 3) & ~3) + n + 1);
-  if (csr_smem <= 200 * 1024) {
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / csr_smem));
-    const int G = csr_group(b, c, per_sm);
-    if (int rc = set_smem<4>(gather_grad_csr_kernel, csr_smem)) return rc;
-    gather_grad_csr_kernel<<<dim3((c + G - 1) / G, 1, b), kStThreads, csr_smem, s>>>(c, n, mpts, G, grad_out, idx,
-                                                                                    grad_points);
-    count_launch();
-    return launch_status();
-  }
   const int G = group_size(c, n), groups = (c + G - 1) / G;
   const size_t smem = (size_t)G * n * 4;
-  if (int rc = set_smem<1>(gather_grad_staged_kernel, smem)) return rc;
-  gather_grad_staged_kernel<<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, mpts, G, grad_out, idx, grad_points);
+  const bool vec = (mpts % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(idx)) & 15) == 0;
+  if (vec) {
+    if (int rc = set_smem<1>(gather_grad_staged_kernel<true>, smem)) return rc;
+    gather_grad_staged_kernel<true><<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, mpts, G, grad_out, idx, grad_points);
+  } else {
+    if (int rc = set_smem<6>(gather_grad_staged_kernel<false>, smem)) return rc;
+    gather_grad_staged_kernel<false><<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, mpts, G, grad_out, idx, grad_points);
+  }
   count_launch();
   return launch_status();
 }
@@ -393,21 +408,19 @@ int three_interpolate_staged_launch(int b, int c, int m, int n, const float *poi
 
 int three_interpolate_grad_staged_launch(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                          const float *weight, float *grad_points, cudaStream_t s) {
-  const size_t csr_smem = sizeof(float) * (2 * (size_t)((n + 3) & ~3) + 6 * (size_t)n + m + 1);
-  if (csr_smem <= 200 * 1024) {
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / csr_smem));
-    const int G = csr_group(b, c, per_sm);
-    if (int rc = set_smem<5>(three_interpolate_grad_csr_kernel, csr_smem)) return rc;
-    three_interpolate_grad_csr_kernel<<<dim3((c + G - 1) / G, 1, b), kStThreads, csr_smem, s>>>(c, n, m, G, grad_out, idx,
-                                                                                               weight, grad_points);
-    count_launch();
-    return launch_status();
-  }
   const int G = group_size(c, m), groups = (c + G - 1) / G;
   const size_t smem = (size_t)G * m * 4;
-  if (int rc = set_smem<3>(three_interpolate_grad_staged_kernel, smem)) return rc;
-  three_interpolate_grad_staged_kernel<<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, m, G, grad_out, idx, weight,
-                                                                                  grad_points);
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(idx) |
+                                     reinterpret_cast<uintptr_t>(weight)) & 15) == 0;
+  if (vec) {
+    if (int rc = set_smem<3>(three_interpolate_grad_staged_kernel<true>, smem)) return rc;
+    three_interpolate_grad_staged_kernel<true><<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, m, G, grad_out, idx,
+                                                                                          weight, grad_points);
+  } else {
+    if (int rc = set_smem<7>(three_interpolate_grad_staged_kernel<false>, smem)) return rc;
+    three_interpolate_grad_staged_kernel<false><<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, m, G, grad_out, idx,
+                                                                                           weight, grad_points);
+  }
   count_launch();
   return launch_status();
 }

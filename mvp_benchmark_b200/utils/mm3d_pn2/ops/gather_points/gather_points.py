@@ -40,8 +40,11 @@ class GatherPoints(Function):
         grad_out_data = grad_out.data.contiguous()
         grad_features = torch.empty(B, C, N, device=grad_out_data.device, dtype=torch.float32)
         with torch.cuda.device(grad_out_data.device):
-            rc = _lib.lib.mvp_gather_points_grad(B, C, N, npoint, _lib.ptr(grad_out_data), _lib.ptr(idx),
-                                                 _lib.ptr(grad_features), _lib.stream_of(grad_out_data))
+            # scratch for the transposed index (the scatter becomes a sum per element: no float atomics)
+            ws = _lib.workspace(_lib.lib.mvp_scatter_workspace_bytes(B, N, npoint), grad_out_data.device)
+            rc = _lib.lib.mvp_gather_points_grad_ws(B, C, N, npoint, _lib.ptr(grad_out_data), _lib.ptr(idx),
+                                                    _lib.ptr(grad_features), _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_of(grad_out_data))
         _lib.check(rc, "mvp_gather_points_grad")
         return grad_features, None
 

@@ -138,8 +138,10 @@ class GroupingOperation(Function):
         grad_out_data = grad_out.data.contiguous()
         grad_features = torch.empty(B, C, N, device=grad_out_data.device, dtype=torch.float32)
         with torch.cuda.device(grad_out_data.device):
-            rc = _lib.lib.mvp_group_points_grad(B, C, N, npoint, nsample, _lib.ptr(grad_out_data), _lib.ptr(idx),
-                                                _lib.ptr(grad_features), _lib.stream_of(grad_out_data))
+            ws = _lib.workspace(_lib.lib.mvp_scatter_workspace_bytes(B, N, npoint * nsample), grad_out_data.device)
+            rc = _lib.lib.mvp_group_points_grad_ws(B, C, N, npoint, nsample, _lib.ptr(grad_out_data), _lib.ptr(idx),
+                                                   _lib.ptr(grad_features), _lib.ptr(ws), ws.numel(),
+                                                   _lib.stream_of(grad_out_data))
         _lib.check(rc, "mvp_group_points_grad")
         return grad_features, None
 

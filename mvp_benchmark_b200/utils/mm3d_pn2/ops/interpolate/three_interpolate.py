@@ -44,9 +44,10 @@ class ThreeInterpolate(Function):
         grad_out_data = grad_out.data.contiguous()
         grad_features = torch.empty(B, c, m, device=grad_out_data.device, dtype=torch.float32)
         with torch.cuda.device(grad_out_data.device):
-            rc = _lib.lib.mvp_three_interpolate_grad(B, c, n, m, _lib.ptr(grad_out_data), _lib.ptr(idx),
-                                                     _lib.ptr(weight), _lib.ptr(grad_features),
-                                                     _lib.stream_of(grad_out_data))
+            ws = _lib.workspace(_lib.lib.mvp_scatter_workspace_bytes(B, m, 3 * n), grad_out_data.device)
+            rc = _lib.lib.mvp_three_interpolate_grad_ws(B, c, n, m, _lib.ptr(grad_out_data), _lib.ptr(idx),
+                                                        _lib.ptr(weight), _lib.ptr(grad_features), _lib.ptr(ws),
+                                                        ws.numel(), _lib.stream_of(grad_out_data))
         _lib.check(rc, "mvp_three_interpolate_grad")
         return grad_features, None, None
 

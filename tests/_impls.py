@@ -190,12 +190,23 @@ class CudaImpl:
         L.check(L.lib.mvp_gather_points(b, c, n, m, p(P), p(I), p(out), self.S()), "mvp_gather_points")
         return self.N(out)
 
-    def gather_grad(self, go, idx, n):
+    def _scatter_ws(self, b, rows, entries):
+        ws = self.L.workspace(self.L.lib.mvp_scatter_workspace_bytes(b, rows, entries), self.dev)
+        ws.fill_(0xA5)
+        return ws
+
+    def gather_grad(self, go, idx, n, ws=False):
+        """ws=True: the workspace (transposed-index) variant mvp_gather_points_grad_ws."""
         t, L, p = self.torch, self.L, self.L.ptr
         G, I = self.T(go), self.T(idx)
         b, c, m = G.shape
         out = self.E((b, c, n), t.float32)
-        L.check(L.lib.mvp_gather_points_grad(b, c, n, m, p(G), p(I), p(out), self.S()), "mvp_gather_points_grad")
+        if ws:
+            w = self._scatter_ws(b, n, m)
+            L.check(L.lib.mvp_gather_points_grad_ws(b, c, n, m, p(G), p(I), p(out), p(w), w.numel(), self.S()),
+                    "mvp_gather_points_grad_ws")
+        else:
+            L.check(L.lib.mvp_gather_points_grad(b, c, n, m, p(G), p(I), p(out), self.S()), "mvp_gather_points_grad")
         return self.N(out)
 
     def group(self, points, idx):
@@ -207,12 +218,17 @@ class CudaImpl:
         L.check(L.lib.mvp_group_points(b, c, n, np_, ns, p(P), p(I), p(out), self.S()), "mvp_group_points")
         return self.N(out)
 
-    def group_grad(self, go, idx, n):
+    def group_grad(self, go, idx, n, ws=False):
         t, L, p = self.torch, self.L, self.L.ptr
         G, I = self.T(go), self.T(idx)
         b, c, np_, ns = G.shape
         out = self.E((b, c, n), t.float32)
-        L.check(L.lib.mvp_group_points_grad(b, c, n, np_, ns, p(G), p(I), p(out), self.S()), "mvp_group_points_grad")
+        if ws:
+            w = self._scatter_ws(b, n, np_ * ns)
+            L.check(L.lib.mvp_group_points_grad_ws(b, c, n, np_, ns, p(G), p(I), p(out), p(w), w.numel(), self.S()),
+                    "mvp_group_points_grad_ws")
+        else:
+            L.check(L.lib.mvp_group_points_grad(b, c, n, np_, ns, p(G), p(I), p(out), self.S()), "mvp_group_points_grad")
         return self.N(out)
 
     def three_nn(self, unknown, known):
@@ -233,13 +249,18 @@ class CudaImpl:
         L.check(L.lib.mvp_three_interpolate(b, c, m, n, p(P), p(I), p(W), p(out), self.S()), "mvp_three_interpolate")
         return self.N(out)
 
-    def three_interpolate_grad(self, go, idx, weight, m):
+    def three_interpolate_grad(self, go, idx, weight, m, ws=False):
         t, L, p = self.torch, self.L, self.L.ptr
         G, I, W = self.T(go), self.T(idx), self.T(weight)
         b, c, n = G.shape
         out = self.E((b, c, m), t.float32)
-        L.check(L.lib.mvp_three_interpolate_grad(b, c, n, m, p(G), p(I), p(W), p(out), self.S()),
-                "mvp_three_interpolate_grad")
+        if ws:
+            w = self._scatter_ws(b, m, 3 * n)
+            L.check(L.lib.mvp_three_interpolate_grad_ws(b, c, n, m, p(G), p(I), p(W), p(out), p(w), w.numel(), self.S()),
+                    "mvp_three_interpolate_grad_ws")
+        else:
+            L.check(L.lib.mvp_three_interpolate_grad(b, c, n, m, p(G), p(I), p(W), p(out), self.S()),
+                    "mvp_three_interpolate_grad")
         return self.N(out)
 
     def knn(self, k, xyz, centers):

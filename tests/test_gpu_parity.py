@@ -333,7 +333,9 @@ def test_gather_vs_oracle(gpu, cpu, b, c, n, m):
     idx = rng.integers(0, n, (b, m)).astype(np.int32)
     go = rng.standard_normal((b, c, m)).astype(np.float32)
     _cases.eq(gpu.gather(pts, idx), cpu.gather(pts, idx), "gather")
-    _cases.close(gpu.gather_grad(go, idx, n), cpu.gather_grad(go, idx, n), "gather grad", atol=1e-5)
+    want = cpu.gather_grad(go, idx, n)
+    _cases.close(gpu.gather_grad(go, idx, n), want, "gather grad", atol=1e-5)
+    _cases.close(gpu.gather_grad(go, idx, n, ws=True), want, "gather grad (workspace variant)", atol=1e-5)
 
 
 @pytest.mark.parametrize("b,c,n,p,s", [(8, 64, 3072, 1536, 1), (4, 3, 2048, 102, 24), (2, 128, 1536, 768, 1), (1, 2, 9, 4, 3)])
@@ -343,7 +345,9 @@ def test_group_vs_oracle(gpu, cpu, b, c, n, p, s):
     idx = rng.integers(0, n, (b, p, s)).astype(np.int32)
     go = rng.standard_normal((b, c, p, s)).astype(np.float32)
     _cases.eq(gpu.group(pts, idx), cpu.group(pts, idx), "group")
-    _cases.close(gpu.group_grad(go, idx, n), cpu.group_grad(go, idx, n), "group grad", atol=1e-5)
+    want = cpu.group_grad(go, idx, n)
+    _cases.close(gpu.group_grad(go, idx, n), want, "group grad", atol=1e-5)
+    _cases.close(gpu.group_grad(go, idx, n, ws=True), want, "group grad (workspace variant)", atol=1e-5)
 
 
 @pytest.mark.parametrize("b,c,m,n", [(8, 512, 384, 768), (4, 256, 768, 1536), (2, 128, 1536, 3072), (1, 3, 4, 5),
@@ -355,7 +359,9 @@ def test_three_interpolate_vs_oracle(gpu, cpu, b, c, m, n):
     w = rng.random((b, n, 3), dtype=np.float32)
     go = rng.standard_normal((b, c, n)).astype(np.float32)
     _cases.eq(gpu.three_interpolate(pts, idx, w), cpu.three_interpolate(pts, idx, w), "three_interpolate")
-    _cases.close(gpu.three_interpolate_grad(go, idx, w, m), cpu.three_interpolate_grad(go, idx, w, m), "interp grad", atol=1e-5)
+    want = cpu.three_interpolate_grad(go, idx, w, m)
+    _cases.close(gpu.three_interpolate_grad(go, idx, w, m), want, "interp grad", atol=1e-5)
+    _cases.close(gpu.three_interpolate_grad(go, idx, w, m, ws=True), want, "interp grad (workspace variant)", atol=1e-5)
 
 
 def test_mm3d_ops_vs_reference_cuda_live(gpu, ref, cuda):

@@ -24,13 +24,10 @@ GRID_VARIANTS = {
 }
 EMD_VARIANTS = {
     "base": [],
-    "tail0": ["-DMVP_EMD_TAIL_MAX=0"],
-    "tail16": ["-DMVP_EMD_TAIL_MAX=16"],
-    "tail64": ["-DMVP_EMD_TAIL_MAX=64"],
-    "tail128": ["-DMVP_EMD_TAIL_MAX=128"],
-    "tail64_fs256": ["-DMVP_EMD_TAIL_MAX=64", "-DMVP_EMD_FULLSCAN_EVALS=256"],
-    "tail0_fs128": ["-DMVP_EMD_TAIL_MAX=0", "-DMVP_EMD_FULLSCAN_EVALS=128"],
-    "tail0_ppc8": ["-DMVP_EMD_TAIL_MAX=0", "-DMVP_EMD_GRID_PPC=8"],
+    "fs0": ["-DMVP_EMD_FULLSCAN_EVALS=0"],
+    "fs128": ["-DMVP_EMD_FULLSCAN_EVALS=128"],
+    "ppc2": ["-DMVP_EMD_GRID_PPC=2"],
+    "ppc8": ["-DMVP_EMD_GRID_PPC=8"],
 }
 FPS_VARIANTS = {"base": [], "pmax8": ["-DMVP_FPS_PMAX=8"], "pmax4": ["-DMVP_FPS_PMAX=4"]}
 SETS = {}
