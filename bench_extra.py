@@ -88,7 +88,8 @@ def vrcnet_census(dev, g, have_ref):
         u, k, d, i = R(b, n, 3), R(b, m, 3), E(b, n, 3), EI(b, n, 3)
         f, w, o, go, gp = N(b, c, m), R(b, n, 3), E(b, c, n), N(b, c, n), E(b, c, m)
         i3 = I(m, b, n, 3)
-        ours.append(lambda: L.mvp_three_nn(b, n, m, P(u), P(k), P(d), P(i), S))
+        wn = _lib.workspace(L.mvp_three_nn_workspace_bytes(b, n, m), dev)
+        ours.append(lambda: L.mvp_three_nn_ws(b, n, m, P(u), P(k), P(d), P(i), P(wn), wn.numel(), S))
         ours.append(lambda: L.mvp_three_interpolate(b, c, m, n, P(f), P(i3), P(w), P(o), S))
         ws = _lib.workspace(L.mvp_scatter_workspace_bytes(b, m, 3 * n), dev)
         ours.append(lambda: L.mvp_three_interpolate_grad_ws(b, c, n, m, P(go), P(i3), P(w), P(gp), P(ws), ws.numel(), S))

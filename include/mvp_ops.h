@@ -189,6 +189,14 @@ int mvp_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_
                                   const float *weight, float *grad_points, void *workspace,
                                   size_t workspace_bytes, mvp_stream_t stream);
 
+/* three_nn with a workspace: the three nearest sources are found through a uniform grid over `known`
+ * (the search of the grid-pruned Chamfer path with a top-3 state; targets it does not finish go through
+ * the exhaustive kernel) — same outputs as mvp_three_nn, bit for bit.  n, m >= 256; other shapes and a
+ * missing / short workspace fall back to mvp_three_nn.  mvp_three_nn_workspace_bytes(b, n, m) bytes. */
+size_t mvp_three_nn_workspace_bytes(int b, int n, int m);
+int mvp_three_nn_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                    void *workspace, size_t workspace_bytes, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ def _load():
         "mvp_gather_points_grad_ws": (_c_int, [_c_int] * 4 + [_p] * 4 + [_c_size_t, _p]),
         "mvp_group_points_grad_ws": (_c_int, [_c_int] * 5 + [_p] * 4 + [_c_size_t, _p]),
         "mvp_three_interpolate_grad_ws": (_c_int, [_c_int] * 4 + [_p] * 5 + [_c_size_t, _p]),
+        "mvp_three_nn_workspace_bytes": (_c_size_t, [_c_int] * 3),
+        "mvp_three_nn_ws": (_c_int, [_c_int] * 3 + [_p] * 5 + [_c_size_t, _p]),
         "mvp_knn": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
     }
     for name, (res, args) in sig.items():

@@ -200,8 +200,9 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
   if (tid == 0) start[ncell] = np;
   __syncthreads();
   {  // keys of the fused brute-force kernels, in case this cloud pair is handed over to them
-    unsigned long long *key = (side ? W.key[1] : W.key[0]) + (size_t)cloud * np;
-    for (int i = tid; i < np; i += kGridThreads) key[i] = ~0ull;
+    unsigned long long *key = side ? W.key[1] : W.key[0];  // null for three_nn: nothing is handed over wholesale
+    if (key)
+      for (int i = tid; i < np; i += kGridThreads) key[(size_t)cloud * np + i] = ~0ull;
   }
 
   // ---- pass 3: scatter (order inside a cell is arbitrary; the query's tie rule is explicit)
@@ -214,10 +215,15 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
 }
 
 // ------------------------------------------------------------------------------------------------ query
+// K = 1: Chamfer, both directions (points of xyz1 against xyz2's grid, then the other way round).
+// K = 3: three_nn — the n points of side 0 against side 1's grid only; the three nearest in ascending (distance,
+//        index) order, which is what the reference's strict-`<` scan in index order keeps (three_nn_cuda.cu:43-58);
+//        outputs (b, n, 3).  Pruning and termination then test the THIRD best distance.
+template <int K>
 __global__ void __launch_bounds__(kGridQThreads)
 chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
                           int *__restrict__ idx1, int *__restrict__ idx2) {
-  const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
+  const long long total1 = (long long)b * n, total = K == 1 ? total1 + (long long)b * m : total1;
   const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
   if (t < total) {
   const int dir = t >= total1 ? 1 : 0;       // 0: points of xyz1 against xyz2's grid; 1: the other way round
@@ -235,12 +241,16 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
   const int gx = h1.y, gy = h1.z, gz = h1.w;
   const int *start = (ts ? W.start[1] : W.start[0]) + (size_t)cloud * ((ts ? W.cap[1] : W.cap[0]) + 1);
   const float4 *T = (ts ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * nt;
-  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq;
-  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq;
+  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq * K;
+  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq * K;
 
   const float inf = __int_as_float(0x7f800000);
-  float best = inf;
-  int bi = 0x7fffffff;
+  // the K best so far, ascending in (distance, index); `best` is the one pruning tests (the K-th)
+  float bd[K];
+  int bk[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) bd[k] = inf, bk[k] = 0x7fffffff;
+  float &best = bd[K - 1];
   bool done = false;
   if (h2.y) {
     const float ux = (self.x - __int_as_float(h0.x)) * inv_s;
@@ -278,9 +288,16 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
         const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
         if (d <= best) {  // rare after the first few candidates
           const int qi = __float_as_int(q.w);
-          if (d < best || qi < bi) {
-            best = d;
-            bi = qi;
+          if (d < bd[K - 1] || qi < bk[K - 1]) {  // (d, qi) precedes the K-th best: insert it in order
+            bd[K - 1] = d;
+            bk[K - 1] = qi;
+#pragma unroll
+            for (int k = K - 1; k > 0; k--) {
+              if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bk[k] < bk[k - 1])) {
+                const float td_ = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td_;
+                const int tk_ = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk_;
+              }
+            }
           }
         }
       }
@@ -365,8 +382,11 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
     }
   }
   if (done) {
-    dist[orig] = best;
-    idx[orig] = bi;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      dist[(size_t)orig * K + k] = bd[k];
+      idx[(size_t)orig * K + k] = bk[k];
+    }
   } else {
     // append to the left-over list of (direction, cloud): one atomic per group of lanes sharing the list
     const int li = dir * b + cloud;
@@ -443,7 +463,7 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
   }
   chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
   const long long total = (long long)b * ((long long)n + m);
-  chamfer_grid_query_kernel<<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+  chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
       b, n, m, W, dist1, dist2, idx1, idx2);
   chamfer_grid_plan_kernel<<<1, 256, 0, s>>>(b, n, m, W);
   count_launch(3);
@@ -455,6 +475,39 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
                                  reinterpret_cast<unsigned char *>(ws) + grid_bytes, key_bytes, W.plan, s);
   if (rc) return rc;
   return chamfer_rest_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, W.list[0], W.list[1], W.count, W.plan, s);
+}
+
+// ---- three_nn through the same grid (pointnet2.cu: mvp_three_nn_ws) --------------------------------------------------
+// pointnet2.cu
+int three_nn_rest_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                         const int *list, const int *count, cudaStream_t s);
+
+bool three_nn_grid_supported(int b, int n, int m) {
+  return b > 0 && b <= 65535 && n >= 256 && m >= 256 && n <= (1 << 20) && m <= (1 << 20) &&
+         (long long)b * ((long long)n + m) < (1LL << 31);
+}
+
+size_t three_nn_grid_workspace_bytes(int b, int n, int m) { return grid_plan(b, n, m, nullptr, nullptr); }
+
+// unknown (b,n,3) against known (b,m,3): grid over `known`, queries in the sorted order of `unknown`; queries that do
+// not finish within the ring / candidate budget are finished by the tiled brute-force kernel through a list.
+int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *ws,
+                         size_t ws_bytes, cudaStream_t s) {
+  GridWs W;
+  if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
+  W.key[0] = W.key[1] = nullptr;
+  const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
+  cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(int) * kGridMaxCells));
+  if (e != cudaSuccess) return (int)e;
+  chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, unknown, known, W);
+  const long long total = (long long)b * n;
+  chamfer_grid_query_kernel<3><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+      b, n, m, W, dist2, nullptr, idx, nullptr);
+  count_launch(2);
+  int rc = launch_status();
+  if (rc) return rc;
+  return three_nn_rest_launch(b, n, m, unknown, known, dist2, idx, W.list[0], W.count, s);
 }
 
 }  // namespace mvp

@@ -83,13 +83,20 @@ ball_query_kernel(int n, int m, float min_radius2, float max_radius2, int nsampl
 // ------------------------------------------------------------------------------------------------
 // three_nn: one thread per target, sources broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
+// kRest: the targets are the count[b] entries of list + b*n (the points the grid search of mvp_three_nn_ws did not
+// finish, chamfer_grid.cu); CTAs beyond the list length leave at once.
+template <bool kRest>
 __global__ void __launch_bounds__(256)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
-                float *__restrict__ dist2, int *__restrict__ idx) {
+                float *__restrict__ dist2, int *__restrict__ idx, const int *__restrict__ list,
+                const int *__restrict__ count) {
   __shared__ float tile[kTile * 3];
   const int b = blockIdx.y;
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  const bool active = p < n;
+  const int nq = kRest ? __ldg(count + b) : n;
+  if (blockIdx.x * 256 >= nq) return;
+  int p = blockIdx.x * 256 + threadIdx.x;
+  const bool active = p < nq;
+  if (kRest && active) p = __ldg(list + (size_t)b * n + p);
   const float *kn = known + (size_t)b * m * 3;
   float ux = 0, uy = 0, uz = 0;
   if (active) {
@@ -395,11 +402,39 @@ MVP_API int mvp_three_nn(int b, int n, int m, const float *unknown, const float 
   for (int b0 = 0; b0 < b; b0 += 65535) {
     const int bb = min(65535, b - b0);
     dim3 grid((n + 255) / 256, bb);
-    three_nn_kernel<<<grid, 256, 0, s>>>(n, m, unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
-                                         dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3);
+    three_nn_kernel<false><<<grid, 256, 0, s>>>(n, m, unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
+                                                dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3, nullptr, nullptr);
     count_launch();
   }
   return launch_status();
+}
+
+namespace mvp {
+// chamfer_grid.cu
+bool three_nn_grid_supported(int b, int n, int m);
+size_t three_nn_grid_workspace_bytes(int b, int n, int m);
+int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *ws,
+                         size_t ws_bytes, cudaStream_t s);
+
+int three_nn_rest_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                         const int *list, const int *count, cudaStream_t s) {
+  three_nn_kernel<true><<<dim3((n + 255) / 256, b), 256, 0, s>>>(n, m, unknown, known, dist2, idx, list, count);
+  count_launch();
+  return launch_status();
+}
+}  // namespace mvp
+
+MVP_API size_t mvp_three_nn_workspace_bytes(int b, int n, int m) {
+  return three_nn_grid_supported(b, n, m) ? three_nn_grid_workspace_bytes(b, n, m) : 16;
+}
+
+MVP_API int mvp_three_nn_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                            void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (three_nn_grid_supported(b, n, m) && unknown && known && dist2 && idx && workspace &&
+      workspace_bytes >= three_nn_grid_workspace_bytes(b, n, m))
+    return three_nn_grid_launch(b, n, m, unknown, known, dist2, idx, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mvp_three_nn(b, n, m, unknown, known, dist2, idx, stream);
 }
 
 MVP_API int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,

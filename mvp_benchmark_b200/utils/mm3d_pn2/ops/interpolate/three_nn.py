@@ -27,8 +27,10 @@ class ThreeNN(Function):
         dist2 = torch.empty(B, N, 3, device=device, dtype=torch.float32)
         idx = torch.empty(B, N, 3, device=device, dtype=torch.int32)
         with torch.cuda.device(device):
-            rc = _lib.lib.mvp_three_nn(B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2),
-                                       _lib.ptr(idx), _lib.stream_of(target))
+            # scratch for the grid over `source` (exact search, same outputs as the exhaustive kernel)
+            ws = _lib.workspace(_lib.lib.mvp_three_nn_workspace_bytes(B, N, m), device)
+            rc = _lib.lib.mvp_three_nn_ws(B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2),
+                                          _lib.ptr(idx), _lib.ptr(ws), ws.numel(), _lib.stream_of(target))
         _lib.check(rc, "mvp_three_nn")
         ctx.mark_non_differentiable(idx)
         return torch.sqrt(dist2), idx

@@ -231,13 +231,19 @@ class CudaImpl:
             L.check(L.lib.mvp_group_points_grad(b, c, n, np_, ns, p(G), p(I), p(out), self.S()), "mvp_group_points_grad")
         return self.N(out)
 
-    def three_nn(self, unknown, known):
+    def three_nn(self, unknown, known, ws=False):
+        """ws=True: mvp_three_nn_ws (grid search where the shape allows it)."""
         t, L, p = self.torch, self.L, self.L.ptr
         u, k = self.T(unknown), self.T(known)
         b, n, _ = u.shape
         m = k.shape[1]
         d, idx = self.E((b, n, 3), t.float32), self.E((b, n, 3), t.int32)
-        L.check(L.lib.mvp_three_nn(b, n, m, p(u), p(k), p(d), p(idx), self.S()), "mvp_three_nn")
+        if ws:
+            w = L.workspace(L.lib.mvp_three_nn_workspace_bytes(b, n, m), self.dev)
+            w.fill_(0xA5)
+            L.check(L.lib.mvp_three_nn_ws(b, n, m, p(u), p(k), p(d), p(idx), p(w), w.numel(), self.S()), "mvp_three_nn_ws")
+        else:
+            L.check(L.lib.mvp_three_nn(b, n, m, p(u), p(k), p(d), p(idx), self.S()), "mvp_three_nn")
         return self.N(d, idx)
 
     def three_interpolate(self, points, idx, weight):

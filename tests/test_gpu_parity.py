@@ -310,6 +310,25 @@ def test_three_nn_vs_oracle(gpu, cpu, kind, b, n, m):
     got, want = gpu.three_nn(u, k), cpu.three_nn(u, k)
     _cases.eq(got[1], want[1], "three_nn idx")
     _cases.eq(got[0], want[0], "three_nn dist2")
+    got = gpu.three_nn(u, k, ws=True)
+    _cases.eq(got[1], want[1], "three_nn idx (workspace variant)")
+    _cases.eq(got[0], want[0], "three_nn dist2 (workspace variant)")
+
+
+@pytest.mark.parametrize("kind_u,kind_k", [("uniform", "uniform"), ("sphere", "sphere"), ("lattice", "lattice"),
+                                           ("duplicates", "duplicates"), ("clustered", "uniform"), ("uniform", "clustered"),
+                                           ("planar", "planar"), ("shifted", "shifted"), ("outliers", "uniform"),
+                                           ("uniform", "constant"), ("tiny", "tiny")])
+@pytest.mark.parametrize("b,n,m", [(3, 3072, 1536), (2, 700, 300), (2, 256, 4099)])
+def test_three_nn_grid_is_bit_identical_to_exhaustive(gpu, kind_u, kind_k, b, n, m):
+    """mvp_three_nn_ws (grid search over `known`, top-3 state, left-over targets through the exhaustive kernel)
+    against mvp_three_nn on benign and hostile distributions — exact ties (lattice, duplicates, constant) included:
+    the three nearest come out in ascending (distance, index) order either way."""
+    u, k = _data.cloud(kind_u, b, n, 73), _data.cloud(kind_k, b, m, 74)
+    want = gpu.three_nn(u, k)
+    got = gpu.three_nn(u, k, ws=True)
+    _cases.eq(got[1], want[1], f"three_nn grid idx {kind_u}/{kind_k}")
+    _cases.eq(got[0], want[0], f"three_nn grid dist2 {kind_u}/{kind_k}")
 
 
 @pytest.mark.parametrize("kind,b,n,p,k", [("uniform", 2, 2048, 512, 16), ("lattice", 2, 700, 128, 10), ("uniform", 1, 300, 300, 100),
