@@ -77,7 +77,7 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING the timed region (NVML, 20 ms period)."""
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, 2 ms period)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
@@ -118,7 +118,7 @@ class ClockSampler:
                 self.reasons.update(self._names(int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.ok:

@@ -291,6 +291,26 @@ def run(dev, hbm_gbs=None):
     entry("three_nn_64x3072_from_1536", _time(lambda: mm.three_nn(u, k)),
           _time(lambda: ref_cuda.three_nn(u, k)) if have_ref else None, 64.0 * 3072 * 1536, "point-pairs/s",
           12.0 * 64 * (3072 + 1536) + 24.0 * 64 * 3072)
+    # ---- the kNN the MODELS run in torch (matmul expansion + topk, model_utils.py:242-259),
+    # restated here, against the fused exact search (mvp_knn_points) at VRCNet's sizes (B = 2*32 after vrcnet.py:452)
+    from mvp_benchmark_b200 import fused
+
+    def torch_knn_point(pk, point_input, point_output):
+        m_, n_ = point_output.size(1), point_input.size(1)
+        inner = -2 * torch.matmul(point_output, point_input.transpose(2, 1).contiguous())
+        xx = torch.sum(point_output ** 2, dim=2, keepdim=True).repeat(1, 1, n_)
+        yy = torch.sum(point_input ** 2, dim=2, keepdim=False).unsqueeze(1).repeat(1, m_, 1)
+        return (-xx - inner - yy).topk(k=pk, dim=-1)
+
+    for tag, n_, m_, k_ in (("self_64x3072_k16", 3072, 3072, 16), ("self_64x1536_k16", 1536, 1536, 16),
+                            ("point_64x1536_from_3072_k10", 1536, 3072, 10), ("point_64x384_from_768_k10", 384, 768, 10)):
+        cl = R(64, m_, 3)
+        qs = cl if tag.startswith("self") else R(64, n_, 3)
+        e = {"ours_ms": _time(lambda: fused.knn_points(k_, cl, qs), 5, 2),
+             "torch_matmul_topk_ms": _time(lambda: torch_knn_point(k_, cl, qs), 3, 1), "unit": "point-pairs/s"}
+        e["ours_per_s"] = 64.0 * n_ * m_ / (e["ours_ms"] * 1e-3)
+        e["speedup_vs_torch_formula"] = e["torch_matmul_topk_ms"] / e["ours_ms"]
+        out["knn_points_" + tag] = e
     out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
     xyz, ctr = R(32, 2048, 3), R(32, 102, 3)
     entry("ball_query_32x2048_102centres_ns12", _time(lambda: mm.ball_query(0, 0.0774596669, 12, xyz, ctr)),

@@ -168,6 +168,20 @@ int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
             float *dist2, mvp_stream_t stream);
 
+/* SURVEY.md §8(f) row 1 — the k-nearest-neighbour search the completion MODELS run in torch
+ * (completion/model_utils.py:242-259 `knn` / `knn_point` / `knn_point_all`: a (B,N,M) matrix of
+ * -|x|^2 + 2 x.y - |y|^2 by matmul, then torch.topk), as one fused exact search for 3-D points.
+ * Opt-in (the call sites are caller code): mvp_benchmark_b200.model_patches replaces the three functions.
+ *   queries (b,n,3), cloud (b,m,3), 1 <= k <= min(m, 64)  ->  dist2 (b,n,k) squared distances, idx (b,n,k),
+ *   ascending in (distance, index): distances are fl(dx*dx + dy*dy + dz*dz) in the contraction every other
+ *   operator here uses, equal distances resolve to the lower index.  (The matmul expansion the models use
+ *   rounds differently — its distances differ by ~1e-7 and may order near-ties the other way; its order among
+ *   exact ties is unspecified.)  Exact: grid-pruned search for k <= 32 and n, m >= 256, exhaustive otherwise;
+ *   both give the same bits.  workspace: mvp_knn_points_workspace_bytes(b,n,m,k) bytes, 16-byte aligned. */
+size_t mvp_knn_points_workspace_bytes(int b, int n, int m, int k);
+int mvp_knn_points(int b, int n, int m, int k, const float *queries, const float *cloud, float *dist2,
+                   int *idx, void *workspace, size_t workspace_bytes, mvp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * The backward scatters again, with a caller-provided workspace (same results, faster): the index is
  * transposed once per cloud into the workspace (start[rows + 1] | perm[entries]) and every gradient

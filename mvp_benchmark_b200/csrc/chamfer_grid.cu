@@ -219,10 +219,30 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
 // K = 3: three_nn — the n points of side 0 against side 1's grid only; the three nearest in ascending (distance,
 //        index) order, which is what the reference's strict-`<` scan in index order keeps (three_nn_cuda.cu:43-58);
 //        outputs (b, n, 3).  Pruning and termination then test the THIRD best distance.
+// kRT (top-k nearest neighbours, mvp_knn_points): K is the register capacity, the runtime `kk` <= K the number of
+//        neighbours wanted.  The first K - kk slots of the ordered list are phantoms at distance -inf, so that the
+//        kk-th real neighbour is always slot K - 1 — every array index stays a compile-time constant (a runtime
+//        `bd[kk - 1]`, even written as a chain of selects, sends the list to local memory).  Outputs are (b, n, kk).
+//        Larger candidate budget and one more ring than the K <= 3 searches.
 template <int K>
+__device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float d, int qi) {
+  bd[K - 1] = d;
+  bk[K - 1] = qi;
+#pragma unroll
+  for (int k = K - 1; k > 0; k--) {
+    if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bk[k] < bk[k - 1])) {
+      const float td_ = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td_;
+      const int tk_ = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk_;
+    }
+  }
+}
+template <int K, bool kRT = false>
 __global__ void __launch_bounds__(kGridQThreads)
 chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
-                          int *__restrict__ idx1, int *__restrict__ idx2) {
+                          int *__restrict__ idx1, int *__restrict__ idx2, int kk) {
+  constexpr int kBudget = kRT ? MVP_GRID_BUDGET + 64 * K : MVP_GRID_BUDGET;
+  constexpr int kMaxRing = kRT ? MVP_GRID_MAXRING + 1 : MVP_GRID_MAXRING;
+  const int ko = kRT ? kk : K;  // neighbours per query in the outputs
   const long long total1 = (long long)b * n, total = K == 1 ? total1 + (long long)b * m : total1;
   const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
   if (t < total) {
@@ -241,16 +261,21 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
   const int gx = h1.y, gy = h1.z, gz = h1.w;
   const int *start = (ts ? W.start[1] : W.start[0]) + (size_t)cloud * ((ts ? W.cap[1] : W.cap[0]) + 1);
   const float4 *T = (ts ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * nt;
-  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq * K;
-  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq * K;
+  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq * ko;
+  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq * ko;
 
   const float inf = __int_as_float(0x7f800000);
   // the K best so far, ascending in (distance, index); `best` is the one pruning tests (the K-th)
   float bd[K];
   int bk[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) bd[k] = inf, bk[k] = 0x7fffffff;
+  for (int k = 0; k < K; k++) {
+    const bool phantom = kRT && k < K - kk;
+    bd[k] = phantom ? -inf : inf;
+    bk[k] = phantom ? -1 : 0x7fffffff;
+  }
   float &best = bd[K - 1];
+  int &bestk = bk[K - 1];
   bool done = false;
   if (h2.y) {
     const float ux = (self.x - __int_as_float(h0.x)) * inv_s;
@@ -267,9 +292,9 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
     const float out = fmaxf(fmaxf(fmaxf(-ux, ux - (float)gx), fmaxf(-uy, uy - (float)gy)), fmaxf(-uz, uz - (float)gz));
     const bool finite = fabsf(ux) + fabsf(uy) + fabsf(uz) < 3.0e38f;  // false for NaN / inf
 #ifdef MVP_GRID_NOBAIL
-    int budget = MVP_GRID_BUDGET;
+    int budget = kBudget;
 #else
-    int budget = (finite && out <= (float)(MVP_GRID_MAXRING + 1)) ? MVP_GRID_BUDGET : -1;
+    int budget = (finite && out <= (float)(kMaxRing + 1)) ? kBudget : -1;
 #endif
 
     // distance (in cells, >= 0, conservative) from coordinate u to the slab of cell c
@@ -288,16 +313,8 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
         const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
         if (d <= best) {  // rare after the first few candidates
           const int qi = __float_as_int(q.w);
-          if (d < bd[K - 1] || qi < bk[K - 1]) {  // (d, qi) precedes the K-th best: insert it in order
-            bd[K - 1] = d;
-            bk[K - 1] = qi;
-#pragma unroll
-            for (int k = K - 1; k > 0; k--) {
-              if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bk[k] < bk[k - 1])) {
-                const float td_ = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td_;
-                const int tk_ = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk_;
-              }
-            }
+          if (d < best || qi < bestk) {  // (d, qi) precedes the K-th (kk-th) best: insert it in order
+            topk_insert<K>(bd, bk, d, qi);
           }
         }
       }
@@ -319,7 +336,7 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
       scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
     };
 
-    for (int r = 1; r <= MVP_GRID_MAXRING && !done && budget >= 0; r++) {
+    for (int r = 1; r <= kMaxRing && !done && budget >= 0; r++) {
       if (r == 1) {
         // ---- the 3x3x3 cube, unrolled: per-axis squared gaps of the two outer slabs once (inf = outside the
         // grid), the centre row first so that a good `best` prunes the other eight
@@ -384,8 +401,11 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
   if (done) {
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      dist[(size_t)orig * K + k] = bd[k];
-      idx[(size_t)orig * K + k] = bk[k];
+      if (!kRT || k >= K - kk) {  // real entries follow the phantoms
+        const int o = kRT ? k - (K - kk) : k;
+        dist[(size_t)orig * ko + o] = bd[k];
+        idx[(size_t)orig * ko + o] = bk[k];
+      }
     }
   } else {
     // append to the left-over list of (direction, cloud): one atomic per group of lanes sharing the list
@@ -464,7 +484,7 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
   chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
   const long long total = (long long)b * ((long long)n + m);
   chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-      b, n, m, W, dist1, dist2, idx1, idx2);
+      b, n, m, W, dist1, dist2, idx1, idx2, 1);
   chamfer_grid_plan_kernel<<<1, 256, 0, s>>>(b, n, m, W);
   count_launch(3);
   int rc = launch_status();
@@ -503,11 +523,137 @@ int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float 
   chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, unknown, known, W);
   const long long total = (long long)b * n;
   chamfer_grid_query_kernel<3><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-      b, n, m, W, dist2, nullptr, idx, nullptr);
+      b, n, m, W, dist2, nullptr, idx, nullptr, 3);
   count_launch(2);
   int rc = launch_status();
   if (rc) return rc;
   return three_nn_rest_launch(b, n, m, unknown, known, dist2, idx, W.list[0], W.count, s);
 }
 
+
+// ---- k nearest neighbours of 3-D points (mvp_knn_points) ---------------------------------------------------------------
+// Exhaustive top-k: one thread per query, the searched cloud broadcast from shared memory; the same ordered list and
+// the same (distance, index) order as the grid search.  kRest: the queries are the count[b] entries of list + b*n
+// (what the grid search did not finish); CTAs beyond the list length leave at once.  Also the whole search for
+// clouds too small for a grid to pay.
+constexpr int kTopkTile = 1024;
+template <int K, bool kRest>
+__global__ void __launch_bounds__(128)
+topk_nn_kernel(int n, int m, int kk, const float *__restrict__ queries, const float *__restrict__ cloud,
+               float *__restrict__ dist2, int *__restrict__ idx, const int *__restrict__ list,
+               const int *__restrict__ count) {
+  __shared__ float4 tile[kTopkTile];
+  const int b = blockIdx.y;
+  const int nq = kRest ? __ldg(count + b) : n;
+  if (blockIdx.x * 128 >= nq) return;
+  int p = blockIdx.x * 128 + threadIdx.x;
+  const bool active = p < nq;
+  if (kRest && active) p = __ldg(list + (size_t)b * n + p);
+  const float *C = cloud + (size_t)b * m * 3;
+  float qx = 0, qy = 0, qz = 0;
+  if (active) {
+    const float *q = queries + ((size_t)b * n + p) * 3;
+    qx = __ldg(q + 0), qy = __ldg(q + 1), qz = __ldg(q + 2);
+  }
+  const float inf = __int_as_float(0x7f800000);
+  float bd[K];
+  int bk[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {  // K - kk phantoms at -inf in front: the kk-th real neighbour is slot K - 1
+    bd[k] = k < K - kk ? -inf : inf;
+    bk[k] = k < K - kk ? -1 : 0x7fffffff;
+  }
+  for (int j0 = 0; j0 < m; j0 += kTopkTile) {
+    const int cnt = min(kTopkTile, m - j0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += 128) {
+      const float *c = C + (size_t)(j0 + j) * 3;
+      tile[j] = make_float4(__ldg(c + 0), __ldg(c + 1), __ldg(c + 2), 0.f);
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int j = 0; j < cnt; j++) {
+      const float4 c = tile[j];
+      const float d = sqdist(c.x - qx, c.y - qy, c.z - qz);
+      // index order: an equal distance never precedes an earlier one; NaN distances are never kept
+      if (d < bd[K - 1] || (d == bd[K - 1] && j0 + j < bk[K - 1])) topk_insert<K>(bd, bk, d, j0 + j);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (k >= K - kk) {
+        dist2[((size_t)b * n + p) * kk + k - (K - kk)] = bd[k];
+        idx[((size_t)b * n + p) * kk + k - (K - kk)] = bk[k];
+      }
+    }
+  }
+}
+
+bool knn_points_grid_supported(int b, int n, int m, int k) {
+  return k <= 32 && b > 0 && b <= 65535 && n >= 256 && m >= 256 && n <= (1 << 20) && m <= (1 << 20) &&
+         (long long)b * ((long long)n + m) < (1LL << 31);
+}
+
+size_t knn_points_workspace_bytes(int b, int n, int m, int k) {
+  return knn_points_grid_supported(b, n, m, k) ? grid_plan(b, n, m, nullptr, nullptr) : 16;
+}
+
+template <int K, bool kGrid = true>
+static int knn_points_launch_k(int b, int n, int m, int k, const float *queries, const float *cloud, float *dist2,
+                               int *idx, void *ws, size_t ws_bytes, cudaStream_t s) {
+  if constexpr (kGrid)
+  if (knn_points_grid_supported(b, n, m, k) && ws && ws_bytes >= grid_plan(b, n, m, nullptr, nullptr)) {
+    GridWs W;
+    grid_plan(b, n, m, ws, &W);
+    W.key[0] = W.key[1] = nullptr;
+    const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
+    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * kGridMaxCells));
+    if (e != cudaSuccess) return (int)e;
+    chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, queries, cloud, W);
+    const long long total = (long long)b * n;
+    chamfer_grid_query_kernel<K, true><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+        b, n, m, W, dist2, nullptr, idx, nullptr, k);
+    topk_nn_kernel<K, true><<<dim3((n + 127) / 128, b), 128, 0, s>>>(n, m, k, queries, cloud, dist2, idx, W.list[0],
+                                                                      W.count);
+    count_launch(3);
+    return launch_status();
+  }
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = std::min(65535, b - b0);
+    topk_nn_kernel<K, false><<<dim3((n + 127) / 128, bb), 128, 0, s>>>(
+        n, m, k, queries + (size_t)b0 * n * 3, cloud + (size_t)b0 * m * 3, dist2 + (size_t)b0 * n * k,
+        idx + (size_t)b0 * n * k, nullptr, nullptr);
+    count_launch();
+  }
+  return launch_status();
+}
+
+int knn_points_launch(int b, int n, int m, int k, const float *queries, const float *cloud, float *dist2, int *idx,
+                      void *ws, size_t ws_bytes, cudaStream_t s) {
+  if (k <= 4) return knn_points_launch_k<4>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  if (k <= 8) return knn_points_launch_k<8>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  if (k <= 12) return knn_points_launch_k<12>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  if (k <= 16) return knn_points_launch_k<16>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  if (k <= 24) return knn_points_launch_k<24>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  if (k <= 32) return knn_points_launch_k<32>(b, n, m, k, queries, cloud, dist2, idx, ws, ws_bytes, s);
+  return knn_points_launch_k<64, false>(b, n, m, k, queries, cloud, dist2, idx, nullptr, 0, s);  // exhaustive only
+}
+
 }  // namespace mvp
+
+// k nearest points of `cloud` (b,m,3) for every query (b,n,3): squared distances and indices (b,n,k) in ascending
+// (distance, index) order; k <= min(m, 64).  See include/mvp_ops.h.
+MVP_API size_t mvp_knn_points_workspace_bytes(int b, int n, int m, int k) {
+  if (b < 0 || n < 0 || m < 0 || k < 1) return 16;
+  return mvp::knn_points_workspace_bytes(b, n, m, k);
+}
+
+MVP_API int mvp_knn_points(int b, int n, int m, int k, const float *queries, const float *cloud, float *dist2, int *idx,
+                           void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || k < 1 || k > 64 || k > m) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0) return MVP_OK;
+  if (!queries || !cloud || !dist2 || !idx) return MVP_ERR_INVALID_ARGUMENT;
+  return mvp::knn_points_launch(b, n, m, k, queries, cloud, dist2, idx, workspace, workspace_bytes, (cudaStream_t)stream);
+}

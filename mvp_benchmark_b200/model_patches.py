@@ -1,0 +1,61 @@
+"""Opt-in replacements for the k-nearest-neighbour helpers of the reference's completion models
+(completion/model_utils.py:242-271) — SURVEY.md §8(f) row 1.  They are CALLER code, outside the drop-in
+boundary, so nothing here is applied by default:
+
+    import model_utils, models.vrcnet
+    from mvp_benchmark_b200 import model_patches
+    model_patches.apply(model_utils, models.vrcnet)      # rebinds knn / knn_point / knn_point_all
+
+`from model_utils import *` copies the names into each model module, hence every module that uses them is
+passed.  The originals build a (B, N, M) matrix -|x|^2 + 2 x.y - |y|^2 with a batched matmul and call
+torch.topk (at VRCNet's sizes: 64 x 3072 x 3072 floats = 2.4 GB per call, ~45 % of the CUDA time of a training
+step); the replacements run one exact grid search (fused.knn_points).  Differences a user can observe:
+neighbours are ranked by the directly evaluated squared distance, ties by index, where the original ranks by
+the matmul expansion (≈1e-7 apart; near-ties may swap) and leaves exact ties unspecified; returned distances
+(knn_point) are recomputed from the gathered points, differentiable like the original's.
+Point sets that are not 3-D (feature-space kNN) fall through to the original function."""
+import torch
+
+from . import fused
+
+_ORIGINAL = {}
+
+
+def _neg_sqdist(queries, cloud, idx):
+    """-(|q - c_idx|^2) for idx (B, N, k) — differentiable wrt both, what the originals' `dist` output holds."""
+    B, N, k = idx.shape
+    gathered = cloud[torch.arange(B, device=cloud.device).view(B, 1, 1), idx.long()]  # (B, N, k, 3)
+    return -((queries.unsqueeze(2) - gathered) ** 2).sum(-1)
+
+
+def knn(x, k):
+    """model_utils.py:242-247: x (B, C, N) -> idx (B, N, k) int64 of the k nearest points (self included)."""
+    if x.dim() != 3 or x.size(1) != 3 or not x.is_cuda or x.dtype != torch.float32 or k > min(x.size(2), 64):
+        return _ORIGINAL["knn"](x, k)
+    _, idx = fused.knn_points(k, x.transpose(1, 2))
+    return idx.long()
+
+
+def knn_point(pk, point_input, point_output):
+    """model_utils.py:250-259: for every point of point_output (B, m, 3) its pk nearest points of point_input
+    (B, n, 3) -> (dist (B, m, pk) = NEGATIVE squared distances, descending; idx (B, m, pk) int64)."""
+    if (point_input.dim() != 3 or point_input.size(2) != 3 or not point_input.is_cuda
+            or point_input.dtype != torch.float32 or pk > min(point_input.size(1), 64)):
+        return _ORIGINAL["knn_point"](pk, point_input, point_output)
+    _, idx = fused.knn_points(pk, point_input, point_output)
+    return _neg_sqdist(point_output, point_input, idx), idx.long()
+
+
+def apply(*modules):
+    """Rebind knn / knn_point / knn_point_all in the given (already imported) modules.  Returns the number of
+    names replaced."""
+    count = 0
+    for mod in modules:
+        for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point)):
+            cur = getattr(mod, name, None)
+            if cur is None or cur is fn:
+                continue
+            _ORIGINAL.setdefault("knn_point" if name == "knn_point_all" else name, cur)
+            setattr(mod, name, fn)
+            count += 1
+    return count

@@ -283,3 +283,18 @@ def knn(k, xyz, center_xyz):
     if rc != 0:
         raise ValueError("oracle_knn: 0 < k <= 100 required (knn_cuda.cu:72-73)")
     return idx, d
+
+
+def knn_points(k, cloud, queries=None):
+    """completion/model_utils.py:242-259 (`knn`, `knn_point`) as an exact search: (dist2 (B, N, k), idx (B, N, k)
+    int32) ascending in (distance, index); queries default to the cloud itself."""
+    c = _f32(cloud)
+    q = c if queries is None else _f32(queries)
+    b, n, _ = q.shape
+    m = c.shape[1]
+    idx = np.empty((b, n, k), np.int32)
+    d = np.empty((b, n, k), np.float32)
+    rc = lib().oracle_knn_points(b, n, m, int(k), _fp(q), _fp(c), _fp(d), _ip(idx))
+    if rc != 0:
+        raise ValueError("oracle_knn_points: 1 <= k <= m required")
+    return d, idx

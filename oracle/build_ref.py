@@ -82,5 +82,27 @@ def build(force=False, verbose=False):
     return target
 
 
+MODEL_FILES = [
+    "completion/model_utils.py", "completion/models/__init__.py", "completion/models/pcn.py",
+    "completion/models/ecg.py", "completion/models/vrcnet.py", "completion/cfgs/pcn.yaml",
+    "completion/cfgs/ecg.yaml", "completion/cfgs/vrcnet.yaml",
+]
+
+
+def stage_models():
+    """Stage the reference's completion MODELS (the callers of the hot path: SURVEY.md §2.1 row 9, out of
+    scope and not rebuilt) unmodified under oracle/_ref/completion/ — git-ignored like the rest of
+    oracle/_ref/, so they never enter the history — for tools/model_step.py, which times an unmodified
+    VRCNet / PCN / ECG training step on our operators and on the reference kernels on the same B200
+    (/root/reference does not exist on the GPU box)."""
+    import shutil
+    for f in MODEL_FILES:
+        dst = os.path.join(OUT, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, f), dst)
+    return os.path.join(OUT, "completion")
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(stage_models())

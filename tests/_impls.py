@@ -61,6 +61,9 @@ class OracleImpl:
     def knn(self, k, xyz, centers):
         return self.o.knn(int(k), xyz, centers)
 
+    def knn_points(self, k, cloud, queries):
+        return self.o.knn_points(int(k), cloud, queries)
+
 
 class CudaImpl:
     name = "cuda"
@@ -277,3 +280,19 @@ class CudaImpl:
         idx, d = self.E((b, m, int(k)), t.int32), self.E((b, m, int(k)), t.float32)
         L.check(L.lib.mvp_knn(b, n, m, int(k), p(x), p(c), p(idx), p(d), self.S()), "mvp_knn")
         return self.N(idx, d)
+
+    def knn_points(self, k, cloud, queries, grid=True):
+        """grid=False: no workspace -> the exhaustive kernel."""
+        t, L, p = self.torch, self.L, self.L.ptr
+        c, q = self.T(cloud), self.T(queries)
+        b, n, _ = q.shape
+        m = c.shape[1]
+        d, idx = self.E((b, n, int(k)), t.float32), self.E((b, n, int(k)), t.int32)
+        if grid:
+            w = L.workspace(L.lib.mvp_knn_points_workspace_bytes(b, n, m, int(k)), self.dev)
+            w.fill_(0xA5)
+            L.check(L.lib.mvp_knn_points(b, n, m, int(k), p(q), p(c), p(d), p(idx), p(w), w.numel(), self.S()),
+                    "mvp_knn_points")
+        else:
+            L.check(L.lib.mvp_knn_points(b, n, m, int(k), p(q), p(c), p(d), p(idx), None, 0, self.S()), "mvp_knn_points")
+        return self.N(d, idx)

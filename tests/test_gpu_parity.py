@@ -340,6 +340,47 @@ def test_knn_vs_oracle(gpu, cpu, kind, b, n, p, k):
     _cases.eq(got[0], want[0], "knn idx")
 
 
+# ---------------------------------------------------------------------------------------------- knn_points
+@pytest.mark.parametrize("kind_q,kind_c", [("uniform", "uniform"), ("sphere", "sphere"), ("lattice", "lattice"),
+                                           ("duplicates", "duplicates"), ("clustered", "uniform"), ("uniform", "clustered"),
+                                           ("planar", "planar"), ("shifted", "shifted"), ("outliers", "uniform"),
+                                           ("uniform", "constant"), ("tiny", "tiny")])
+@pytest.mark.parametrize("b,n,m,k", [(3, 1536, 3072, 10), (2, 700, 300, 16), (2, 256, 2051, 20), (2, 300, 1000, 32),
+                                     (2, 1024, 1024, 1), (2, 513, 777, 5)])
+def test_knn_points_grid_vs_oracle(gpu, cpu, kind_q, kind_c, b, n, m, k):
+    """mvp_knn_points through the grid (runtime-k ordered list, left-over queries through the exhaustive kernel) on
+    benign and hostile distributions, exact ties included: bit-identical to the CPU restatement, and the exhaustive
+    kernel gives the same bits."""
+    q, c = _data.cloud(kind_q, b, n, 83), _data.cloud(kind_c, b, m, 84)
+    want = cpu.knn_points(k, c, q)
+    got = gpu.knn_points(k, c, q)
+    _cases.eq(got[1], want[1], f"knn_points idx {kind_q}/{kind_c}")
+    _cases.eq(got[0], want[0], f"knn_points dist2 {kind_q}/{kind_c}")
+    if k in (10, 32):
+        ex = gpu.knn_points(k, c, q, grid=False)
+        _cases.eq(ex[1], want[1], "knn_points exhaustive idx")
+        _cases.eq(ex[0], want[0], "knn_points exhaustive dist2")
+
+
+@pytest.mark.parametrize("b,n,m,k", [(8, 12, 12, 2), (2, 5, 7, 7), (1, 300, 100, 64), (2, 100, 3000, 40), (70, 64, 64, 3)])
+def test_knn_points_small_and_large_k(gpu, cpu, b, n, m, k):
+    """Shapes outside the grid's range (small clouds, k > 32) run the exhaustive kernel."""
+    q, c = _data.uniform(b, n, 85), _data.uniform(b, m, 86)
+    want, got = cpu.knn_points(k, c, q), gpu.knn_points(k, c, q)
+    _cases.eq(got[1], want[1], "knn_points idx")
+    _cases.eq(got[0], want[0], "knn_points dist2")
+
+
+def test_knn_points_self_query_at_vrcnet_size(gpu, cpu):
+    """knn(pt, 16) on a 3072-point cloud (vrcnet.py:246): first neighbour is the point itself at distance 0."""
+    x = _data.uniform(4, 3072, 87)
+    d, i = gpu.knn_points(16, x, x)
+    assert (i[:, :, 0] == np.arange(3072)[None]).all() and (d[:, :, 0] == 0).all()
+    assert (np.diff(d, axis=2) >= 0).all()
+    want = cpu.knn_points(16, x, x)
+    _cases.eq(i, want[1], "knn_points self idx")
+
+
 # ---------------------------------------------------------------------------------------------- gathers
 # staged path (M >= N/2: TMA-staged rows, shared-memory atomics in the backward) and direct path (M << N, rows that do
 # not fit shared memory), aligned and unaligned rows, channel counts that do not divide the group size

@@ -187,3 +187,44 @@ def test_ops_are_cuda_graph_capturable(ops, cuda):
         assert torch.equal(a, b)
     for a, b in zip(got[1], want[1]):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def _torch_knn_point(pk, point_input, point_output):
+    """The formula of completion/model_utils.py:250-259, restated for the test (matmul expansion + topk)."""
+    inner = -2 * torch.matmul(point_output, point_input.transpose(2, 1))
+    xx = torch.sum(point_output ** 2, dim=2, keepdim=True)
+    yy = torch.sum(point_input ** 2, dim=2).unsqueeze(1)
+    return (-xx - inner - yy).topk(k=pk, dim=-1)
+
+
+def test_model_patches_knn_and_knn_point(cuda, cpu):
+    """Opt-in kNN replacements: same shapes / dtypes / sign conventions as
+    model_utils.knn / knn_point, same neighbour sets as the matmul + topk formula away from near-ties,
+    gradients through the returned distances, non-3-D inputs fall through to the original function."""
+    import types
+    from mvp_benchmark_b200 import model_patches as mp
+    calls = []
+
+    def orig_knn(x, k):
+        calls.append("knn")
+        return torch.zeros(x.size(0), x.size(2), k, dtype=torch.long, device=x.device)
+
+    fake = types.SimpleNamespace(knn=orig_knn, knn_point=_torch_knn_point, knn_point_all=_torch_knn_point)
+    assert mp.apply(fake) == 3 and mp.apply(fake) == 0
+    B, N, M = 4, 1536, 768
+    cloud = T(_data.uniform(B, N, 11), cuda)
+    sub = cloud[:, :M].contiguous().requires_grad_(True)
+    idx = fake.knn(cloud.transpose(1, 2).contiguous(), 16)
+    assert idx.shape == (B, N, 16) and idx.dtype == torch.int64 and not calls
+    _cases.eq(idx.cpu().numpy().astype(np.int32), cpu.o.knn_points(16, cloud.cpu().numpy())[1], "patched knn")
+    negd, pidx = fake.knn_point(10, cloud, sub)
+    assert negd.shape == (B, M, 10) and pidx.dtype == torch.int64 and negd.requires_grad
+    ref_d, ref_i = _torch_knn_point(10, cloud, sub.detach())
+    torch.testing.assert_close(negd.detach(), ref_d, atol=5e-6, rtol=0)
+    agree = (pidx.sort(dim=2)[0] == ref_i.sort(dim=2)[0]).all(dim=2).float().mean().item()
+    assert agree > 0.995, agree
+    negd.sum().backward()
+    assert sub.grad is not None and torch.isfinite(sub.grad).all()
+    feat = torch.randn(2, 64, 100, device=cuda)            # feature-space kNN: not ours
+    fake.knn(feat, 5)
+    assert calls == ["knn"]

@@ -68,3 +68,29 @@ def test_oracle_emd_invariants():
     assert len(np.unique(a[0])) > 900          # near-bijection after 50 rounds (emd_module.py:99)
     d3k, a3k = oracle.emd_forward(x1, x2, 0.002, 3000)
     assert len(np.unique(a3k[0])) >= len(np.unique(a[0]))
+
+
+KNN_GOLD = os.path.join(HERE, "golden", "knn_model_utils.npz")
+
+
+@pytest.mark.parametrize("case", ["self16", "self20", "point10", "point2_small", "point4_sphere"])
+def test_oracle_knn_points_vs_reference_model_utils(case):
+    """oracle.knn_points against the reference's own torch `knn` / `knn_point` (completion/model_utils.py:242-259,
+    outputs stored by tests/golden/make_golden_knn.py).  The reference ranks by the matmul expansion
+    -|x|^2 + 2x.y - |y|^2 (rounding ~1e-6 at unit scale): wherever its k-th and (k+1)-th distances are further
+    apart than that, the neighbour SET must be identical; everywhere, the exact distances of the reference's
+    choice and ours must agree to that rounding, rank by rank."""
+    import oracle
+    G = np.load(KNN_GOLD)
+    cloud, queries, ref_idx, k = G[case + "_cloud"], G[case + "_queries"], G[case + "_idx"], int(G[case + "_k"])
+    d, idx = oracle.knn_points(k, cloud, queries)
+    assert idx.shape == ref_idx.shape and (np.diff(d, axis=2) >= 0).all()
+    clear = G[case + "_kth_gap"] > 5e-6
+    assert clear.mean() > 0.9
+    same_set = (np.sort(idx, axis=2) == np.sort(ref_idx, axis=2)).all(axis=2)
+    assert same_set[clear].all()
+    b = np.arange(cloud.shape[0])[:, None, None]
+    exact_ref = ((queries[:, :, None, :].astype(np.float64) - cloud[b, ref_idx].astype(np.float64)) ** 2).sum(-1)
+    np.testing.assert_allclose(d, exact_ref, atol=5e-6, rtol=0)
+    if case + "_negdist" in G.files:           # knn_point also returns -distance (model_utils.py:258)
+        np.testing.assert_allclose(-d, G[case + "_negdist"], atol=5e-6, rtol=0)
