@@ -145,6 +145,14 @@ def cpu_chamfer_sample(budget_s, b=B, n=N, m=M, seed=0):
     `nq` queries of both directions of one cloud.  Returns (pairs_per_s, cores, description, seconds)."""
     import numpy as np
     import oracle
+    # all the host threads there are: torchrun exports OMP_NUM_THREADS=1 to every rank, which would otherwise
+    # turn the CPU arm into a single-thread run at N > 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if oracle.num_threads() < avail:
+        oracle.set_num_threads(avail)
     cores = oracle.num_threads()
     rng = np.random.default_rng(seed)
     x1 = rng.random((n, 3), dtype=np.float32)

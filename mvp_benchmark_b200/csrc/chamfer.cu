@@ -186,6 +186,64 @@ chamfer_grad_kernel(int b, int n, int m, const float *__restrict__ xyz1, const f
   }
 }
 
+// The same two passes with four consecutive points per thread (n and m multiples of 4, 16-byte aligned tensors):
+// coordinates, indices and upstream gradients arrive as 128-bit loads, the own halves leave as three 128-bit
+// stores, and the scattered halves as ONE 64-bit + one 32-bit reduction per point instead of three 32-bit ones
+// (red.global.add.v2.f32 on whichever pair of the 12-byte row is 8-byte aligned).
+template <bool kScatter>
+__global__ void __launch_bounds__(256)
+chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                     const float *__restrict__ gd1, const float *__restrict__ gd2,
+                     const int *__restrict__ idx1, const int *__restrict__ idx2, float *gx1, float *gx2) {
+  const long long total1 = (long long)b * n / 4, total = total1 + (long long)b * m / 4;  // groups of 4 points
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const bool first = q < total1;
+    const long long p = (first ? q : q - total1) * 4;
+    const int na = first ? n : m, nb = first ? m : n;
+    const long long cloud = p / na;  // na % 4 == 0: the four points share a cloud
+    const float *A = first ? xyz1 : xyz2;
+    const float *Bp = (first ? xyz2 : xyz1) + cloud * nb * 3;
+    float *GA = first ? gx1 : gx2;
+    float *GB = (first ? gx2 : gx1) + cloud * nb * 3;
+    const int4 j4 = __ldg(reinterpret_cast<const int4 *>((first ? idx1 : idx2) + p));
+    const float4 g4 = __ldg(reinterpret_cast<const float4 *>((first ? gd1 : gd2) + p));
+    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(A + p * 3));
+    const float4 a1 = __ldg(reinterpret_cast<const float4 *>(A + p * 3) + 1);
+    const float4 a2 = __ldg(reinterpret_cast<const float4 *>(A + p * 3) + 2);
+    const float ax[4] = {a0.x, a0.w, a1.z, a2.y}, ay[4] = {a0.y, a1.x, a1.w, a2.z}, az[4] = {a0.z, a1.y, a2.x, a2.w};
+    const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float vx[4], vy[4], vz[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float *t = Bp + (long long)jj[e] * 3;
+      const float g = gg[e] * 2;
+      vx[e] = g * (ax[e] - __ldg(t + 0));
+      vy[e] = g * (ay[e] - __ldg(t + 1));
+      vz[e] = g * (az[e] - __ldg(t + 2));
+    }
+    if (!kScatter) {
+      float4 *o = reinterpret_cast<float4 *>(GA + p * 3);
+      o[0] = make_float4(vx[0], vy[0], vz[0], vx[1]);
+      o[1] = make_float4(vy[1], vz[1], vx[2], vy[2]);
+      o[2] = make_float4(vz[2], vx[3], vy[3], vz[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float *t = GB + (long long)jj[e] * 3;
+        if ((reinterpret_cast<uintptr_t>(t) & 7) == 0) {
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t), "f"(-vx[e]), "f"(-vy[e]) : "memory");
+          atomicAdd(t + 2, -vz[e]);
+        } else {
+          atomicAdd(t, -vx[e]);
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t + 1), "f"(-vy[e]), "f"(-vz[e]) : "memory");
+        }
+      }
+    }
+  }
+}
+
 }  // namespace mvp
 
 using namespace mvp;
@@ -254,10 +312,20 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
   cudaStream_t s = (cudaStream_t)stream;
   const long long total = (long long)b * (n + m);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-  chamfer_grad_kernel<false><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
-                                                  gradxyz2);
-  chamfer_grad_kernel<true><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
-                                                 gradxyz2);
+  auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (n % 4 == 0 && m % 4 == 0 && al16(xyz1) && al16(xyz2) && al16(graddist1) && al16(graddist2) && al16(idx1) &&
+      al16(idx2) && al16(gradxyz1) && al16(gradxyz2)) {
+    const int grid4 = (int)std::min<long long>((total / 4 + 255) / 256, (long long)kNumSMs * 16);
+    chamfer_grad4_kernel<false><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                      gradxyz2);
+    chamfer_grad4_kernel<true><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                     gradxyz2);
+  } else {
+    chamfer_grad_kernel<false><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                    gradxyz2);
+    chamfer_grad_kernel<true><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                   gradxyz2);
+  }
   count_launch(2);
   count_launch();
   return launch_status();

@@ -22,6 +22,10 @@
 //
 // Degenerate inputs (non-finite coordinates, zero or astronomically large extent) mark the grid invalid; all
 // queries against it go to the left-over list, i.e. the brute-force path and its semantics.
+#include <cooperative_groups.h>
+
+#include <cstdio>
+
 #include "common.cuh"
 #include "grid.cuh"
 
@@ -88,10 +92,22 @@ static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
 }
 
 // ------------------------------------------------------------------------------------------------ build
+// Clouds of up to kGridRankPts points keep (cell, rank inside the cell) of every point in shared memory between the
+// histogram and the scatter pass: the rank is what the histogram's atomicAdd returned, so the scatter needs no second
+// round of shared-memory atomics (2 cycles per lane each — they, not the loads, bound this kernel).
+constexpr int kGridRankPts = 16384;
+__host__ __device__ inline size_t grid_hist_words(const int cap[2]) {  // histogram, padded for 128-bit access
+  return ((size_t)(cap[0] > cap[1] ? cap[0] : cap[1]) + 7) & ~(size_t)7;
+}
+static size_t grid_build_smem(const int cap[2], int n, int m) {
+  const int np = std::max(n, m);
+  return sizeof(int) * (grid_hist_words(cap) + (np <= kGridRankPts ? (size_t)np : 0));
+}
+
 __global__ void __launch_bounds__(kGridThreads, 1)
 chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                           GridWs W) {
-  extern __shared__ int hist[];  // cap ints
+  extern __shared__ __align__(16) int hist[];  // cap ints
   __shared__ float s_red[6][32];
   __shared__ int s_fin[32];
   __shared__ int s_warp[32];
@@ -106,13 +122,25 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
   // ---- pass 1: bounding box and finiteness
   float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   int fin = 1;
-  for (int i = tid; i < np; i += kGridThreads) {
+  // every pass walks the cloud in batches of kBatch points per thread with all loads of a batch issued before their
+  // first use: the passes are latency-bound (one CTA per SM, 16 points per thread at n = 16384)
+  constexpr int kBatch = 4;
+  for (int i0 = tid; i0 < np; i0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const float v = __ldg(P + (size_t)i * 3 + a);
-      lo[a] = fminf(lo[a], v);
-      hi[a] = fmaxf(hi[a], v);
-      fin &= (fabsf(v) <= 3.0e38f) ? 1 : 0;  // false for NaN and +-inf
+    for (int u = 0; u < kBatch; u++) {
+      const int i = min(i0 + u * kGridThreads, np - 1);  // clamped: a repeated point changes neither box nor flag
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        lo[a] = fminf(lo[a], v[u][a]);
+        hi[a] = fmaxf(hi[a], v[u][a]);
+        fin &= (fabsf(v[u][a]) <= 3.0e38f) ? 1 : 0;  // false for NaN and +-inf
+      }
     }
   }
 #pragma unroll
@@ -161,9 +189,27 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
     return (cz * h.g[1] + cy) * h.g[0] + cx;
   };
 
-  // ---- pass 2: histogram
-  for (int i = tid; i < np; i += kGridThreads)
-    atomicAdd(&hist[cell_of(__ldg(P + (size_t)i * 3 + 0), __ldg(P + (size_t)i * 3 + 1), __ldg(P + (size_t)i * 3 + 2))], 1);
+  // ---- pass 2: histogram (and, for clouds that fit, every point's cell and arrival rank)
+  const bool ranked = max(n, m) <= kGridRankPts;
+  unsigned *code = reinterpret_cast<unsigned *>(hist + grid_hist_words(W.cap));  // [np] when ranked
+  for (int i0 = tid; i0 < np; i0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = min(i0 + u * kGridThreads, np - 1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = i0 + u * kGridThreads;
+      if (i < np) {
+        const int c = cell_of(v[u][0], v[u][1], v[u][2]);
+        const int r = atomicAdd(&hist[c], 1);
+        if (ranked) code[i] = ((unsigned)c << 15) | (unsigned)r;  // c < 2^15 cells, r < 2^14 points
+      }
+    }
+  }
   __syncthreads();
 
   // ---- exclusive scan over the cells (contiguous chunk per thread, warp scan, scan of warp totals)
@@ -207,11 +253,296 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
 
   // ---- pass 3: scatter (order inside a cell is arbitrary; the query's tie rule is explicit)
   float4 *S = (side ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * np;
-  for (int i = tid; i < np; i += kGridThreads) {
-    const float x = __ldg(P + (size_t)i * 3 + 0), y = __ldg(P + (size_t)i * 3 + 1), z = __ldg(P + (size_t)i * 3 + 2);
-    const int pos = atomicAdd(&hist[cell_of(x, y, z)], 1);
-    S[pos] = make_float4(x, y, z, __int_as_float(i));
+  for (int i0 = tid; i0 < np; i0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = min(i0 + u * kGridThreads, np - 1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = i0 + u * kGridThreads;
+      if (i < np) {
+        int pos;
+        if (ranked) {
+          const unsigned cr = code[i];
+          pos = hist[cr >> 15] + (int)(cr & 0x7fffu);  // hist holds the cell starts now
+        } else {
+          pos = atomicAdd(&hist[cell_of(v[u][0], v[u][1], v[u][2])], 1);
+        }
+        S[pos] = make_float4(v[u][0], v[u][1], v[u][2], __int_as_float(i));
+      }
+    }
   }
+}
+
+// ---- the same build for clouds of up to kGridRankPts points, split over a cluster of TWO CTAs ------------------------
+// One CTA per (cloud, side) leaves 84 of the 148 SMs idle at B = 32 and every thread walks 16 points through three
+// dependent passes.  Here each CTA of a pair owns half of the points: partial bounding boxes and partial histograms
+// meet through distributed shared memory (two cluster barriers), both CTAs derive the same header and the same
+// cell starts, and CTA 1's cursor of a cell starts behind CTA 0's points of that cell.
+#ifdef MVP_GRID_BUILD_TIMING  // debugging aid: per-phase clock64 stamps of thread 0, printed by cloud 0 / side 0
+#define MVP_B2_STAMP(k) b2_t[k] = clock64()
+#else
+#define MVP_B2_STAMP(k)
+#endif
+constexpr int kBuild2Per = (kGridRankPts / MVP_GRID_PPC + kGridThreads - 1) / kGridThreads;  // cells per thread (8)
+static_assert(kGridRankPts / MVP_GRID_PPC <= kGridMaxCells, "cap of the cluster build");
+
+__global__ void __cluster_dims__(1, 1, 2) __launch_bounds__(kGridThreads, 1)
+chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                           GridWs W) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) int hist[];  // cap ints, then the codes of this CTA's points
+  __shared__ float s_red[6][32];
+  __shared__ int s_fin[32];
+  __shared__ int s_warp[32];
+  __shared__ float s_part[8];    // this CTA's box (lo xyz, hi xyz) and finiteness flag, read by the peer
+  __shared__ GridHdr s_hdr;
+  const int cloud = blockIdx.x, side = blockIdx.y;
+  const int rank = (int)cluster.block_rank(), peer = rank ^ 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = side ? m : n;
+  const int cap = side ? W.cap[1] : W.cap[0];
+  const float *P = (side ? xyz2 : xyz1) + (size_t)cloud * np * 3;
+  const int half0 = (np + 1) / 2;
+  const int first = rank ? half0 : 0, mine = rank ? np - half0 : half0;  // this CTA's points: [first, first + mine)
+  const float inf = __int_as_float(0x7f800000);
+  constexpr int kBatch = 4;
+#ifdef MVP_GRID_BUILD_TIMING
+  long long b2_t[10];
+#endif
+  MVP_B2_STAMP(0);
+
+  // ---- pass 1: bounding box and finiteness of this half
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  int fin = 1;
+  for (int j0 = tid; j0 < mine; j0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = first + min(j0 + u * kGridThreads, mine - 1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        lo[a] = fminf(lo[a], v[u][a]);
+        hi[a] = fmaxf(hi[a], v[u][a]);
+        fin &= (fabsf(v[u][a]) <= 3.0e38f) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+    fin &= __shfl_xor_sync(0xffffffffu, fin, off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      s_red[a][warp] = lo[a];
+      s_red[3 + a][warp] = hi[a];
+    }
+    s_fin[warp] = fin;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kGridThreads / 32; w++) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        lo[a] = fminf(lo[a], s_red[a][w]);
+        hi[a] = fmaxf(hi[a], s_red[3 + a][w]);
+      }
+      fin &= s_fin[w];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) s_part[a] = lo[a], s_part[3 + a] = hi[a];
+    s_part[6] = __int_as_float(fin);
+  }
+  MVP_B2_STAMP(1);
+  cluster.sync();
+  MVP_B2_STAMP(2);
+  if (tid == 0) {
+    const float *q = cluster.map_shared_rank(s_part, peer);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {  // min / max commute: both CTAs arrive at the same box, hence the same header
+      lo[a] = fminf(lo[a], q[a]);
+      hi[a] = fmaxf(hi[a], q[3 + a]);
+    }
+    fin &= __float_as_int(q[6]);
+    const GridHdr h = grid_header(lo, hi, fin, cap);
+    s_hdr = h;
+    if (rank == 0) {
+      W.hdr[side * b + cloud] = h;
+      W.count[side * b + cloud] = 0;
+    }
+  }
+  __syncthreads();
+  const GridHdr h = s_hdr;
+  const int ncell = h.ncell;
+  MVP_B2_STAMP(3);
+  for (int c = tid; c < ncell; c += kGridThreads) hist[c] = 0;
+  __syncthreads();
+  MVP_B2_STAMP(4);
+
+  auto cell_of = [&](float x, float y, float z) {
+    if (!h.valid) return 0;
+    const int cx = cell_coord((x - h.lo[0]) * h.inv_s, h.g[0]);
+    const int cy = cell_coord((y - h.lo[1]) * h.inv_s, h.g[1]);
+    const int cz = cell_coord((z - h.lo[2]) * h.inv_s, h.g[2]);
+    return (cz * h.g[1] + cy) * h.g[0] + cx;
+  };
+
+  // ---- pass 2: histogram of this half; every point keeps (cell, arrival rank) for the scatter
+  unsigned *code = reinterpret_cast<unsigned *>(hist + grid_hist_words(W.cap));  // [mine]
+  for (int j0 = tid; j0 < mine; j0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = first + min(j0 + u * kGridThreads, mine - 1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int j = j0 + u * kGridThreads;
+      if (j < mine) {
+        const int c = cell_of(v[u][0], v[u][1], v[u][2]);
+        code[j] = ((unsigned)c << 15) | (unsigned)atomicAdd(&hist[c], 1);
+      }
+    }
+  }
+  MVP_B2_STAMP(5);
+  cluster.sync();  // both partial histograms are complete
+  MVP_B2_STAMP(6);
+
+  // ---- exclusive scan over the cells of (own + peer) counts; the counts sit in registers across the barrier after
+  // which this CTA overwrites its histogram with its cursors
+  // (each thread owns kBuild2Per = 8 consecutive cells: two 128-bit loads from each histogram — scalar loads at a
+  // stride of 8 words are 8-way bank conflicts here and eight remote round trips there; measured 19-24k of the
+  // kernel's 47k cycles before)
+  static_assert(kBuild2Per == 8, "two int4 per thread");
+  const int4 *own4 = reinterpret_cast<const int4 *>(hist);
+  const int4 *oth4 = reinterpret_cast<const int4 *>(cluster.map_shared_rank(hist, peer));
+  const int c0 = tid * kBuild2Per;
+  int own[kBuild2Per], oth[kBuild2Per], sum = 0;
+  {
+    int4 a0 = make_int4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    if (c0 < ncell) {  // words past ncell (inside the padded allocation) are masked below
+      a0 = own4[2 * tid], a1 = own4[2 * tid + 1];
+      b0 = oth4[2 * tid], b1 = oth4[2 * tid + 1];
+    }
+    const int ta[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const int tb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < kBuild2Per; e++) {
+      own[e] = c0 + e < ncell ? ta[e] : 0;
+      oth[e] = c0 + e < ncell ? tb[e] : 0;
+      sum += own[e] + oth[e];
+    }
+  }
+  int incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  cluster.sync();  // (also a CTA barrier) the peer has read this CTA's histogram: it may be overwritten now
+  if (warp == 0) {
+    int v = s_warp[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+  if (c0 < ncell) {
+    int cur[kBuild2Per];
+#pragma unroll
+    for (int e = 0; e < kBuild2Per; e++) {
+      cur[e] = run + (rank ? oth[e] : 0);  // CTA 1 fills a cell behind CTA 0's points
+      run += own[e] + oth[e];
+    }
+    int4 *h4 = reinterpret_cast<int4 *>(hist);
+    h4[2 * tid] = make_int4(cur[0], cur[1], cur[2], cur[3]);
+    h4[2 * tid + 1] = make_int4(cur[4], cur[5], cur[6], cur[7]);
+  }
+  __syncthreads();
+  int *start = (side ? W.start[1] : W.start[0]) + (size_t)cloud * (cap + 1);
+  if (rank == 0)  // CTA 0's cursors are the cell starts: coalesced copy
+    for (int c = tid; c < ncell; c += kGridThreads) start[c] = hist[c];
+  if (rank == 0 && tid == 0) start[ncell] = np;
+  __syncthreads();
+  MVP_B2_STAMP(7);
+  {  // keys of the fused brute-force kernels, in case this cloud pair is handed over to them
+    unsigned long long *key = side ? W.key[1] : W.key[0];
+    if (key)
+      for (int j = tid; j < mine; j += kGridThreads) key[(size_t)cloud * np + first + j] = ~0ull;
+  }
+
+  MVP_B2_STAMP(8);
+  // ---- pass 3: scatter this half (order inside a cell is arbitrary; the query's tie rule is explicit)
+  float4 *S = (side ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * np;
+  for (int j0 = tid; j0 < mine; j0 += kBatch * kGridThreads) {
+    float v[kBatch][3];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int i = first + min(j0 + u * kGridThreads, mine - 1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) v[u][a] = __ldg(P + (size_t)i * 3 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int j = j0 + u * kGridThreads;
+      if (j < mine) {
+        const unsigned cr = code[j];
+        S[hist[cr >> 15] + (int)(cr & 0x7fffu)] = make_float4(v[u][0], v[u][1], v[u][2], __int_as_float(first + j));
+      }
+    }
+  }
+  MVP_B2_STAMP(9);
+#ifdef MVP_GRID_BUILD_TIMING
+  __syncthreads();
+  if (tid == 0 && cloud == 0 && side == 0)
+    printf("build2 rank %d: pass1 %lld sync %lld header %lld zero %lld pass2 %lld sync %lld scan %lld keys %lld pass3 %lld total %lld\n", rank,
+           b2_t[1] - b2_t[0], b2_t[2] - b2_t[1], b2_t[3] - b2_t[2], b2_t[4] - b2_t[3], b2_t[5] - b2_t[4], b2_t[6] - b2_t[5],
+           b2_t[7] - b2_t[6], b2_t[8] - b2_t[7], b2_t[9] - b2_t[8], b2_t[9] - b2_t[0]);
+#endif
+}
+
+// Launches the build for both sides: the two-CTA cluster kernel when both clouds fit it, else one CTA per side.
+static int grid_build_launch(int b, int n, int m, const float *xyz1, const float *xyz2, const GridWs &W,
+                             cudaStream_t s) {
+  const size_t smem = grid_build_smem(W.cap, n, m);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * (kGridMaxCells + 8 + kGridRankPts)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chamfer_grid_build2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(int) * (kGridRankPts / MVP_GRID_PPC + 8 + kGridRankPts)));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (std::max(n, m) <= kGridRankPts && std::max(W.cap[0], W.cap[1]) <= kBuild2Per * kGridThreads)
+    chamfer_grid_build2_kernel<<<dim3(b, 2, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
+  else
+    chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
+  return MVP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ query
@@ -473,15 +804,10 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
   if (ws_bytes < grid_bytes + key_bytes) return MVP_ERR_WORKSPACE;
   W.key[0] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ws) + grid_bytes);
   W.key[1] = W.key[0] + (size_t)b * n;
-  const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(int) * kGridMaxCells));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  {
+    const int rc = grid_build_launch(b, n, m, xyz1, xyz2, W, s);
+    if (rc) return rc;
   }
-  chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
   const long long total = (long long)b * ((long long)n + m);
   chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
       b, n, m, W, dist1, dist2, idx1, idx2, 1);
@@ -516,11 +842,10 @@ int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float 
   GridWs W;
   if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
   W.key[0] = W.key[1] = nullptr;
-  const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
-  cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(int) * kGridMaxCells));
-  if (e != cudaSuccess) return (int)e;
-  chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, unknown, known, W);
+  {
+    const int rc = grid_build_launch(b, n, m, unknown, known, W, s);
+    if (rc) return rc;
+  }
   const long long total = (long long)b * n;
   chamfer_grid_query_kernel<3><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
       b, n, m, W, dist2, nullptr, idx, nullptr, 3);
@@ -607,11 +932,10 @@ static int knn_points_launch_k(int b, int n, int m, int k, const float *queries,
     GridWs W;
     grid_plan(b, n, m, ws, &W);
     W.key[0] = W.key[1] = nullptr;
-    const size_t smem = sizeof(int) * (size_t)std::max(W.cap[0], W.cap[1]);
-    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(int) * kGridMaxCells));
-    if (e != cudaSuccess) return (int)e;
-    chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, queries, cloud, W);
+    {
+      const int rc = grid_build_launch(b, n, m, queries, cloud, W, s);
+      if (rc) return rc;
+    }
     const long long total = (long long)b * n;
     chamfer_grid_query_kernel<K, true><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
         b, n, m, W, dist2, nullptr, idx, nullptr, k);

@@ -21,6 +21,13 @@
 #define MVP_FPS_PMAX 8  // tuning knob (tools/pair_variants.py): points per thread before more warps are used
 #endif
 
+#ifdef MVP_FPS_TIMING  // debugging aid: clock64 phase totals of thread 0 of cloud 0, printed at the end
+#include <cstdio>
+#define MVP_FPS_STAMP(k) { const long long t_ = clock64(); fps_acc[k] += t_ - fps_last; fps_last = t_; }
+#else
+#define MVP_FPS_STAMP(k)
+#endif
+
 namespace mvp {
 
 __device__ __forceinline__ uint32_t fps_key(int k, int log2T) {
@@ -122,6 +129,9 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
   int old = 0;
   if (tid == 0) idxs[0] = 0;
   __syncthreads();
+#ifdef MVP_FPS_TIMING
+  long long fps_acc[6] = {0, 0, 0, 0, 0, 0}, fps_last = clock64();
+#endif
 
   for (int j = 1; j < m; j++) {
     float vmax = -1.f;
@@ -154,8 +164,10 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
       }
     }
     const int vbits = __float_as_int(vmax);
+    MVP_FPS_STAMP(0);
     const int wbits = redux_max_s32(vbits);
     uint32_t key = 0xffffffffu;
+    MVP_FPS_STAMP(1);
     if (vbits == wbits) {
 #pragma unroll
       for (int i = 0; i < P; i++) {
@@ -167,21 +179,30 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
         }
       }
     }
+    MVP_FPS_STAMP(2);
     const uint32_t wkey = redux_min_u32(key);
     const int buf = j & 1;
     if (lane == 0) {
       s_val[buf][warp] = wbits;
       s_key[buf][warp] = wkey;
     }
+    MVP_FPS_STAMP(3);
     __syncthreads();
     const int v = s_val[buf][lane];  // slots >= NW hold the sentinel
     const uint32_t kk = s_key[buf][lane];
     const int bv = redux_max_s32(v);
     const uint32_t bk = redux_min_u32(v == bv ? kk : 0xffffffffu);
     old = fps_unkey(bk, log2T);
+    MVP_FPS_STAMP(4);
     if (tid == 0) idxs[j] = old;
     (void)NW;
   }
+#ifdef MVP_FPS_TIMING
+  if (tid == 0 && blockIdx.x == 0)
+    printf("fps TB %d P %d n %d m %d: cycles/pick  update %lld redux.max %lld keys %lld redux.min+STS %lld bar+LDS+2redux+unkey %lld\n",
+           TB, P, n, m, fps_acc[0] / (m - 1), fps_acc[1] / (m - 1), fps_acc[2] / (m - 1), fps_acc[3] / (m - 1),
+           fps_acc[4] / (m - 1));
+#endif
   if (temp != nullptr) {
     temp += (size_t)blockIdx.x * n;
 #pragma unroll
