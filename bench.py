@@ -46,7 +46,7 @@ B, N, M = 32, 16384, 16384
 L2_BYTES = 126 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of the forward's kernels from the ncu --set full capture summarised in
 # profiles/ (per forward, B=32 N=M=16384)
-TRAFFIC_BYTES = 36.9e6  # build 15.3 + 2.7 MB, query 18.9 + 0.0 MB (profiles/r1_chamfer_grid_full.md)
+TRAFFIC_BYTES = 37.3e6  # build2 15.5 + 2.9 MB, query 18.9 + 0.0 MB (profiles/r1_chamfer_grid_full.md)
 METRIC = "chamfer_fwd_bwd_point_pairs_per_s"
 UNIT = "point-pairs/s"
 WORKLOAD = "chamfer_distance_fwd_bwd B=32 N=M=16384 fp32 uniform[0,1)^3 (PCN/C2 fine-output CD size)"
@@ -299,12 +299,55 @@ def run_ours(args):
         t_wall = time.perf_counter() - t_wall
     launches = _lib.launch_count() - launches0
     mdist.barrier()
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
-    total_ms = mdist.max_over_ranks(total_ms, dev)
+    direct_ms = mdist.max_over_ranks(ev[0][0].elapsed_time(ev[-1][2]), dev) / steps
+    direct_fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    direct_bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+
+    # ---- the same steps replayed from CUDA graphs (one forward and one backward graph per input set): the eight
+    # launches of a step reach the GPU without the host-side gaps between dependent launches (~18 us per forward
+    # when launched one by one from the host).  This is the headline `value`.
+    cap = torch.cuda.Stream(dev)
+    cap.wait_stream(torch.cuda.current_stream(dev))
+    cap_stream = ctypes.c_void_p(cap.cuda_stream)
+    graphs = []
+    with torch.cuda.stream(cap):
+        for k in range(nsets):
+            a, c = X1[k], X2[k]
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=cap):
+                _lib.check(L.mvp_chamfer_forward(b, n, m, P(a), P(c), P(d1), P(d2), P(i1), P(i2), P(ws), ws.numel(),
+                                                 cap_stream), "mvp_chamfer_forward (capture)")
+            with torch.cuda.graph(gb, stream=cap):
+                _lib.check(L.mvp_chamfer_backward(b, n, m, P(a), P(c), P(G1), P(G2), P(i1), P(i2), P(gx1), P(gx2),
+                                                  cap_stream), "mvp_chamfer_backward (capture)")
+            graphs.append((gf, gb))
+    torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count() - launches0 - launches) // nsets  # counted once, at capture
+    for k in range(warm):
+        gf, gb = graphs[k % nsets]
+        gf.replay(), gb.replay()
+    torch.cuda.synchronize()
+    gev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    mdist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk2:
+        for k in range(steps):
+            gf, gb = graphs[(warm + k) % nsets]
+            gev[k][0].record()
+            gf.replay()
+            gev[k][1].record()
+            gb.replay()
+            gev[k][2].record()
+        torch.cuda.synchronize()
+    mdist.barrier()
+    clk.samples += clk2.samples
+    clk.reasons |= clk2.reasons
+    total_ms = mdist.max_over_ranks(gev[0][0].elapsed_time(gev[-1][2]), dev)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in gev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in gev) / steps
     ms_per_step = total_ms / steps
     value = world * pairs / (ms_per_step * 1e-3)
+    launches = launches_per_step * steps
 
     # ---- the same step with the brute-force forward (every pair evaluated), for the FP32-issue roofline
     bsteps = max(3, min(steps, 20))
@@ -424,7 +467,9 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD.replace("B=32", f"B={b}").replace("16384", str(n)), "per_gpu_batch": b,
                    "global_batch": b * world, "n": n, "m": m, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": f"inputs rotate through {nsets} sets = {nsets * set_bytes >> 20} MiB > 126 MiB L2"},
+                   "l2": f"inputs rotate through {nsets} sets = {nsets * set_bytes >> 20} MiB > 126 MiB L2",
+                   "launch": "each step = one forward + one backward CUDA graph replayed on the input set of the step "
+                             "(direct_launch: the same steps launched kernel by kernel from the host)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "serial_ms_per_step": e2e_serial_ms,
                 "api": "metrics.cd()(xyz1, xyz2) + autograd backward, pinned host in/out; copy-in / compute / copy-out "
@@ -432,9 +477,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "algorithm": "forward = exact grid-pruned nearest neighbour (chamfer_grid.cu), outputs bit-identical to brute "
                      "force; point-pairs counts B*N*M per step as the reference's metric does, not pairs evaluated",
-        "kernel_ms": {"chamfer_forward": fwd_ms, "chamfer_backward": bwd_ms, "wall_ms_per_step": 1e3 * t_wall / steps},
+        "kernel_ms": {"chamfer_forward": fwd_ms, "chamfer_backward": bwd_ms},
+        "direct_launch": {"ms_per_step": direct_ms, "value": world * pairs / (direct_ms * 1e-3), "chamfer_forward_ms": direct_fwd_ms,
+                          "chamfer_backward_ms": direct_bwd_ms, "wall_ms_per_step": 1e3 * t_wall / steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": TRAFFIC_BYTES if (b, n, m) == (B, N, M) else None, "kernel": "chamfer forward, both directions (chamfer_grid_build_kernel + "
+                     "traffic": TRAFFIC_BYTES if (b, n, m) == (B, N, M) else None, "kernel": "chamfer forward, both directions (chamfer_grid_build2_kernel + "
                      "chamfer_grid_query_kernel + plan + 3 hand-over kernels that leave at once; shares in "
                      "profiles/r1_launches_bench.md)", "algorithmic_bytes": fwd_bytes, "peak_source": peak_src,
                      "note": "latency/issue bound, not HBM bound: ~1M independent searches of ~30 candidates each; "

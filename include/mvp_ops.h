@@ -184,7 +184,7 @@ int mvp_knn_points(int b, int n, int m, int k, const float *queries, const float
 
 /* ---------------------------------------------------------------------------------------------
  * The backward scatters again, with a caller-provided workspace (same results, faster): the index is
- * transposed once per cloud into the workspace (start[rows + 1] | perm[entries]) and every gradient
+ * transposed once per cloud into the workspace (start[rows + 1] | perm[entries] | weights permuted alike) and every gradient
  * element is then SUMMED by one thread and written once — no floating-point atomics, no memset.
  *   rows    = destination columns per channel (n of gather / group, m of three_interpolate)
  *   entries = index entries per cloud (npoints, npoints*nsample, 3*n of three_interpolate)

@@ -313,7 +313,8 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
   const long long total = (long long)b * (n + m);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
   auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (n % 4 == 0 && m % 4 == 0 && al16(xyz1) && al16(xyz2) && al16(graddist1) && al16(graddist2) && al16(idx1) &&
+  // four points per thread need enough points to fill the machine: below ~512k the one-point kernels are faster
+  if (total >= (1 << 19) && n % 4 == 0 && m % 4 == 0 && al16(xyz1) && al16(xyz2) && al16(graddist1) && al16(graddist2) && al16(idx1) &&
       al16(idx2) && al16(gradxyz1) && al16(gradxyz2)) {
     const int grid4 = (int)std::min<long long>((total / 4 + 255) / 256, (long long)kNumSMs * 16);
     chamfer_grad4_kernel<false><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,

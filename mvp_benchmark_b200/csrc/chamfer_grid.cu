@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "grid.cuh"
@@ -46,6 +47,11 @@ constexpr int kGridQThreads = MVP_GRID_QTHREADS;  // query CTA
 #ifndef MVP_GRID_BUDGET
 #define MVP_GRID_BUDGET 512          // candidate evaluations per query before it gives up
 #endif
+
+#ifndef MVP_GRID_SCAN_UNROLL
+#define MVP_GRID_SCAN_UNROLL 2       // candidate loop of the query kernel (1: 0.144, 2: 0.137, 4: 0.143 ms forward at the headline size)
+#endif
+constexpr int kScanUnroll = MVP_GRID_SCAN_UNROLL;
 
 struct GridWs {  // carved out of the caller's workspace by grid_plan()
   GridHdr *hdr;        // [2][b]
@@ -288,8 +294,8 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
 #else
 #define MVP_B2_STAMP(k)
 #endif
-constexpr int kBuild2Per = (kGridRankPts / MVP_GRID_PPC + kGridThreads - 1) / kGridThreads;  // cells per thread (8)
-static_assert(kGridRankPts / MVP_GRID_PPC <= kGridMaxCells, "cap of the cluster build");
+constexpr int kBuild2MinPts = 6144;  // measured (tools/grid_sizes.py): at 3072 points one CTA per side is 7-9 us faster, at 16384 10-14 us slower
+constexpr int kBuild2Per = 8;  // cells per thread: clouds whose grids have up to 8192 cells (16384 points at 2 per cell)
 
 __global__ void __cluster_dims__(1, 1, 2) __launch_bounds__(kGridThreads, 1)
 chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
@@ -534,11 +540,16 @@ static int grid_build_launch(int b, int n, int m, const float *xyz1, const float
                                          (int)(sizeof(int) * (kGridMaxCells + 8 + kGridRankPts)));
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(chamfer_grid_build2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(int) * (kGridRankPts / MVP_GRID_PPC + 8 + kGridRankPts)));
+                               (int)(sizeof(int) * (kBuild2Per * kGridThreads + 8 + kGridRankPts)));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (std::max(n, m) <= kGridRankPts && std::max(W.cap[0], W.cap[1]) <= kBuild2Per * kGridThreads)
+  static const int min_pts = [] {  // tuning aid: clouds below MVP_GRID_BUILD2_MIN points use one CTA per side
+    const char *e = getenv("MVP_GRID_BUILD2_MIN");
+    return e ? atoi(e) : kBuild2MinPts;
+  }();
+  if (std::max(n, m) >= min_pts && std::max(n, m) <= kGridRankPts &&
+      std::max(W.cap[0], W.cap[1]) <= kBuild2Per * kGridThreads)
     chamfer_grid_build2_kernel<<<dim3(b, 2, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
   else
     chamfer_grid_build_kernel<<<dim3(b, 2), kGridThreads, smem, s>>>(b, n, m, xyz1, xyz2, W);
@@ -639,6 +650,7 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
         return;
       }
       budget -= e - a;
+#pragma unroll(K == 1 ? kScanUnroll : 1)  // longer ordered lists: the duplicated insertion code costs more than it saves
       for (int i = a; i < e; i++) {
         const float4 q = __ldg(T + i);
         const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
@@ -689,8 +701,12 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
           if (lbyz * s2 > best) continue;  // also true for rows outside the grid (inf) once best is finite ...
           const int yy = cy + oy[t], zz = cz + oz[t];
           if (yy < 0 || yy >= gy || zz < 0 || zz >= gz) continue;  // ... and this covers best == inf
+#ifdef MVP_GRID_NOXCLIP
+          const int x0 = xlo, x1 = xhi;
+#else
           const int x0 = (gxs[0] + lbyz) * s2 > best ? cx : xlo;
           const int x1 = (gxs[2] + lbyz) * s2 > best ? cx : xhi;
+#endif
           const int base = (zz * gy + yy) * gx;
           scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
           if (budget < 0) break;

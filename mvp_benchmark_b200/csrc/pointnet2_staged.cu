@@ -207,11 +207,15 @@ three_interpolate_grad_staged_kernel(int c, int n, int m, int G, const float *__
 constexpr int kCsrThreads = 1024;
 constexpr int kCsrMaxRows = 48 * 1024;  // start[] lives in shared memory during the build (192 KB)
 
-static size_t csr_cloud_ints(int rows, int entries) { return ((size_t)rows + 1 + entries + 3) & ~(size_t)3; }
+// per cloud: start[rows + 1] | perm[entries] (the gathered column of every entry, in destination order) |
+// wperm[entries] (three_interpolate: the entry's weight, permuted alike — read coalesced by every channel group
+// instead of gathered 4 bytes per 32-byte sector from weight[] each time)
+static size_t csr_cloud_ints(int rows, int entries) { return ((size_t)rows + 1 + 2 * (size_t)entries + 3) & ~(size_t)3; }
 
 // grid (clouds).  idx: `entries` destinations per cloud (entry e of gather: column e; of interpolate: (target e/3, k = e%3)).
 __global__ void __launch_bounds__(kCsrThreads, 1)
-scatter_csr_build_kernel(int rows, int entries, size_t cloud_ints, const int *__restrict__ idx, int *__restrict__ ws) {
+scatter_csr_build_kernel(int rows, int entries, size_t cloud_ints, const int *__restrict__ idx,
+                         const float *__restrict__ weight, int *__restrict__ ws) {
   extern __shared__ int start[];  // rows + 1
   __shared__ int s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,7 +256,17 @@ scatter_csr_build_kernel(int rows, int entries, size_t cloud_ints, const int *__
     run += cnt;
   }
   __syncthreads();
-  for (int e = tid; e < entries; e += kCsrThreads) perm[atomicAdd(&start[__ldg(id + e) + 1], 1)] = e;
+  if (weight) {  // three_interpolate: entry e = 3 * target + k
+    const float *w = weight + (size_t)blockIdx.x * entries;
+    float *wperm = reinterpret_cast<float *>(perm + entries);
+    for (int e = tid; e < entries; e += kCsrThreads) {
+      const int slot = atomicAdd(&start[__ldg(id + e) + 1], 1);
+      perm[slot] = e / 3;
+      wperm[slot] = __ldg(w + e);
+    }
+  } else {
+    for (int e = tid; e < entries; e += kCsrThreads) perm[atomicAdd(&start[__ldg(id + e) + 1], 1)] = e;
+  }
   __syncthreads();
   for (int j = tid; j <= rows; j += kCsrThreads) out_start[j] = start[j];
 }
@@ -262,13 +276,13 @@ scatter_csr_build_kernel(int rows, int entries, size_t cloud_ints, const int *__
 template <bool kInterp, int G>
 __global__ void __launch_bounds__(kStThreads)
 scatter_csr_apply_kernel(int c, int rows, int cols, size_t cloud_ints, const float *__restrict__ grad_out,
-                         const float *__restrict__ weight, const int *__restrict__ ws, float *__restrict__ grad_points) {
+                         const int *__restrict__ ws, float *__restrict__ grad_points) {
   extern __shared__ __align__(128) float rowbuf[];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
   stage_rows(rowbuf, grad_out + ((size_t)b * c + c0) * cols, gcount * cols, &bar);
   const int *start = ws + (size_t)b * cloud_ints, *perm = start + rows + 1;
-  const float *w = kInterp ? weight + (size_t)b * cols * 3 : nullptr;
+  const float *wperm = reinterpret_cast<const float *>(perm + (kInterp ? 3 * (size_t)cols : (size_t)cols));
   float *gp = grad_points + ((size_t)b * c + c0) * rows;
   for (int j = threadIdx.x; j < rows; j += kStThreads) {
     float acc[G];
@@ -276,9 +290,8 @@ scatter_csr_apply_kernel(int c, int rows, int cols, size_t cloud_ints, const flo
     for (int g = 0; g < G; g++) acc[g] = 0.f;
     const int q1 = __ldg(start + j + 1);
     for (int q = __ldg(start + j); q < q1; q++) {
-      const int e = __ldg(perm + q);
-      const int p = kInterp ? e / 3 : e;
-      const float wt = kInterp ? __ldg(w + e) : 1.f;
+      const int p = __ldg(perm + q);
+      const float wt = kInterp ? __ldg(wperm + q) : 1.f;
 #pragma unroll
       for (int g = 0; g < G; g++)
         if (g < gcount) {
@@ -317,7 +330,8 @@ int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const floa
     if (e != cudaSuccess) return (int)e;
     granted = sizeof(int) * (kCsrMaxRows + 1);
   }
-  scatter_csr_build_kernel<<<b, kCsrThreads, bsmem, s>>>(rows, entries, cloud_ints, idx, (int *)workspace);
+  scatter_csr_build_kernel<<<b, kCsrThreads, bsmem, s>>>(rows, entries, cloud_ints, idx, interp ? weight : nullptr,
+                                                         (int *)workspace);
   // channels per CTA: as many as keep the staged rows within ~64 KB (three CTAs per SM)
   int G = 4;  // one of the instantiated values 4, 2, 1
   while (G > 1 && ((size_t)G * cols * 4 > kStRowBytes || G > c)) G >>= 1;
@@ -328,7 +342,7 @@ int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const floa
   do {                                                                                                              \
     rc = set_smem<TAG>(scatter_csr_apply_kernel<I, GG>, smem);                                                      \
     if (!rc)                                                                                                        \
-      scatter_csr_apply_kernel<I, GG><<<grid, kStThreads, smem, s>>>(c, rows, cols, cloud_ints, grad_out, weight,    \
+      scatter_csr_apply_kernel<I, GG><<<grid, kStThreads, smem, s>>>(c, rows, cols, cloud_ints, grad_out,            \
                                                                       (const int *)workspace, grad_points);         \
   } while (0)
   if (interp) {

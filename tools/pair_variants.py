@@ -16,11 +16,14 @@ OUT = os.path.join(ROOT, "gpurun_build")
 CSRC = os.path.join(ROOT, "mvp_benchmark_b200", "csrc")
 GRID_VARIANTS = {
     "base": [],
-    "noplan": ["-DMVP_GRID_NOPLAN"],
-    "nobail": ["-DMVP_GRID_NOBAIL"],
-    "noplan_nobail": ["-DMVP_GRID_NOPLAN", "-DMVP_GRID_NOBAIL"],
-    "budget1536": ["-DMVP_GRID_BUDGET=1536"],
     "q256": ["-DMVP_GRID_QTHREADS=256"],
+    "q64": ["-DMVP_GRID_QTHREADS=64"],
+    "ppc1": ["-DMVP_GRID_PPC=1"],
+    "ppc3": ["-DMVP_GRID_PPC=3"],
+    "ppc4": ["-DMVP_GRID_PPC=4"],
+    "noxclip": ["-DMVP_GRID_NOXCLIP"],
+    "unroll2": ["-DMVP_GRID_SCAN_UNROLL=2"],
+    "unroll4": ["-DMVP_GRID_SCAN_UNROLL=4"],
 }
 EMD_VARIANTS = {
     "base": [],
@@ -56,7 +59,7 @@ def build(which):
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
                "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-shared", "-Xptxas", "-v"] + flags + \
               [os.path.join(CSRC, f) for f in (("capi.cu", "emd.cu") if which == "emd" else ("capi.cu", "fps.cu") if which == "fps" else
-                                               ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu"))] + ["-o", lib]
+                                               ("capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu", "pointnet2.cu", "pointnet2_staged.cu"))] + ["-o", lib]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             print(name, "FAILED\n", r.stderr[-2000:])
