@@ -14,8 +14,10 @@
 // position on equality with strides T/2..1 (:17-23), so among equal maxima the winner is the point with
 // the smallest  key(k) = (bitrev_T(k mod T), k div T).  We reduce (distance, key) with max-then-min.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "grid.cuh"
 
 #ifndef MVP_FPS_PMAX
 #define MVP_FPS_PMAX 8  // tuning knob (tools/pair_variants.py): points per thread before more warps are used
@@ -213,6 +215,209 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
   }
 }
 
+// ---- spatially sorted variant (xyz input, clouds of up to 8192 points) ----------------------------------------------------
+// Same picks, bit for bit; what changes is how much of the cloud a pick touches.  The CTA first sorts its cloud by the
+// cells of a uniform grid (about P points per cell, shared-memory counting sort), so the P points a thread owns are
+// neighbours in space and fit a small box.  td[k] = min(td[k], d(k, new)) cannot change when the new point is further
+// from the thread's box than the largest td inside it, so such a thread keeps its cached (max, key) and a warp without
+// any affected lane skips the update, both `redux` and the key selection.  After the first few dozen picks only the
+// neighbourhood of the new point is affected — one or two warps of eight.  The skip test is conservative: box distance
+// (monotone in every rounding step of the distance the update would compute) scaled by (1 - 1e-5); NaN compares false,
+// i.e. "update".  Tie order: keys are those of the ORIGINAL indices, so ownership of points by threads is irrelevant.
+template <int TB, int P>
+__global__ void __launch_bounds__(TB)
+fps_sorted_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
+                  int *__restrict__ idxs) {
+  static_assert(P % 2 == 0, "points are processed in packed pairs");
+  extern __shared__ __align__(16) float4 s_pts[];   // [n] by original index | order[n] | hist[cap]
+  __shared__ float s_red[6][32];
+  __shared__ int s_fin[32], s_warp[32];
+  __shared__ GridHdr s_hdr;
+  __shared__ int s_val[2][32];
+  __shared__ uint32_t s_key[2][32];
+  int *s_order = reinterpret_cast<int *>(s_pts + n);
+  int *s_hist = s_order + n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *dataset = data + (size_t)blockIdx.x * n * 3;
+  idxs += (size_t)blockIdx.x * m;
+  const float inf = __int_as_float(0x7f800000);
+
+  // ---- the cloud into shared memory; bounding box
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  int fin = 1;
+  for (int k = tid; k < n; k += TB) {
+    const float x = __ldg(dataset + k * 3 + 0), y = __ldg(dataset + k * 3 + 1), z = __ldg(dataset + k * 3 + 2);
+    s_pts[k] = make_float4(x, y, z, 0.f);
+    lo[0] = fminf(lo[0], x), lo[1] = fminf(lo[1], y), lo[2] = fminf(lo[2], z);
+    hi[0] = fmaxf(hi[0], x), hi[1] = fmaxf(hi[1], y), hi[2] = fmaxf(hi[2], z);
+    fin &= (fabsf(x) <= 3.0e38f && fabsf(y) <= 3.0e38f && fabsf(z) <= 3.0e38f) ? 1 : 0;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+    fin &= __shfl_xor_sync(0xffffffffu, fin, off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) s_red[a][warp] = lo[a], s_red[3 + a][warp] = hi[a];
+    s_fin[warp] = fin;
+  }
+  if (warp == 0) {
+    s_val[0][lane] = s_val[1][lane] = (int)0x80000000;
+    s_key[0][lane] = s_key[1][lane] = 0xffffffffu;
+  }
+  __syncthreads();
+  const int cap = max(8, n / P);  // about P points per cell: a thread's chunk of the sorted order is one cell's worth
+  if (tid == 0) {
+    for (int w = 1; w < TB / 32; w++) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) lo[a] = fminf(lo[a], s_red[a][w]), hi[a] = fmaxf(hi[a], s_red[3 + a][w]);
+      fin &= s_fin[w];
+    }
+    s_hdr = grid_header(lo, hi, fin, cap);
+  }
+  __syncthreads();
+  const GridHdr h = s_hdr;
+  const int ncell = h.ncell;
+  for (int c = tid; c < ncell; c += TB) s_hist[c] = 0;
+  __syncthreads();
+  auto cell_of = [&](const float4 &p) {
+    if (!h.valid) return 0;
+    const int cx = cell_coord((p.x - h.lo[0]) * h.inv_s, h.g[0]);
+    const int cy = cell_coord((p.y - h.lo[1]) * h.inv_s, h.g[1]);
+    const int cz = cell_coord((p.z - h.lo[2]) * h.inv_s, h.g[2]);
+    return (cz * h.g[1] + cy) * h.g[0] + cx;
+  };
+  for (int k = tid; k < n; k += TB) atomicAdd(&s_hist[cell_of(s_pts[k])], 1);
+  __syncthreads();
+  {  // exclusive scan of the cell counts -> fill cursors
+    const int per = (ncell + TB - 1) / TB;
+    const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
+    int sum = 0;
+    for (int c = c0; c < c1; c++) sum += s_hist[c];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = lane < TB / 32 ? s_warp[lane] : 0;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += u;
+      }
+      s_warp[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+    for (int c = c0; c < c1; c++) {
+      const int cnt = s_hist[c];
+      s_hist[c] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += TB) s_order[atomicAdd(&s_hist[cell_of(s_pts[k])], 1)] = k;
+  __syncthreads();
+
+  // ---- this thread's P points: sorted positions [tid * P, tid * P + P)
+  fps_u64 PX[P / 2], PY[P / 2], PZ[P / 2];
+  float td[P];
+  uint32_t pkey[P];
+  float blo[3] = {inf, inf, inf}, bhi[3] = {-inf, -inf, -inf};
+  uint32_t tkey = 0xffffffffu;
+#pragma unroll
+  for (int hh = 0; hh < P / 2; hh++) {
+    float x[2] = {0.f, 0.f}, y[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = 2 * hh + e, pos = tid * P + i;
+      if (pos < n) {
+        const int k = s_order[pos];
+        const float4 p = s_pts[k];
+        x[e] = p.x, y[e] = p.y, z[e] = p.z;
+        blo[0] = fminf(blo[0], p.x), blo[1] = fminf(blo[1], p.y), blo[2] = fminf(blo[2], p.z);
+        bhi[0] = fmaxf(bhi[0], p.x), bhi[1] = fmaxf(bhi[1], p.y), bhi[2] = fmaxf(bhi[2], p.z);
+        td[i] = 1e10f;  // furthest_point_sample.py:30
+        pkey[i] = fps_key(k, log2T);
+        tkey = min(tkey, pkey[i]);
+      } else {
+        td[i] = -1.f;  // never selected
+        pkey[i] = 0xffffffffu;
+      }
+    }
+    PX[hh] = fps_pack2(x[0], x[1]);
+    PY[hh] = fps_pack2(y[0], y[1]);
+    PZ[hh] = fps_pack2(z[0], z[1]);
+  }
+  float tmax = tid * P < n ? 1e10f : -1.f;  // largest running minimum of this thread's points, tkey: its key
+  int wbits = 0;
+  uint32_t wkey = 0xffffffffu;
+  int old = 0;
+  if (tid == 0) idxs[0] = 0;
+
+  for (int j = 1; j < m; j++) {
+    const float4 o = s_pts[old];
+    const float ex = fmaxf(fmaxf(blo[0] - o.x, o.x - bhi[0]), 0.f);
+    const float ey = fmaxf(fmaxf(blo[1] - o.y, o.y - bhi[1]), 0.f);
+    const float ez = fmaxf(fmaxf(blo[2] - o.z, o.z - bhi[2]), 0.f);
+    const float lb2 = sqdist(ex, ey, ez) * (1.f - 1e-5f);
+    const bool affected = !(lb2 > tmax);  // NaN anywhere -> update
+    if (__any_sync(0xffffffffu, affected) || j == 1) {
+      if (affected) {
+        const fps_u64 qx = fps_pack2(o.x, o.x), qy = fps_pack2(o.y, o.y), qz = fps_pack2(o.z, o.z);
+        float vmax = -1.f;
+#pragma unroll
+        for (int hh = 0; hh < P / 2; hh++) {
+          float d0, d1;
+          fps_unpack2(fps_dist2(PX[hh], PY[hh], PZ[hh], qx, qy, qz), d0, d1);  // point - old (:65-66)
+          td[2 * hh] = fminf(d0, td[2 * hh]);
+          td[2 * hh + 1] = fminf(d1, td[2 * hh + 1]);
+          vmax = fps_max3(vmax, td[2 * hh], td[2 * hh + 1]);
+        }
+        uint32_t key = 0xffffffffu;
+        const int vb = __float_as_int(vmax);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+          if (__float_as_int(td[i]) == vb) key = min(key, pkey[i]);  // padding (td = -1, key all ones) changes nothing
+        tmax = vmax;
+        tkey = key;
+      }
+      const int vbits = __float_as_int(tmax);
+      wbits = redux_max_s32(vbits);
+      wkey = redux_min_u32(vbits == wbits ? tkey : 0xffffffffu);
+    }
+    const int buf = j & 1;
+    if (lane == 0) {
+      s_val[buf][warp] = wbits;
+      s_key[buf][warp] = wkey;
+    }
+    __syncthreads();
+    const int v = s_val[buf][lane];  // slots >= TB / 32 hold the sentinel
+    const uint32_t kk = s_key[buf][lane];
+    const int bv = redux_max_s32(v);
+    const uint32_t bk = redux_min_u32(v == bv ? kk : 0xffffffffu);
+    old = fps_unkey(bk, log2T);
+    if (tid == 0) idxs[j] = old;
+  }
+  if (temp != nullptr) {
+    temp += (size_t)blockIdx.x * n;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int pos = tid * P + i;
+      if (pos < n) temp[s_order[pos]] = td[i];
+    }
+  }
+}
+
 // Fallback for clouds too large for registers (n > 32768): running minima in global `temp`.
 template <bool WITH_DIST>
 __global__ void __launch_bounds__(1024)
@@ -280,9 +485,35 @@ static int ref_block_size(int work_size) {
   return t;
 }
 
+static bool fps_use_sorted() {  // MVP_FPS_SORTED=0: the unsorted kernel (A/B timing)
+  static const bool on = [] {
+    const char *e = getenv("MVP_FPS_SORTED");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <bool WD, int TB, int P>
 static void fps_launch_one(int b, int n, int m, int log2T, const float *data, float *temp, int *idx,
                            cudaStream_t s) {
+  if constexpr (!WD && TB * P <= 8192) {
+    // measured (tools/fps_sizes.py): 457 against 601 ns per pick at n = 8192, but 318 against 242 at n = 2048 — with
+    // 8 points per thread the boxes are a sizeable part of a small cloud, nearly every warp keeps an affected lane,
+    // and the test only lengthens the dependent chain of a pick
+    if (fps_use_sorted() && n > 4096) {
+      const size_t smem = (size_t)n * (sizeof(float4) + sizeof(int)) + sizeof(int) * (size_t)std::max(8, n / P);
+      static size_t granted = 40 * 1024;
+      if (smem > granted) {
+        const size_t want = (size_t)TB * P * (sizeof(float4) + sizeof(int)) + sizeof(int) * (size_t)std::max(8, TB);
+        if (cudaFuncSetAttribute(fps_sorted_kernel<TB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) !=
+            cudaSuccess)
+          return;  // launch_status() reports it
+        granted = want;
+      }
+      fps_sorted_kernel<TB, P><<<b, TB, smem, s>>>(n, m, log2T, data, temp, idx);
+      return;
+    }
+  }
   // the shared-memory copy of the cloud: 16 B per point, for clouds up to 8192 points (128 KB)
   constexpr bool kSmem = !WD && TB * P <= 8192;
   const size_t smem = kSmem ? (size_t)n * sizeof(float4) : 0;
