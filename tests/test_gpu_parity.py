@@ -267,7 +267,10 @@ def test_emd_input_errors(gpu):
 FPS_CASES = [("uniform", 32, 2048, 2048), ("uniform", 4, 3072, 1536), ("uniform", 4, 1536, 768), ("uniform", 4, 768, 384),
              ("uniform", 4, 3072, 2048), ("lattice", 2, 2048, 2048), ("duplicates", 2, 1000, 1000), ("sphere", 2, 16384, 256),
              ("uniform", 2, 1, 1), ("uniform", 2, 5, 9), ("lattice", 2, 100, 100), ("uniform", 1, 40000, 64),
-             ("duplicates", 1, 4096, 4096), ("uniform", 2, 6000, 50), ("uniform", 2, 20000, 40)]
+             ("duplicates", 1, 4096, 4096), ("uniform", 2, 6000, 50), ("uniform", 2, 20000, 40),
+             # above 4096 points: the spatially sorted kernel (box skip test) — ties, dense cells, degenerate grids
+             ("lattice", 2, 8192, 600), ("duplicates", 2, 5000, 700), ("clustered", 2, 8000, 300), ("planar", 2, 6144, 200),
+             ("constant", 1, 5000, 20), ("tiny", 1, 5000, 50), ("outliers", 2, 7000, 400), ("uniform", 3, 8192, 2048)]
 
 
 @pytest.mark.parametrize("kind,b,n,m", FPS_CASES)
