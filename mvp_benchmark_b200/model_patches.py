@@ -1,5 +1,6 @@
 """Opt-in replacements for the k-nearest-neighbour helpers of the reference's completion models
-(completion/model_utils.py:242-271) — SURVEY.md §8(f) row 1.  They are CALLER code, outside the drop-in
+(completion/model_utils.py:242-271) — SURVEY.md §8(f) row 1 — and for its neighbour-feature gather
+(get_edge_features, :113-124; §8(f) row 2: the grouping around the kNN).  They are CALLER code, outside the drop-in
 boundary, so nothing here is applied by default:
 
     import model_utils, models.vrcnet
@@ -46,12 +47,28 @@ def knn_point(pk, point_input, point_output):
     return _neg_sqdist(point_output, point_input, idx), idx.long()
 
 
+def get_edge_features(x, idx):
+    """model_utils.py:113-124: x (B, C, 1, N), idx (B, N, k) -> the neighbours' features (B, C, k, N).  The original
+    transposes x, gathers rows with advanced indexing and returns a permuted (non-contiguous) view that the next
+    convolution has to copy; this is the same gather as ONE grouping_operation call (the reference's own operator,
+    utils/mm3d_pn2/ops/group_points/group_points.py:166-218) on the transposed index, contiguous in the layout the
+    convolution wants, with the operator's scatter as backward.  Same values bit for bit in the forward pass."""
+    if (x.dim() != 4 or x.size(2) != 1 or not x.is_cuda or x.dtype != torch.float32 or idx.dim() != 3
+            or idx.size(1) != x.size(3)):
+        return _ORIGINAL["get_edge_features"](x, idx)
+    import mm3d_pn2
+    return mm3d_pn2.grouping_operation(x.squeeze(2).contiguous(), idx.transpose(1, 2).int().contiguous())
+
+
 def apply(*modules):
-    """Rebind knn / knn_point / knn_point_all in the given (already imported) modules.  Returns the number of
-    names replaced."""
+    """Rebind knn / knn_point / knn_point_all / get_edge_features in the given (already imported) modules.  Returns
+    the number of names replaced."""
+    from . import install
+    install()  # `mm3d_pn2` must resolve to this repository's package
     count = 0
     for mod in modules:
-        for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point)):
+        for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
+                         ("get_edge_features", get_edge_features)):
             cur = getattr(mod, name, None)
             if cur is None or cur is fn:
                 continue

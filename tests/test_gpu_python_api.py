@@ -210,7 +210,7 @@ def test_model_patches_knn_and_knn_point(cuda, cpu):
         return torch.zeros(x.size(0), x.size(2), k, dtype=torch.long, device=x.device)
 
     fake = types.SimpleNamespace(knn=orig_knn, knn_point=_torch_knn_point, knn_point_all=_torch_knn_point)
-    assert mp.apply(fake) == 3 and mp.apply(fake) == 0
+    assert mp.apply(fake) == 3 and mp.apply(fake) == 0   # (this stand-in module has no get_edge_features)
     B, N, M = 4, 1536, 768
     cloud = T(_data.uniform(B, N, 11), cuda)
     sub = cloud[:, :M].contiguous().requires_grad_(True)
@@ -228,3 +228,31 @@ def test_model_patches_knn_and_knn_point(cuda, cpu):
     feat = torch.randn(2, 64, 100, device=cuda)            # feature-space kNN: not ours
     fake.knn(feat, 5)
     assert calls == ["knn"]
+
+
+def test_model_patches_get_edge_features(cuda):
+    """The neighbour-feature gather of SA_module (model_utils.py:113-124) as one grouping_operation: same values bit
+    for bit, contiguous (B, C, k, N), gradients equal to the advanced-indexing original's up to summation order."""
+    import types
+    from mvp_benchmark_b200 import model_patches as mp
+
+    def original(x, idx):                                  # model_utils.py:113-124, restated
+        batch_size, num_points, k = idx.size()
+        idx = (idx + torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points).view(-1)
+        x = x.squeeze(2)
+        num_dims = x.size(1)
+        x = x.transpose(2, 1).contiguous()
+        feature = x.view(batch_size * num_points, -1)[idx, :]
+        return feature.view(batch_size, num_points, k, num_dims).permute(0, 3, 2, 1)
+
+    fake = types.SimpleNamespace(get_edge_features=original)
+    assert mp.apply(fake) == 1
+    B, C, N, k = 3, 37, 1536, 16
+    x0 = torch.randn(B, C, 1, N, device=cuda)
+    idx = torch.randint(0, N, (B, N, k), device=cuda)
+    a, b = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    got, want = fake.get_edge_features(a, idx), original(b, idx)
+    assert got.shape == (B, C, k, N) and got.is_contiguous() and torch.equal(got, want)
+    g = torch.randn_like(got)
+    got.backward(g), want.backward(g)
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5)
