@@ -437,14 +437,20 @@ def run_ours(args):
         e2e_pipelined(k)
     torch.cuda.synchronize()
     mdist.barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(s_in)
-    for k in range(steps):
-        e2e_pipelined(warm + k)
-    p1.record(s_out)  # s_out's last copy depends on the last compute, which depends on the last copy-in
-    torch.cuda.synchronize()
-    mdist.barrier()
-    e2e_ms = mdist.max_over_ranks(p0.elapsed_time(p1), dev) / steps
+    # K steps, three times over: host->device throughput of a virtualised host varies between runs by 2x and more
+    # (tools/pcie_probe.py: 11-43 GB/s for the same pinned buffer), device->host does not; the median run is reported,
+    # all three are listed.
+    e2e_runs = []
+    for rep in range(3):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(s_in)
+        for k in range(steps):
+            e2e_pipelined(warm + k)
+        p1.record(s_out)  # s_out's last copy depends on the last compute, which depends on the last copy-in
+        torch.cuda.synchronize()
+        mdist.barrier()
+        e2e_runs.append(mdist.max_over_ranks(p0.elapsed_time(p1), dev) / steps)
+    e2e_ms = sorted(e2e_runs)[1]
     e2e_value = world * pairs / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (Chamfer forward)
@@ -472,6 +478,7 @@ def run_ours(args):
                              "(direct_launch: the same steps launched kernel by kernel from the host)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "serial_ms_per_step": e2e_serial_ms,
+                "runs_ms_per_step": e2e_runs,
                 "api": "metrics.cd()(xyz1, xyz2) + autograd backward, pinned host in/out; copy-in / compute / copy-out "
                        "pipelined on three streams (serial_ms_per_step: the same on one stream)"},
         "gpu_launches": int(launches),

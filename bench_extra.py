@@ -153,6 +153,37 @@ def vrcnet_census(dev, g, have_ref):
     return res
 
 
+def model_steps():
+    """One training step of the reference's UNMODIFIED VRCNet (B = 32, cfgs/vrcnet.yaml) through tools/model_step.py:
+    on the reference's kernels, on ours, and on ours with the opt-in model patches.  Needs the models staged under
+    oracle/_ref/completion (oracle/build_ref.py, where /root/reference exists); returns None without them."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.isfile(os.path.join(root, "oracle", "_ref", "completion", "models", "vrcnet.py")):
+        return None
+    out = {"model": "vrcnet", "batch": 32, "step": "zero_grad + forward + backward + Adam (completion/train.py:122-142)"}
+    for tag, extra in (("ref_cuda_ms", ["--ops", "ref"]), ("ours_ms", ["--ops", "ours"]),
+                       ("ours_with_model_patches_ms", ["--ops", "ours", "--patch-knn"])):
+        if tag == "ref_cuda_ms" and not os.path.isfile(os.path.join(root, "oracle", "_ref", "libref_ops.so")):
+            continue
+        try:
+            p = subprocess.run([sys.executable, os.path.join(root, "tools", "model_step.py"), "--model", "vrcnet",
+                                "--steps", "6", "--warmup", "3", *extra], capture_output=True, text=True, timeout=300)
+            line = [l for l in p.stdout.splitlines() if l.startswith("MODEL_STEP ")]
+            out[tag] = json.loads(line[-1][len("MODEL_STEP "):])["ms_per_step"] if line else None
+        except Exception as e:  # secondary number
+            out[tag] = None
+            out["error"] = repr(e)
+    if out.get("ref_cuda_ms") and out.get("ours_ms"):
+        out["speedup_vs_ref_cuda"] = out["ref_cuda_ms"] / out["ours_ms"]
+        if out.get("ours_with_model_patches_ms"):
+            out["speedup_with_model_patches"] = out["ref_cuda_ms"] / out["ours_with_model_patches_ms"]
+    return out
+
+
 def run(dev, hbm_gbs=None):
     import json
     import os
@@ -312,6 +343,9 @@ def run(dev, hbm_gbs=None):
         e["speedup_vs_torch_formula"] = e["torch_matmul_topk_ms"] / e["ours_ms"]
         out["knn_points_" + tag] = e
     out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
+    steps = model_steps()
+    if steps is not None:
+        out["vrcnet_training_step"] = steps
     xyz, ctr = R(32, 2048, 3), R(32, 102, 3)
     entry("ball_query_32x2048_102centres_ns12", _time(lambda: mm.ball_query(0, 0.0774596669, 12, xyz, ctr)),
           _time(lambda: ref_cuda.ball_query(0, 0.0774596669, 12, xyz, ctr)) if have_ref else None, 32.0 * 102,
