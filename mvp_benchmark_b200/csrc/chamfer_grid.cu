@@ -7,10 +7,11 @@
 // is strictly greater than a distance already found.  What changes is the amount of work: B*N*M pair
 // evaluations become ~B*(N+M)*(a few dozen).
 //
-//   build   one CTA per (cloud, side): bounding box -> isotropic cell size with <= `cap` cells -> counting sort of
-//           the cloud by cell (shared-memory histogram, block scan, scatter) into a float4 array
-//           (x, y, z, original index) + a cell-start table.  x is the fastest-varying cell coordinate, so a run of
-//           cells along x is ONE contiguous range of the sorted array.
+//   build   per (cloud, side): bounding box -> isotropic cell size with <= `cap` cells -> counting sort of the cloud
+//           by cell (shared-memory histogram, block scan, scatter) into a float4 array (x, y, z, original index) +
+//           a cell-start table.  x is the fastest-varying cell coordinate, so a run of cells along x is ONE
+//           contiguous range of the sorted array.  One CTA (chamfer_grid_build_kernel), or a cluster of two CTAs
+//           meeting through distributed shared memory (chamfer_grid_build2_kernel) for clouds of 6144-16384 points.
 //   query   one thread per point, visited in the SORTED order of its own cloud (neighbouring threads look at
 //           neighbouring cells of the other cloud's grid).  Cubes of cells of growing radius r around the
 //           point's cell; rows of cells whose lower bound exceeds the best distance are skipped; the search
@@ -22,6 +23,9 @@
 //
 // Degenerate inputs (non-finite coordinates, zero or astronomically large extent) mark the grid invalid; all
 // queries against it go to the left-over list, i.e. the brute-force path and its semantics.
+//
+// The same build + query serve three_nn (K = 3) and the models' k-nearest-neighbour search (mvp_knn_points: an
+// ordered list of up to 32 neighbours per thread, exhaustive top-k kernel for what the grid does not finish).
 #include <cooperative_groups.h>
 
 #include <cstdio>

@@ -75,7 +75,9 @@ def test_chamfer_forward_vs_oracle(gpu, cpu, kind, b, n, m):
         _cases.eq(g, w, f"chamfer {kind} {b}x{n}x{m} {nm}")
 
 
-GRID_SHAPES = [(4, 2048, 2048), (2, 513, 1023), (2, 2048, 3072), (1, 5000, 777), (3, 600, 4097), (2, 8192, 8192)]
+GRID_SHAPES = [(4, 2048, 2048), (2, 513, 1023), (2, 2048, 3072), (1, 5000, 777), (3, 600, 4097), (2, 8192, 8192),
+               # the two-CTA cluster build (6144 <= max(n, m) <= 16384): odd sizes, very different sides, the PCN coarse shape
+               (1, 16384, 1024), (2, 7001, 513), (1, 6145, 12000)]
 
 
 @pytest.mark.parametrize("kind", ["uniform", "sphere", "duplicates", "lattice", "clustered", "planar", "outliers",
