@@ -34,3 +34,35 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_other_ranks_exit_quietly():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ("--gpus", "2"))
     assert out.strip() == ""
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use the cores it is allowed."""
+    d = json.loads(_run({"OMP_NUM_THREADS": "1"}).strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_committed_gpu_bench_lines_carry_the_contract():
+    """The B200 lines committed under profiles/ (what the round's numbers are quoted from): every key of the bench
+    contract, the roofline and cpu_baseline objects, clocks sampled during the timed region, and weak scaling of
+    `value` over the committed GPU counts."""
+    base = None
+    for n in (1, 2, 4, 8):
+        path = os.path.join(ROOT, "profiles", f"r1_bench_n{n}.json")
+        if not os.path.isfile(path):
+            continue
+        d = json.load(open(path))
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+            assert key in d, (n, key)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["dtype"] == "f32" and d["gpu_launches"] > 0
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            base = d["value"]
+            c = d["cpu_baseline"]
+            assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+        elif base:
+            assert d["value"] / (n * base) > 0.9, (n, d["value"], base)

@@ -84,3 +84,22 @@ def test_calc_square_dist_and_sampler_config(ops):
     assert len(s.samplers) == 2
     g = mm3d.GroupAll(use_xyz=True)(torch.rand(2, 6, 3), None, torch.rand(2, 5, 6))
     assert g.shape == (2, 8, 1, 6)
+
+
+def test_model_patches_fall_through_for_what_the_fused_ops_do_not_cover():
+    """Opt-in model patches: CPU tensors, feature-space kNN (C != 3) and k beyond the fused op's
+    range go to the ORIGINAL function of the patched module — the patches never compute on the CPU themselves."""
+    import types
+    import torch
+    from mvp_benchmark_b200 import model_patches as mp
+    seen = []
+    fake = types.SimpleNamespace(
+        knn=lambda x, k: seen.append(("knn", tuple(x.shape), k)) or "orig-knn",
+        knn_point=lambda pk, a, b: seen.append(("knn_point", pk)) or ("orig-d", "orig-i"),
+        get_edge_features=lambda x, idx: seen.append(("gef", tuple(x.shape))) or "orig-gef")
+    assert mp.apply(fake) == 3
+    assert fake.knn(torch.zeros(2, 3, 50), 4) == "orig-knn"                  # CPU tensor
+    assert fake.knn(torch.zeros(2, 64, 50), 4) == "orig-knn"                 # feature space
+    assert fake.knn_point(5, torch.zeros(2, 50, 3), torch.zeros(2, 10, 3)) == ("orig-d", "orig-i")
+    assert fake.get_edge_features(torch.zeros(2, 8, 1, 50), torch.zeros(2, 50, 4, dtype=torch.long)) == "orig-gef"
+    assert [s[0] for s in seen] == ["knn", "knn", "knn_point", "gef"]
