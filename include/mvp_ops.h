@@ -168,6 +168,18 @@ int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
             float *dist2, mvp_stream_t stream);
 
+/* SURVEY.md §8(f) row 3 — the loss epilogue the models compute from the Chamfer outputs with torch glue
+ * (completion/model_utils.py:67-72, calc_cd):  cd_p[b] = (mean_i sqrt(dist1[b,i]) + mean_j sqrt(dist2[b,j])) / 2,
+ * cd_t[b] = mean_i dist1[b,i] + mean_j dist2[b,j];  dist1 (b,n), dist2 (b,m) -> cd_p (b), cd_t (b).  fp32, fixed
+ * summation order (deterministic); within 1e-5 relative of torch's reductions.  The gradient entry point returns
+ * grad_dist1 (b,n), grad_dist2 (b,m) from the upstream gradients of cd_p and cd_t (b each):
+ * grad_cd_p / (4 n sqrt(d)) + grad_cd_t / n — infinite at d == 0, as torch's sqrt backward.  Opt-in
+ * (mvp_benchmark_b200.model_patches rebinds calc_cd). */
+int mvp_chamfer_loss(int b, int n, int m, const float *dist1, const float *dist2, float *cd_p, float *cd_t,
+                     mvp_stream_t stream);
+int mvp_chamfer_loss_grad(int b, int n, int m, const float *dist1, const float *dist2, const float *grad_cd_p,
+                          const float *grad_cd_t, float *grad_dist1, float *grad_dist2, mvp_stream_t stream);
+
 /* SURVEY.md §8(f) row 1 — the k-nearest-neighbour search the completion MODELS run in torch
  * (completion/model_utils.py:242-259 `knn` / `knn_point` / `knn_point_all`: a (B,N,M) matrix of
  * -|x|^2 + 2 x.y - |y|^2 by matmul, then torch.topk), as one fused exact search for 3-D points.

@@ -1,0 +1,95 @@
+// Loss epilogue of the Chamfer distance — SURVEY.md §8(f) row 3.
+//
+// The completion models turn the four outputs of the Chamfer operator into two numbers per cloud with torch glue
+// (completion/model_utils.py:67-77, calc_cd):
+//     cd_p = (sqrt(dist1).mean(1) + sqrt(dist2).mean(1)) / 2        cd_t = dist1.mean(1) + dist2.mean(1)
+// i.e. two sqrt kernels, four reductions and three elementwise kernels per call, four calls per VRCNet step.  Here:
+// one CTA per cloud sums sqrt(d) and d over both directions in one pass (fp32, fixed order: strided per-thread
+// partial sums, shuffle tree, 8 warp partials summed by thread 0 — deterministic, unlike a float atomic), and one
+// elementwise kernel produces both upstream gradients  d cd_p / d dist = 1 / (4 n sqrt(d)),  d cd_t / d dist = 1 / n
+// (infinite at d == 0, exactly like torch's sqrt backward).  Opt-in: mvp_benchmark_b200.model_patches rebinds calc_cd.
+#include "common.cuh"
+
+namespace mvp {
+
+constexpr int kLossThreads = 256;
+
+__global__ void __launch_bounds__(kLossThreads)
+chamfer_loss_kernel(int n, int m, const float *__restrict__ dist1, const float *__restrict__ dist2,
+                    float *__restrict__ cd_p, float *__restrict__ cd_t) {
+  __shared__ float s_part[4][kLossThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *d1 = dist1 + (size_t)b * n, *d2 = dist2 + (size_t)b * m;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // sum sqrt(d1), sum d1, sum sqrt(d2), sum d2
+  for (int i = tid; i < n; i += kLossThreads) {
+    const float d = __ldg(d1 + i);
+    acc[0] += __fsqrt_rn(d);
+    acc[1] += d;
+  }
+  for (int i = tid; i < m; i += kLossThreads) {
+    const float d = __ldg(d2 + i);
+    acc[2] += __fsqrt_rn(d);
+    acc[3] += d;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1)
+#pragma unroll
+    for (int a = 0; a < 4; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
+  if (lane == 0)
+#pragma unroll
+    for (int a = 0; a < 4; a++) s_part[a][warp] = acc[a];
+  __syncthreads();
+  if (tid == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < kLossThreads / 32; w++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) t[a] += s_part[a][w];
+    cd_p[b] = (t[0] / (float)n + t[2] / (float)m) / 2;
+    cd_t[b] = t[1] / (float)n + t[3] / (float)m;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+chamfer_loss_grad_kernel(int b, int n, int m, const float *__restrict__ dist1, const float *__restrict__ dist2,
+                         const float *__restrict__ g_p, const float *__restrict__ g_t, float *__restrict__ gd1,
+                         float *__restrict__ gd2) {
+  const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const bool first = i < total1;
+    const long long p = first ? i : i - total1;
+    const int cnt = first ? n : m;
+    const int cloud = (int)(p / cnt);
+    const float d = __ldg((first ? dist1 : dist2) + p);
+    // torch: mean backward (g / cnt), then sqrt backward (g / (2 sqrt(d))), after the "/ 2" of cd_p
+    const float gp = (__ldg(g_p + cloud) / 2) / (float)cnt;
+    const float gt = __ldg(g_t + cloud) / (float)cnt;
+    (first ? gd1 : gd2)[p] = gp / (2 * __fsqrt_rn(d)) + gt;
+  }
+}
+
+}  // namespace mvp
+
+using namespace mvp;
+
+MVP_API int mvp_chamfer_loss(int b, int n, int m, const float *dist1, const float *dist2, float *cd_p, float *cd_t,
+                             mvp_stream_t stream) {
+  if (b < 0 || n <= 0 || m <= 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0) return MVP_OK;
+  if (!dist1 || !dist2 || !cd_p || !cd_t) return MVP_ERR_INVALID_ARGUMENT;
+  chamfer_loss_kernel<<<b, kLossThreads, 0, (cudaStream_t)stream>>>(n, m, dist1, dist2, cd_p, cd_t);
+  count_launch();
+  return launch_status();
+}
+
+MVP_API int mvp_chamfer_loss_grad(int b, int n, int m, const float *dist1, const float *dist2, const float *grad_cd_p,
+                                  const float *grad_cd_t, float *grad_dist1, float *grad_dist2, mvp_stream_t stream) {
+  if (b < 0 || n <= 0 || m <= 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0) return MVP_OK;
+  if (!dist1 || !dist2 || !grad_cd_p || !grad_cd_t || !grad_dist1 || !grad_dist2) return MVP_ERR_INVALID_ARGUMENT;
+  const long long total = (long long)b * ((long long)n + m);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  chamfer_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, n, m, dist1, dist2, grad_cd_p, grad_cd_t,
+                                                                   grad_dist1, grad_dist2);
+  count_launch();
+  return launch_status();
+}

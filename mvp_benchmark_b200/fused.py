@@ -33,3 +33,43 @@ def knn_points(k, cloud, queries=None):
                                      _lib.ptr(ws), ws.numel(), _lib.stream_of(queries))
     _lib.check(rc, "mvp_knn_points")
     return dist2, idx
+
+
+class _ChamferLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dist1, dist2):
+        dist1, dist2 = dist1.contiguous(), dist2.contiguous()
+        dev = _lib.require_cuda(dist1, dist2, dtype=torch.float32, what="chamfer_loss")
+        if dist1.dim() != 2 or dist2.dim() != 2 or dist1.size(0) != dist2.size(0):
+            raise ValueError(f"chamfer_loss: expected (B, N) and (B, M), got {tuple(dist1.shape)} and {tuple(dist2.shape)}")
+        B, n = dist1.shape
+        m = dist2.size(1)
+        cd_p = torch.empty(B, device=dev, dtype=torch.float32)
+        cd_t = torch.empty(B, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            rc = _lib.lib.mvp_chamfer_loss(B, n, m, _lib.ptr(dist1), _lib.ptr(dist2), _lib.ptr(cd_p), _lib.ptr(cd_t),
+                                           _lib.stream_of(dist1))
+        _lib.check(rc, "mvp_chamfer_loss")
+        ctx.save_for_backward(dist1, dist2)
+        return cd_p, cd_t
+
+    @staticmethod
+    def backward(ctx, g_p, g_t):
+        dist1, dist2 = ctx.saved_tensors
+        B, n = dist1.shape
+        m = dist2.size(1)
+        g_p = (torch.zeros(B, device=dist1.device) if g_p is None else g_p).contiguous().float()
+        g_t = (torch.zeros(B, device=dist1.device) if g_t is None else g_t).contiguous().float()
+        gd1, gd2 = torch.empty_like(dist1), torch.empty_like(dist2)
+        with torch.cuda.device(dist1.device):
+            rc = _lib.lib.mvp_chamfer_loss_grad(B, n, m, _lib.ptr(dist1), _lib.ptr(dist2), _lib.ptr(g_p), _lib.ptr(g_t),
+                                                _lib.ptr(gd1), _lib.ptr(gd2), _lib.stream_of(dist1))
+        _lib.check(rc, "mvp_chamfer_loss_grad")
+        return gd1, gd2
+
+
+def chamfer_loss(dist1, dist2):
+    """(cd_p, cd_t) per cloud from the Chamfer operator's dist1 (B, N) and dist2 (B, M) — the torch glue of
+    completion/model_utils.py:71-72 as one reduction kernel (and one elementwise kernel backward):
+    cd_p = (sqrt(dist1).mean(1) + sqrt(dist2).mean(1)) / 2,  cd_t = dist1.mean(1) + dist2.mean(1).  Differentiable."""
+    return _ChamferLoss.apply(dist1, dist2)

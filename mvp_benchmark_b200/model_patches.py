@@ -1,6 +1,7 @@
 """Opt-in replacements for the k-nearest-neighbour helpers of the reference's completion models
 (completion/model_utils.py:242-271) — SURVEY.md §8(f) row 1 — and for its neighbour-feature gather
-(get_edge_features, :113-124; §8(f) row 2: the grouping around the kNN).  They are CALLER code, outside the drop-in
+(get_edge_features, :113-124; §8(f) row 2: the grouping around the kNN) and the Chamfer loss epilogue (calc_cd,
+:67-77; §8(f) row 3).  They are CALLER code, outside the drop-in
 boundary, so nothing here is applied by default:
 
     import model_utils, models.vrcnet
@@ -60,15 +61,29 @@ def get_edge_features(x, idx):
     return mm3d_pn2.grouping_operation(x.squeeze(2).contiguous(), idx.transpose(1, 2).int().contiguous())
 
 
+def calc_cd(output, gt, calc_f1=False):
+    """model_utils.py:67-77: the Chamfer operator, then its loss epilogue (two sqrt, four means, three elementwise
+    torch kernels) as ONE reduction kernel (fused.chamfer_loss).  Same returns."""
+    import metrics
+    dist1, dist2, _, _ = metrics.cd()(gt, output)
+    if not dist1.is_cuda:
+        return _ORIGINAL["calc_cd"](output, gt, calc_f1)
+    cd_p, cd_t = fused.chamfer_loss(dist1, dist2)
+    if calc_f1:
+        f1, _, _ = metrics.fscore(dist1, dist2)
+        return cd_p, cd_t, f1
+    return cd_p, cd_t
+
+
 def apply(*modules):
-    """Rebind knn / knn_point / knn_point_all / get_edge_features in the given (already imported) modules.  Returns
-    the number of names replaced."""
+    """Rebind knn / knn_point / knn_point_all / get_edge_features / calc_cd in the given (already imported) modules.
+    Returns the number of names replaced."""
     from . import install
     install()  # `mm3d_pn2` must resolve to this repository's package
     count = 0
     for mod in modules:
         for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
-                         ("get_edge_features", get_edge_features)):
+                         ("get_edge_features", get_edge_features), ("calc_cd", calc_cd)):
             cur = getattr(mod, name, None)
             if cur is None or cur is fn:
                 continue

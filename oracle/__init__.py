@@ -298,3 +298,14 @@ def knn_points(k, cloud, queries=None):
     if rc != 0:
         raise ValueError("oracle_knn_points: 1 <= k <= m required")
     return d, idx
+
+
+def chamfer_loss(dist1, dist2):
+    """calc_cd's epilogue (completion/model_utils.py:71-72) -> (cd_p (B,), cd_t (B,))."""
+    d1, d2 = _f32(dist1), _f32(dist2)
+    b, n = d1.shape
+    m = d2.shape[1]
+    cd_p, cd_t = np.empty(b, np.float32), np.empty(b, np.float32)
+    if lib().oracle_chamfer_loss(b, n, m, _fp(d1), _fp(d2), _fp(cd_p), _fp(cd_t)) != 0:
+        raise ValueError("oracle_chamfer_loss: n, m > 0 required")
+    return cd_p, cd_t

@@ -256,3 +256,53 @@ def test_model_patches_get_edge_features(cuda):
     g = torch.randn_like(got)
     got.backward(g), want.backward(g)
     torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("b,n,m", [(64, 2048, 1024), (3, 16384, 16384), (5, 7, 3), (2, 1000, 1)])
+def test_chamfer_loss_epilogue(cuda, cpu, b, n, m):
+    """fused.chamfer_loss against the oracle and against the torch formula of
+    completion/model_utils.py:71-72, forward and backward, 1e-5 relative."""
+    from mvp_benchmark_b200 import fused
+    rng = np.random.default_rng(5)
+    d1 = (rng.random((b, n), dtype=np.float32) ** 2 * 0.01).astype(np.float32)
+    d2 = (rng.random((b, m), dtype=np.float32) ** 2 * 0.01).astype(np.float32)
+    a, c = T(d1, cuda, grad=True), T(d2, cuda, grad=True)
+    cd_p, cd_t = fused.chamfer_loss(a, c)
+    want_p, want_t = cpu.o.chamfer_loss(d1, d2)
+    np.testing.assert_allclose(cd_p.detach().cpu().numpy(), want_p, rtol=1e-5)
+    np.testing.assert_allclose(cd_t.detach().cpu().numpy(), want_t, rtol=1e-5)
+    wp, wt = torch.rand(b, device=cuda), torch.rand(b, device=cuda)
+    ((cd_p * wp).sum() + (cd_t * wt).sum()).backward()
+    a2, c2 = T(d1, cuda, grad=True), T(d2, cuda, grad=True)
+    ref_p = (torch.sqrt(a2).mean(1) + torch.sqrt(c2).mean(1)) / 2
+    ref_t = a2.mean(1) + c2.mean(1)
+    ((ref_p * wp).sum() + (ref_t * wt).sum()).backward()
+    torch.testing.assert_close(cd_p.detach(), ref_p.detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(a.grad, a2.grad, rtol=1e-5, atol=0)
+    torch.testing.assert_close(c.grad, c2.grad, rtol=1e-5, atol=0)
+
+
+def test_model_patches_calc_cd(ops, cuda):
+    """calc_cd rebinding: Chamfer operator + fused epilogue, same returns as model_utils.calc_cd (with and without
+    the F-score), gradients reach the prediction."""
+    import types
+    from mvp_benchmark_b200 import model_patches as mp
+    metrics, _ = ops
+
+    def original(output, gt, calc_f1=False):                # model_utils.py:67-77, restated
+        dist1, dist2, _, _ = metrics.cd()(gt, output)
+        cd_p = (torch.sqrt(dist1).mean(1) + torch.sqrt(dist2).mean(1)) / 2
+        cd_t = dist1.mean(1) + dist2.mean(1)
+        if calc_f1:
+            return cd_p, cd_t, metrics.fscore(dist1, dist2)[0]
+        return cd_p, cd_t
+
+    fake = types.SimpleNamespace(calc_cd=original)
+    assert mp.apply(fake) == 1
+    gt = T(_data.uniform(4, 2048, 21), cuda)
+    p1, p2 = T(_data.uniform(4, 1024, 22), cuda, grad=True), T(_data.uniform(4, 1024, 22), cuda, grad=True)
+    got, want = fake.calc_cd(p1, gt, calc_f1=True), original(p2, gt, calc_f1=True)
+    for g_, w_ in zip(got, want):
+        torch.testing.assert_close(g_, w_, rtol=1e-5, atol=0)
+    got[0].sum().backward(), want[0].sum().backward()
+    torch.testing.assert_close(p1.grad, p2.grad, rtol=1e-4, atol=1e-7)

@@ -94,3 +94,14 @@ def test_oracle_knn_points_vs_reference_model_utils(case):
     np.testing.assert_allclose(d, exact_ref, atol=5e-6, rtol=0)
     if case + "_negdist" in G.files:           # knn_point also returns -distance (model_utils.py:258)
         np.testing.assert_allclose(-d, G[case + "_negdist"], atol=5e-6, rtol=0)
+
+
+@pytest.mark.parametrize("case", ["vrcnet", "square", "tiny"])
+def test_oracle_chamfer_loss_vs_reference_calc_cd(case):
+    """oracle.chamfer_loss against the reference's own calc_cd (completion/model_utils.py:67-77, run on CPU over its
+    pure-torch Chamfer by tests/golden/make_golden_loss.py): 1e-5 relative, north_star's floating-point bar."""
+    import oracle
+    G = np.load(os.path.join(HERE, "golden", "calc_cd_epilogue.npz"))
+    cd_p, cd_t = oracle.chamfer_loss(G[case + "_dist1"], G[case + "_dist2"])
+    np.testing.assert_allclose(cd_p, G[case + "_cd_p"], rtol=1e-5, atol=0)
+    np.testing.assert_allclose(cd_t, G[case + "_cd_t"], rtol=1e-5, atol=0)
