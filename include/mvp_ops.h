@@ -180,6 +180,13 @@ int mvp_chamfer_loss(int b, int n, int m, const float *dist1, const float *dist2
 int mvp_chamfer_loss_grad(int b, int n, int m, const float *dist1, const float *dist2, const float *grad_cd_p,
                           const float *grad_cd_t, float *grad_dist1, float *grad_dist2, mvp_stream_t stream);
 
+/* SURVEY.md §8(f) row 2 — the glue between three_nn and three_interpolate (completion/model_utils.py:286-293,
+ * three_nn_upsampling): dist2 (b,n,3) SQUARED distances as mvp_three_nn returns them -> weight (b,n,3),
+ * w_k = (1/d_k) / (1/d_0 + 1/d_1 + 1/d_2) with d_k = max(sqrt(dist2_k), 1e-10): the sqrt of three_nn.py:38 and five
+ * torch kernels in one pass, IEEE operations (the sum in the order torch 2.11 adds three elements; within 2 ulp of
+ * any other order).  Opt-in (model_patches rebinds three_nn_upsampling). */
+int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight, mvp_stream_t stream);
+
 /* SURVEY.md §8(f) row 1 — the k-nearest-neighbour search the completion MODELS run in torch
  * (completion/model_utils.py:242-259 `knn` / `knn_point` / `knn_point_all`: a (B,N,M) matrix of
  * -|x|^2 + 2 x.y - |y|^2 by matmul, then torch.topk), as one fused exact search for 3-D points.

@@ -67,9 +67,37 @@ chamfer_loss_grad_kernel(int b, int n, int m, const float *__restrict__ dist1, c
   }
 }
 
+// Inverse-distance weights of the three nearest sources (completion/model_utils.py:286-293, three_nn_upsampling):
+//     dist = max(sqrt(d2), 1e-10);  w_k = (1 / dist_k) / ((1 / dist_0 + 1 / dist_2) + 1 / dist_1)
+// from the SQUARED distances mvp_three_nn returns — the sqrt of three_nn.py:38 and the five torch kernels of the
+// glue in one elementwise pass, every operation the IEEE one torch performs, in torch's order.
+__global__ void __launch_bounds__(256)
+three_nn_weights_kernel(long long total, const float *__restrict__ dist2, float *__restrict__ weight) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    float r[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      r[k] = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(__ldg(dist2 + i * 3 + k)), 1e-10f));
+    const float norm = __fadd_rn(__fadd_rn(r[0], r[2]), r[1]);  // the order torch 2.11's reduce kernel adds three elements in (measured)
+#pragma unroll
+    for (int k = 0; k < 3; k++) weight[i * 3 + k] = __fdiv_rn(r[k], norm);
+  }
+}
+
 }  // namespace mvp
 
 using namespace mvp;
+
+MVP_API int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight, mvp_stream_t stream) {
+  if (b < 0 || n < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0) return MVP_OK;
+  if (!dist2 || !weight) return MVP_ERR_INVALID_ARGUMENT;
+  const long long total = (long long)b * n;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  three_nn_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(total, dist2, weight);
+  count_launch();
+  return launch_status();
+}
 
 MVP_API int mvp_chamfer_loss(int b, int n, int m, const float *dist1, const float *dist2, float *cd_p, float *cd_t,
                              mvp_stream_t stream) {

@@ -73,3 +73,24 @@ def chamfer_loss(dist1, dist2):
     completion/model_utils.py:71-72 as one reduction kernel (and one elementwise kernel backward):
     cd_p = (sqrt(dist1).mean(1) + sqrt(dist2).mean(1)) / 2,  cd_t = dist1.mean(1) + dist2.mean(1).  Differentiable."""
     return _ChamferLoss.apply(dist1, dist2)
+
+
+def three_nn_weights(target, source):
+    """The three nearest points of `source` (B, M, 3) for every point of `target` (B, N, 3) and their normalised
+    inverse-distance weights — completion/model_utils.py:286-293 (three_nn_upsampling: three_nn, clamp, reciprocal,
+    sum, divide) as the grid search plus ONE elementwise kernel.  Returns (idx (B, N, 3) int32, weight (B, N, 3));
+    not differentiable (the original's weights are not either: three_nn marks its outputs non-differentiable)."""
+    target, source = target.detach().contiguous(), source.detach().contiguous()
+    dev = _lib.require_cuda(target, source, dtype=torch.float32, what="three_nn_weights")
+    B, N, _ = target.shape
+    m = source.size(1)
+    dist2 = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, N, 3, device=dev, dtype=torch.int32)
+    weight = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(_lib.lib.mvp_three_nn_workspace_bytes(B, N, m), dev)
+        _lib.check(_lib.lib.mvp_three_nn_ws(B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2), _lib.ptr(idx),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_of(target)), "mvp_three_nn")
+        _lib.check(_lib.lib.mvp_three_nn_weights(B, N, _lib.ptr(dist2), _lib.ptr(weight), _lib.stream_of(target)),
+                   "mvp_three_nn_weights")
+    return idx, weight

@@ -61,6 +61,14 @@ def get_edge_features(x, idx):
     return mm3d_pn2.grouping_operation(x.squeeze(2).contiguous(), idx.transpose(1, 2).int().contiguous())
 
 
+def three_nn_upsampling(target_points, source_points):
+    """model_utils.py:286-293: (idx, weight) for three_interpolate — three_nn plus five torch kernels of glue as the
+    grid search plus one elementwise kernel (fused.three_nn_weights).  Same values."""
+    if not target_points.is_cuda or target_points.dtype != torch.float32:
+        return _ORIGINAL["three_nn_upsampling"](target_points, source_points)
+    return fused.three_nn_weights(target_points, source_points)
+
+
 def calc_cd(output, gt, calc_f1=False):
     """model_utils.py:67-77: the Chamfer operator, then its loss epilogue (two sqrt, four means, three elementwise
     torch kernels) as ONE reduction kernel (fused.chamfer_loss).  Same returns."""
@@ -83,7 +91,8 @@ def apply(*modules):
     count = 0
     for mod in modules:
         for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
-                         ("get_edge_features", get_edge_features), ("calc_cd", calc_cd)):
+                         ("get_edge_features", get_edge_features), ("calc_cd", calc_cd),
+                         ("three_nn_upsampling", three_nn_upsampling)):
             cur = getattr(mod, name, None)
             if cur is None or cur is fn:
                 continue

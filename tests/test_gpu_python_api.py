@@ -306,3 +306,29 @@ def test_model_patches_calc_cd(ops, cuda):
         torch.testing.assert_close(g_, w_, rtol=1e-5, atol=0)
     got[0].sum().backward(), want[0].sum().backward()
     torch.testing.assert_close(p1.grad, p2.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_three_nn_weights_chain(ops, cuda):
+    """fused.three_nn_weights / the three_nn_upsampling patch against three_nn + the torch glue
+    of completion/model_utils.py:286-293: same indices, weights within 2 ulp (bit-equal with the torch build the order of the sum was measured on)."""
+    import types
+    from mvp_benchmark_b200 import model_patches as mp
+    _, mm = ops
+
+    def original(target_points, source_points):            # model_utils.py:286-293, restated
+        dist, idx = mm.three_nn(target_points, source_points)
+        dist = torch.max(dist, torch.ones(1, device=dist.device) * 1e-10)
+        norm = torch.sum((1.0 / dist), 2, keepdim=True)
+        norm = norm.repeat(1, 1, 3)
+        return idx, (1.0 / dist) / norm
+
+    fake = types.SimpleNamespace(three_nn_upsampling=original)
+    assert mp.apply(fake) == 1
+    for kind, n, m in (("uniform", 3072, 1536), ("duplicates", 768, 384), ("lattice", 300, 100)):
+        t, s = T(_data.cloud(kind, 4, n, 31), cuda), T(_data.cloud(kind, 4, m, 32), cuda)
+        if kind != "uniform":
+            s = t[:, :m].contiguous()                       # exact coincidences: distance 0 -> the 1e-10 clamp
+        (gi, gw), (wi, ww) = fake.three_nn_upsampling(t, s), original(t, s)
+        assert torch.equal(gi, wi) and gw.shape == (4, n, 3)
+        # bit-equal with torch 2.11 (same IEEE operations, its order of adding the three reciprocals); 2 ulp otherwise
+        torch.testing.assert_close(gw, ww, rtol=3e-7, atol=0)

@@ -64,5 +64,9 @@ mm.gather_points(f2, gi).sum().backward()
 gi3 = torch.randint(0, 3072, (2, 1536, 4), device=dev, generator=g, dtype=torch.int32)
 f3 = torch.randn(2, 16, 3072, device=dev, generator=g).requires_grad_(True)
 mm.grouping_operation(f3, gi3).sum().backward()
+la, lc = R(3, 2048).requires_grad_(True), R(3, 1024).requires_grad_(True)
+cp, ct = fused.chamfer_loss(la, lc)
+(cp.sum() + ct.sum()).backward()
+fused.three_nn_weights(u, kn)
 torch.cuda.synchronize()
 print("sanitize_ops: all entry points ran,", _lib.launch_count(), "kernels launched")
