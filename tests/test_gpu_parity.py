@@ -151,6 +151,20 @@ def test_chamfer_backward_vs_oracle(gpu, cpu, b, n, m):
     _cases.close(got[1], want[1], "gradxyz2")
 
 
+@pytest.mark.parametrize("b,n,m", [(36, 8192, 8192), (20, 16384, 12000), (40, 8191, 8193)])
+def test_chamfer_backward_large_vs_oracle(gpu, cpu, b, n, m):
+    """From 512k points up (n, m multiples of 4) the four-points-per-thread kernels with 64-bit vector reductions
+    run; sizes off that path keep the one-point kernels.  Both against the oracle."""
+    x1, x2 = _data.uniform(b, n, 15), _data.uniform(b, m, 16)
+    rng = np.random.default_rng(1)
+    g1, g2 = rng.random((b, n), dtype=np.float32), rng.random((b, m), dtype=np.float32)
+    _, _, i1, i2 = gpu.chamfer_forward(x1, x2)
+    want = cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
+    got = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
+    _cases.close(got[0], want[0], "gradxyz1")
+    _cases.close(got[1], want[1], "gradxyz2")
+
+
 def test_chamfer_full_size_properties_and_reference(gpu, ref, cuda):
     """BASELINE target size B=32, N=M=16384: checked through properties and against the reference
     kernels live (the CPU oracle would need minutes)."""
