@@ -232,7 +232,18 @@ chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const 
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         float *t = GB + (long long)jj[e] * 3;
-        if ((reinterpret_cast<uintptr_t>(t) & 7) == 0) {
+        // A 12-byte row sits at offset 0, 4, 8 or 12 of a 16-byte chunk.  Offsets 0 and 4 lie inside ONE chunk: a
+        // single 128-bit reduction covers the row, its fourth lane adding +0 to the neighbouring row's element
+        // (exact: x + 0 = x; only -0 becomes +0) — where that neighbour exists inside this cloud's rows.  Offsets 8
+        // and 12 straddle two chunks: one 64-bit and one 32-bit reduction.
+        const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(t) & 15);
+        if (off == 0 && jj[e] + 1 < nb) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t), "f"(-vx[e]), "f"(-vy[e]), "f"(-vz[e]),
+                       "f"(0.f) : "memory");
+        } else if (off == 4 && jj[e] > 0) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t - 1), "f"(0.f), "f"(-vx[e]), "f"(-vy[e]),
+                       "f"(-vz[e]) : "memory");
+        } else if ((off & 7) == 0) {
           asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t), "f"(-vx[e]), "f"(-vy[e]) : "memory");
           atomicAdd(t + 2, -vz[e]);
         } else {
