@@ -16,6 +16,11 @@ OUT = os.path.join(ROOT, "gpurun_build")
 CSRC = os.path.join(ROOT, "mvp_benchmark_b200", "csrc")
 GRID_VARIANTS = {
     "base": [],
+    "minb10": ["-DMVP_GRID_QMINB=10"],
+    "minb12": ["-DMVP_GRID_QMINB=12"],
+    "minb16": ["-DMVP_GRID_QMINB=16"],
+    "q256minb6": ["-DMVP_GRID_QTHREADS=256", "-DMVP_GRID_QMINB=6"],
+    "zbase": [],  # the base library once more, last: the first variant of a run pays the clock ramp
     "q256": ["-DMVP_GRID_QTHREADS=256"],
     "q64": ["-DMVP_GRID_QTHREADS=64"],
     "ppc1": ["-DMVP_GRID_PPC=1"],
