@@ -391,6 +391,20 @@ def run_ours(args):
     out_host = {k: torch.empty(s, dtype=t).pin_memory() for k, s, t in
                 [("d1", (b, n), torch.float32), ("d2", (b, m), torch.float32), ("i1", (b, n), torch.int32),
                  ("i2", (b, m), torch.int32), ("g1", (b, n, 3), torch.float32), ("g2", (b, m, 3), torch.float32)]}
+    # Freshly pinned host memory reaches its host->device bandwidth only after a while on this (virtualised) host
+    # (tools/pinned_probe.py: 16-33 GB/s for the first dozen copies of some buffers, 53.5 GB/s for all of them half a
+    # second later): touch every buffer with a few copies in both directions and give the host a second, outside any
+    # timed region — part of the warm-up.
+    scratch = torch.empty(b, max(n, m), 3, device=dev)
+    for _ in range(3):
+        for t in h1 + h2:
+            scratch[:, :t.size(1)].copy_(t, non_blocking=True)
+        for t in out_host.values():
+            t.copy_(scratch.view(-1)[:t.numel()].view(t.shape).to(t.dtype) if t.dtype != torch.float32
+                    else scratch.view(-1)[:t.numel()].view(t.shape), non_blocking=True)
+    torch.cuda.synchronize()
+    time.sleep(1.0)
+    del scratch
     h2d = sum(t.numel() * t.element_size() for t in (h1[0], h2[0]))
     d2h = sum(t.numel() * t.element_size() for t in out_host.values())
 

@@ -586,13 +586,13 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float 
 #define MVP_GRID_QMINB 12            // resident CTAs per SM the query kernel is compiled for: 42 registers, a few spills, more warps in flight (forward 0.137 -> 0.133 ms; 10: 0.136, 16: 0.139)
 #endif
 #ifndef MVP_GRID_QMINB3
-#define MVP_GRID_QMINB3 0            // the same for three_nn (K = 3); 0 = no occupancy target
+#define MVP_GRID_QMINB3 12           // the same for three_nn (K = 3): 68 -> 63 us at 64 x 3072 from 1536; 0 = no occupancy target
 #endif
 #ifndef MVP_GRID_QMINBK
-#define MVP_GRID_QMINBK 0            // ... and for the k-nearest-neighbour lists
+#define MVP_GRID_QMINBK 6            // ... and for the k-nearest-neighbour lists of 12 and 16 entries (356 -> 319 us at 64 x 3072, k = 16; 8: 339)
 #endif
 template <int K, bool kRT = false>
-__global__ void __launch_bounds__(kGridQThreads, (kRT ? MVP_GRID_QMINBK : K == 1 ? MVP_GRID_QMINB : MVP_GRID_QMINB3))  // (an explicit 1 lets ptxas take 100+ registers)
+__global__ void __launch_bounds__(kGridQThreads, (kRT ? (K == 16 || K == 12 ? MVP_GRID_QMINBK : 0) : K == 1 ? MVP_GRID_QMINB : MVP_GRID_QMINB3))  // (an explicit 1 lets ptxas take 100+ registers)
 chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
                           int *__restrict__ idx1, int *__restrict__ idx2, int kk) {
   constexpr int kBudget = kRT ? MVP_GRID_BUDGET + 64 * K : MVP_GRID_BUDGET;
