@@ -171,7 +171,7 @@ def model_steps():
             continue
         try:
             p = subprocess.run([sys.executable, os.path.join(root, "tools", "model_step.py"), "--model", "vrcnet",
-                                "--steps", "6", "--warmup", "3", *extra], capture_output=True, text=True, timeout=300)
+                                "--steps", "10", "--warmup", "3", *extra], capture_output=True, text=True, timeout=300)
             line = [l for l in p.stdout.splitlines() if l.startswith("MODEL_STEP ")]
             out[tag] = json.loads(line[-1][len("MODEL_STEP "):])["ms_per_step"] if line else None
         except Exception as e:  # secondary number

@@ -115,21 +115,24 @@ def run_arm(a):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     t0 = time.perf_counter()
-    e0.record()
+    evs[0].record()
     for i in range(a.steps):
         loss = step(i)
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3 / a.steps
-    ms = e0.elapsed_time(e1) / a.steps
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps))
+    mean_ms = evs[0].elapsed_time(evs[-1]) / a.steps
+    ms = per_step[len(per_step) // 2]  # median step: the host side of a step (Python, allocator) hiccups now and then
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     out = {"model": a.model, "num_points": n, "ops": a.ops, "patch_knn": bool(a.patch_knn), "ddp": bool(a.ddp), "batch_per_gpu": B, "n_gpus": world,
-           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "wall_ms_per_step": wall,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "mean_ms_per_step": mean_ms,
+           "wall_ms_per_step": wall,
            "samples_per_s": B * world / ms * 1e3, "loss": float(loss.item()),
            "params": sum(p.numel() for p in net.parameters())}
     if a.profile:
