@@ -46,7 +46,7 @@ B, N, M = 32, 16384, 16384
 L2_BYTES = 126 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of the forward's kernels from the ncu --set full capture summarised in
 # profiles/ (per forward, B=32 N=M=16384)
-TRAFFIC_BYTES = 37.3e6  # build2 15.5 + 2.9 MB, query 18.9 + 0.0 MB (profiles/r1_chamfer_grid_full.md)
+TRAFFIC_BYTES = 36.2e6  # build2 14.8 + 2.3 MB, query 19.0 + 0.1 MB (profiles/r1_chamfer_grid_full.md)
 METRIC = "chamfer_fwd_bwd_point_pairs_per_s"
 UNIT = "point-pairs/s"
 WORKLOAD = "chamfer_distance_fwd_bwd B=32 N=M=16384 fp32 uniform[0,1)^3 (PCN/C2 fine-output CD size)"
