@@ -402,14 +402,11 @@ template <int WARPS>
 static int pair_launch(int b, int n, int m, const PairShape &sh, int use_tma, const float *xyz1, const float *xyz2,
                        u64 *rowkey, u64 *colkey, const int *plan, cudaStream_t s) {
   const size_t smem = sizeof(PairSmem<WARPS>);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chamfer_pair_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  {
+    static size_t granted[2][kMaxDevices];
+    int rc0 = grant_dyn_smem(chamfer_pair_kernel<WARPS, false>, smem, granted[0], 0);
+    if (!rc0) rc0 = grant_dyn_smem(chamfer_pair_kernel<WARPS, true>, smem, granted[1], 0);
+    if (rc0) return rc0;
   }
   // plan-driven: one wave of resident CTAs striding over the handed-over clouds' tiles
   const int resident = kNumSMs * (WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4));

@@ -538,15 +538,13 @@ chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, 
 static int grid_build_launch(int b, int n, int m, const float *xyz1, const float *xyz2, const GridWs &W,
                              cudaStream_t s) {
   const size_t smem = grid_build_smem(W.cap, n, m);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(int) * (kGridMaxCells + 8 + kGridRankPts)));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(chamfer_grid_build2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(int) * (kBuild2Per * kGridThreads + 8 + kGridRankPts)));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  {
+    static size_t granted[2][kMaxDevices];
+    int rc0 = grant_dyn_smem(chamfer_grid_build_kernel, sizeof(int) * (kGridMaxCells + 8 + kGridRankPts), granted[0], 0);
+    if (!rc0)
+      rc0 = grant_dyn_smem(chamfer_grid_build2_kernel, sizeof(int) * (kBuild2Per * kGridThreads + 8 + kGridRankPts),
+                           granted[1], 0);
+    if (rc0) return rc0;
   }
   static const int min_pts = [] {  // tuning aid: clouds below MVP_GRID_BUILD2_MIN points use one CTA per side
     const char *e = getenv("MVP_GRID_BUILD2_MIN");

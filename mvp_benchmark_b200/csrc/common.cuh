@@ -14,11 +14,32 @@ namespace mvp {
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 extern unsigned long long g_launch_count;  // defined in capi.cu
-inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+inline void count_launch(int n = 1) {  // callers may be DataParallel worker threads, one per device
+  __atomic_fetch_add(&g_launch_count, (unsigned long long)n, __ATOMIC_RELAXED);
+}
 
 inline int launch_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+// Opt a kernel in to `bytes` of dynamic shared memory (above the default 48 KB).  The attribute belongs to the CURRENT
+// DEVICE, and the reference drives these operators from nn.DataParallel — one process, one thread per device
+// (completion/train.py:49) — so the high-water mark is kept per device: `granted` is a zero-initialised static array
+// of kMaxDevices entries owned by the call site.  Concurrent callers on one device set the same value: benign.
+constexpr int kMaxDevices = 64;
+template <typename K>
+inline int grant_dyn_smem(K kernel, size_t bytes, size_t *granted, size_t preset = 40 * 1024) {
+  if (bytes <= preset) return MVP_OK;  // static + dynamic share the default 48 KB: nothing to opt in to
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && bytes <= granted[dev]) return MVP_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (tracked) granted[dev] = bytes;
+  return MVP_OK;
 }
 
 // The reference's squared distance `dx*dx + dy*dy + dz*dz` as nvcc contracts it (SASS-verified for

@@ -502,14 +502,9 @@ static void fps_launch_one(int b, int n, int m, int log2T, const float *data, fl
     // and the test only lengthens the dependent chain of a pick
     if (fps_use_sorted() && n > 4096) {
       const size_t smem = (size_t)n * (sizeof(float4) + sizeof(int)) + sizeof(int) * (size_t)std::max(8, n / P);
-      static size_t granted = 40 * 1024;
-      if (smem > granted) {
-        const size_t want = (size_t)TB * P * (sizeof(float4) + sizeof(int)) + sizeof(int) * (size_t)std::max(8, TB);
-        if (cudaFuncSetAttribute(fps_sorted_kernel<TB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) !=
-            cudaSuccess)
-          return;  // launch_status() reports it
-        granted = want;
-      }
+      static size_t granted[kMaxDevices];
+      const size_t want = (size_t)TB * P * (sizeof(float4) + sizeof(int)) + sizeof(int) * (size_t)std::max(8, TB);
+      if (grant_dyn_smem(fps_sorted_kernel<TB, P>, smem > 40 * 1024 ? want : smem, granted)) return;  // launch_status() reports it
       fps_sorted_kernel<TB, P><<<b, TB, smem, s>>>(n, m, log2T, data, temp, idx);
       return;
     }
@@ -517,14 +512,10 @@ static void fps_launch_one(int b, int n, int m, int log2T, const float *data, fl
   // the shared-memory copy of the cloud: 16 B per point, for clouds up to 8192 points (128 KB)
   constexpr bool kSmem = !WD && TB * P <= 8192;
   const size_t smem = kSmem ? (size_t)n * sizeof(float4) : 0;
-  if (smem > 40 * 1024) {
-    static size_t granted = 0;
-    if (smem > granted) {
-      if (cudaFuncSetAttribute(fps_kernel<TB, P, WD, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(TB * P * sizeof(float4))) != cudaSuccess)
-        return;  // launch_status() reports it
-      granted = TB * P * sizeof(float4);
-    }
+  {
+    static size_t granted[kMaxDevices];
+    if (grant_dyn_smem(fps_kernel<TB, P, WD, kSmem>, smem > 40 * 1024 ? TB * P * sizeof(float4) : smem, granted))
+      return;  // launch_status() reports it
   }
   fps_kernel<TB, P, WD, kSmem><<<b, TB, smem, s>>>(n, m, log2T, data, temp, idx);
 }

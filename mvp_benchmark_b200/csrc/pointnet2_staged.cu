@@ -20,15 +20,11 @@ namespace mvp {
 constexpr int kStThreads = 512;
 constexpr size_t kStRowBytes = 64 * 1024;  // shared-memory budget for the staged rows of a CTA (3 CTAs / SM)
 
-// opt in to > 48 KB of dynamic shared memory, once per kernel (TAG names the kernel: one high-water mark each) and size
+// opt in to > 48 KB of dynamic shared memory, per kernel (TAG names the kernel: one high-water mark each) and device
 template <int TAG, typename K>
 static int set_smem(K kernel, size_t bytes) {
-  static size_t granted = 40 * 1024;  // static + dynamic share the default 48 KB: opt in a little below it
-  if (bytes <= granted) return MVP_OK;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return (int)e;
-  granted = bytes;
-  return MVP_OK;
+  static size_t granted[kMaxDevices];
+  return grant_dyn_smem(kernel, bytes, granted);
 }
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -323,12 +319,10 @@ int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const floa
   if (!workspace || workspace_bytes < scatter_csr_workspace_bytes(b, rows, entries)) return -100;
   const size_t cloud_ints = csr_cloud_ints(rows, entries);
   const size_t bsmem = sizeof(int) * ((size_t)rows + 1);
-  static size_t granted = 40 * 1024;
-  if (bsmem > granted) {
-    cudaError_t e = cudaFuncSetAttribute(scatter_csr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(int) * (kCsrMaxRows + 1)));
-    if (e != cudaSuccess) return (int)e;
-    granted = sizeof(int) * (kCsrMaxRows + 1);
+  {
+    static size_t granted[kMaxDevices];
+    const int rc0 = grant_dyn_smem(scatter_csr_build_kernel, bsmem > 40 * 1024 ? sizeof(int) * (kCsrMaxRows + 1) : bsmem, granted);
+    if (rc0) return rc0;
   }
   scatter_csr_build_kernel<<<b, kCsrThreads, bsmem, s>>>(rows, entries, cloud_ints, idx, interp ? weight : nullptr,
                                                          (int *)workspace);
