@@ -156,13 +156,13 @@ def vrcnet_census(dev, g, have_ref):
 def model_steps():
     """One training step of the reference's UNMODIFIED VRCNet (B = 32, cfgs/vrcnet.yaml) through tools/model_step.py:
     on the reference's kernels, on ours, and on ours with the opt-in model patches.  Needs the models staged under
-    oracle/_ref/completion (oracle/build_ref.py, where /root/reference exists); returns None without them."""
+    baseline/_ref/completion (oracle/build_ref.py, where /root/reference exists); returns None without them."""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.abspath(__file__))
-    if not os.path.isfile(os.path.join(root, "oracle", "_ref", "completion", "models", "vrcnet.py")):
+    if not os.path.isfile(os.path.join(root, "baseline", "_ref", "completion", "models", "vrcnet.py")):
         return None
     out = {"model": "vrcnet", "batch": 32, "step": "zero_grad + forward + backward + Adam (completion/train.py:122-142)"}
     for tag, extra in (("ref_cuda_ms", ["--ops", "ref"]), ("ours_ms", ["--ops", "ours"]),

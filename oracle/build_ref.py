@@ -91,16 +91,18 @@ MODEL_FILES = [
 
 def stage_models():
     """Stage the reference's completion MODELS (the callers of the hot path: SURVEY.md §2.1 row 9, out of
-    scope and not rebuilt) unmodified under oracle/_ref/completion/ — git-ignored like the rest of
-    oracle/_ref/, so they never enter the history — for tools/model_step.py, which times an unmodified
-    VRCNet / PCN / ECG training step on our operators and on the reference kernels on the same B200
-    (/root/reference does not exist on the GPU box)."""
+    scope and not rebuilt) unmodified under baseline/_ref/completion/ — the git-ignored place for an
+    unmodified copy of the reference, which travels to the GPU box but never enters the history — for
+    tools/model_step.py, which times an unmodified VRCNet / PCN / ECG training step on our operators and
+    on the reference kernels on the same B200 (/root/reference does not exist on the GPU box).
+    oracle/_ref/ itself holds build outputs only."""
     import shutil
+    dest = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
     for f in MODEL_FILES:
-        dst = os.path.join(OUT, f)
+        dst = os.path.join(dest, f)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         shutil.copyfile(os.path.join(REF, f), dst)
-    return os.path.join(OUT, "completion")
+    return os.path.join(dest, "completion")
 
 
 if __name__ == "__main__":

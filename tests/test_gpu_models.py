@@ -2,7 +2,7 @@
 training step on top of this repository's operators, and the loss of that step equals the loss of the same step on
 the reference's own CUDA kernels (oracle/ref_packages -> oracle/_ref/libref_ops.so), same seed, same weights, same
 inputs.  The models are not part of the repository: oracle/build_ref.py stages them under the git-ignored
-oracle/_ref/completion/ where /root/reference exists; without them (or without the reference library) the tests skip.
+baseline/_ref/completion/ where /root/reference exists; without them (or without the reference library) the tests skip.
 """
 import json
 import os
@@ -14,7 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGED = os.path.join(ROOT, "oracle", "_ref", "completion", "models", "vrcnet.py")
+STAGED = os.path.join(ROOT, "baseline", "_ref", "completion", "models", "vrcnet.py")
 REFLIB = os.path.join(ROOT, "oracle", "_ref", "libref_ops.so")
 
 

@@ -5,7 +5,7 @@ sm_100a on the same B200 — the north star's "VRCNet end-to-end training step v
 
 The models are the callers of the hot path (out of scope, not rebuilt).  They are not
 part of this repository: `oracle/build_ref.py:stage_models()` stages completion/model_utils.py,
-completion/models/*.py and completion/cfgs/*.yaml byte for byte under the git-ignored oracle/_ref/completion/
+completion/models/*.py and completion/cfgs/*.yaml byte for byte under the git-ignored baseline/_ref/completion/
 in the container where /root/reference exists, and this tool imports them from there.  Which operator
 library the model's `from metrics import …` / `from mm3d_pn2 import …` (completion/model_utils.py:19-21)
 resolve to is decided by what is first on sys.path:
@@ -29,7 +29,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGED = os.path.join(ROOT, "oracle", "_ref", "completion")
+STAGED = os.path.join(ROOT, "baseline", "_ref", "completion")
 
 
 class Cfg(dict):
@@ -40,7 +40,7 @@ class Cfg(dict):
 def load_model(model_name, ops):
     import yaml
     if not os.path.isdir(STAGED):
-        raise SystemExit("oracle/_ref/completion missing: run `python oracle/build_ref.py` where /root/reference exists")
+        raise SystemExit("baseline/_ref/completion missing: run `python oracle/build_ref.py` where /root/reference exists")
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     if ops == "ours":
