@@ -35,6 +35,56 @@ def _worker(rank, world, port, q):
     torch.distributed.destroy_process_group()
 
 
+def _worker_overlapped(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from mvp_benchmark_b200 import dist as mdist
+    r, w, _ = mdist.init_from_env(backend="gloo")
+    batch = torch.arange(8 * 3, dtype=torch.float32).view(8, 3) / 10
+    mine = mdist.shard_batch(batch, r, w)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))
+    unused = torch.nn.Linear(2, 2)                                   # never part of the graph: no gradient
+    params = list(model.parameters()) + list(unused.parameters())
+    reducer = mdist.OverlappedGradientAllReduce(params, bucket_bytes=64, average=True)
+    out = []
+    for step in range(2):                                             # state resets between steps
+        for p in params:
+            p.grad = None
+        model(mine * (step + 1)).square().sum().backward()
+        calls = reducer.finish()
+        out.append((calls, [None if p.grad is None else p.grad.tolist() for p in params]))
+    mdist.barrier()
+    q.put((rank, out))
+    torch.distributed.destroy_process_group()
+
+
+def test_overlapped_gradient_all_reduce_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlapped, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    batch = torch.arange(8 * 3, dtype=torch.float32).view(8, 3) / 10
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))
+    for step in range(2):
+        for p in model.parameters():
+            p.grad = None
+        model(batch * (step + 1)).square().sum().backward()
+        (c0, g0), (c1, g1) = res[0][1][step], res[1][1][step]
+        assert c0 == c1 and c0 >= 3                                  # same collectives on both ranks, several buckets
+        assert g0[-2:] == [None, None] and g1[-2:] == [None, None]   # the unused layer stays without gradient
+        for a, b, p in zip(g0, g1, model.parameters()):
+            a, b = torch.tensor(a), torch.tensor(b)
+            assert torch.allclose(a, b) and torch.allclose(a, p.grad / 2, rtol=1e-5, atol=1e-6)   # averaged over 2 ranks
+
+
 def test_shard_bounds_cover_everything():
     from mvp_benchmark_b200.dist import shard_bounds
     for total in (1, 7, 32, 256):

@@ -96,6 +96,9 @@ def run_arm(a):
         from mvp_benchmark_b200 import dist as mdist
     params = list(net.parameters())
     fwd_net = net
+    reducer = None
+    if world > 1 and not a.ddp and not a.no_overlap:   # bucketed all-reduce overlapped with backward (dist.py)
+        reducer = mdist.OverlappedGradientAllReduce(params, bucket_bytes=a.bucket_mb << 20)
     if world > 1 and a.ddp:   # comparison arm: torch's DistributedDataParallel (bucketed all-reduce overlapped with backward)
         fwd_net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], bucket_cap_mb=a.bucket_mb,
                                                             find_unused_parameters=True)
@@ -105,8 +108,10 @@ def run_arm(a):
         opt.zero_grad()
         out2, loss2, net_loss = fwd_net(x, gt, alpha=alpha)       # train.py:134
         net_loss.backward()                                        # train.py:141 (one device per process)
-        if world > 1 and not a.ddp:
-            mdist.allreduce_gradients(params, world, bucket_bytes=a.bucket_mb << 20)   # the one collective of a step
+        if reducer is not None:
+            reducer.finish()                                       # the one collective of a step
+        elif world > 1 and not a.ddp:
+            mdist.allreduce_gradients(params, world, bucket_bytes=a.bucket_mb << 20)
         opt.step()                                                 # train.py:142
         return net_loss
 
@@ -130,7 +135,7 @@ def run_arm(a):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    out = {"model": a.model, "num_points": n, "ops": a.ops, "patch_knn": bool(a.patch_knn), "ddp": bool(a.ddp), "batch_per_gpu": B, "n_gpus": world,
+    out = {"model": a.model, "num_points": n, "ops": a.ops, "patch_knn": bool(a.patch_knn), "ddp": bool(a.ddp), "overlapped_allreduce": reducer is not None, "batch_per_gpu": B, "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "mean_ms_per_step": mean_ms,
            "wall_ms_per_step": wall,
            "samples_per_s": B * world / ms * 1e3, "loss": float(loss.item()),
@@ -167,6 +172,7 @@ def main():
                     help="opt-in: replace model_utils.knn_point / knn by the fused operators (SURVEY.md §8f row 1)")
     ap.add_argument("--ddp", action="store_true", help="N>1: torch DDP instead of mvp_benchmark_b200.dist.allreduce_gradients")
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: all-reduce after backward instead of overlapped with it")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     if not a.both:
