@@ -33,9 +33,13 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_is_sm100a_only_and_has_no_torch_dependency():
     from mvp_benchmark_b200 import _lib
-    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    archs = set(re.findall(r"sm_\d+a?", out))
-    assert archs == {"sm_100a"}, archs
+    archs, err = set(), ""
+    for _ in range(3):  # cuobjdump now and then returns nothing on a loaded machine: ask again before judging
+        r = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+        archs, err = set(re.findall(r"sm_\d+a?", r.stdout)), r.stderr
+        if archs:
+            break
+    assert archs == {"sm_100a"}, (archs, err[-500:])
     ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "torch" not in ldd and "python" not in ldd and "c10" not in ldd
 
