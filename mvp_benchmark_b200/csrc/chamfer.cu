@@ -339,6 +339,5 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
                                                    gradxyz2);
   }
   count_launch(2);
-  count_launch();
   return launch_status();
 }

@@ -762,7 +762,9 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
       if (!kRT || k >= K - kk) {  // real entries follow the phantoms
         const int o = kRT ? k - (K - kk) : k;
         dist[(size_t)orig * ko + o] = bd[k];
-        idx[(size_t)orig * ko + o] = bk[k];
+        // a slot nothing filled (every remaining candidate had a NaN distance) keeps distance +inf and gets a
+        // valid, distinct index: callers index with the result
+        idx[(size_t)orig * ko + o] = (kRT && bk[k] == 0x7fffffff) ? o : bk[k];
       }
     }
   } else {
@@ -936,7 +938,8 @@ topk_nn_kernel(int n, int m, int kk, const float *__restrict__ queries, const fl
     for (int k = 0; k < K; k++) {
       if (k >= K - kk) {
         dist2[((size_t)b * n + p) * kk + k - (K - kk)] = bd[k];
-        idx[((size_t)b * n + p) * kk + k - (K - kk)] = bk[k];
+        // unfilled slot (NaN distances are never kept): distance stays +inf, the index a valid distinct one
+        idx[((size_t)b * n + p) * kk + k - (K - kk)] = bk[k] == 0x7fffffff ? k - (K - kk) : bk[k];
       }
     }
   }

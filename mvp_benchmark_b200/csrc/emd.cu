@@ -773,6 +773,10 @@ emd_grad_kernel(long long total, int n, const float *__restrict__ xyz1, const fl
     const long long cloud = i / n;
     const int j2 = __ldg(assignment + i);
     const float g = __ldg(graddist + i) * 2;
+    if (j2 < 0 || j2 >= n) {  // unassigned (the forward leaves -1 when iters == 0; its dist is 0): zero gradient
+      gradxyz1[i * 3 + 0] = gradxyz1[i * 3 + 1] = gradxyz1[i * 3 + 2] = 0.f;
+      continue;
+    }
     const long long o = (cloud * n + j2) * 3;
     gradxyz1[i * 3 + 0] = 0.f + g * (__ldg(xyz1 + i * 3 + 0) - __ldg(xyz2 + o + 0));
     gradxyz1[i * 3 + 1] = 0.f + g * (__ldg(xyz1 + i * 3 + 1) - __ldg(xyz2 + o + 1));
@@ -808,11 +812,16 @@ MVP_API size_t mvp_emd_forward_workspace_bytes(int b, int n) {
   return (size_t)b * n * 28;
 }
 
+// `granted`: the call site's per-device high-water mark of the kernel's dynamic shared memory (common.cuh)
 template <typename K>
-static int emd_launch(K kernel, int b, int cluster, size_t smem, cudaStream_t stream, int n, int arg, float eps, int iters,
-                      const float *xyz1, const float *xyz2, float *dist, int *assignment, void *workspace) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+static int emd_launch(K kernel, size_t *granted, int b, int cluster, size_t smem, cudaStream_t stream, int n, int arg,
+                      float eps, int iters, const float *xyz1, const float *xyz2, float *dist, int *assignment,
+                      void *workspace) {
+  {
+    const int rc = grant_dyn_smem(kernel, smem, granted, 0);
+    if (rc) return rc;
+  }
+  cudaError_t e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(b * cluster));
   cfg.blockDim = dim3(kEmdThreads);
@@ -848,13 +857,15 @@ MVP_API int mvp_emd_forward_algo(int algo, int b, int n, int m, const float *xyz
     const int cluster = emd_cluster_size(b, n);
     const int cap = std::max(8, n / kEmdGridPPC);
     const size_t smem = (size_t)n * 20 + sizeof(int) * (size_t)((cap + 1 + 3) & ~3) + sizeof(int) * (size_t)(n / cluster);
-    return emd_launch(emd_auction_grid_kernel, b, cluster, smem, (cudaStream_t)stream, n, cap, eps, iters, xyz1, xyz2,
+    static size_t granted_grid[kMaxDevices];
+    return emd_launch(emd_auction_grid_kernel, granted_grid, b, cluster, smem, (cudaStream_t)stream, n, cap, eps, iters, xyz1, xyz2,
                       dist, assignment, workspace);
   }
   int cluster = 1, tile_cap = 0;
   size_t smem = 0;
   if (!emd_smem_plan(b, n, &cluster, &tile_cap, &smem)) return MVP_ERR_INVALID_ARGUMENT;
-  return emd_launch(emd_auction_kernel, b, cluster, smem, (cudaStream_t)stream, n, tile_cap, eps, iters, xyz1, xyz2, dist,
+  static size_t granted_full[kMaxDevices];
+  return emd_launch(emd_auction_kernel, granted_full, b, cluster, smem, (cudaStream_t)stream, n, tile_cap, eps, iters, xyz1, xyz2, dist,
                     assignment, workspace);
 }
 

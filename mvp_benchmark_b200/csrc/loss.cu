@@ -63,7 +63,9 @@ chamfer_loss_grad_kernel(int b, int n, int m, const float *__restrict__ dist1, c
     // torch: mean backward (g / cnt), then sqrt backward (g / (2 sqrt(d))), after the "/ 2" of cd_p
     const float gp = (__ldg(g_p + cloud) / 2) / (float)cnt;
     const float gt = __ldg(g_t + cloud) / (float)cnt;
-    (first ? gd1 : gd2)[p] = gp / (2 * __fsqrt_rn(d)) + gt;
+    // an absent / zero upstream gradient of cd_p contributes nothing: autograd never runs sqrt's backward for an
+    // unused output, so d == 0 must not turn 0 / 0 into NaN here (cd_t-only training with coincident points)
+    (first ? gd1 : gd2)[p] = (gp != 0.f ? gp / (2 * __fsqrt_rn(d)) : 0.f) + gt;
   }
 }
 

@@ -40,36 +40,69 @@ def shard_batch(t, rank, world, dim=0):
     return t.narrow(dim, lo, hi - lo)
 
 
-def allreduce_gradients(params, world=None, bucket_bytes=32 << 20, average=True):
-    """Sum (or average) the .grad of `params` across ranks with as few collectives as possible: grads are
-    flattened into buckets of `bucket_bytes` (sized for launch latency, not link count — NVSwitch gives
-    every pair full bandwidth).  Returns the number of collectives issued."""
+def _pack(bucket):
+    """Flat fp32-or-native buffer of a bucket of parameters: every parameter's gradient (zeros where this rank
+    has none) followed by one 'used' flag per parameter.  The layout depends on the PARAMETER list only, never on
+    which gradients happen to exist on this rank, so all ranks always exchange buffers of equal size and meaning."""
+    ref = bucket[0]
+    parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(ref.dtype) for p in bucket]
+    used = torch.tensor([0.0 if p.grad is None else 1.0 for p in bucket], dtype=ref.dtype, device=ref.device)
+    return torch.cat(parts + [used])
+
+
+def _unpack(bucket, flat, scale):
+    """Writes the reduced gradients back.  A parameter no rank used (flag sum 0) keeps grad None, as in a
+    single-process step; one that only OTHER ranks used receives their (scaled) sum, so the optimiser steps
+    identically everywhere."""
+    used = flat[flat.numel() - len(bucket):]
+    used = used.tolist()
+    off = 0
+    for p, u in zip(bucket, used):
+        n = p.numel()
+        if u > 0:
+            g = flat[off:off + n].view_as(p)
+            if scale != 1.0:
+                g = g * scale
+            if p.grad is None:
+                p.grad = g.to(p.dtype).clone()
+            else:
+                p.grad.copy_(g)
+        off += n
+
+
+def allreduce_gradients(params, world=None, bucket_bytes=32 << 20, average=True, weight=None):
+    """Sum (or average) the .grad of `params` across ranks with as few collectives as possible: gradients are
+    flattened into buckets of `bucket_bytes` (sized for launch latency, not link count — NVSwitch gives every pair
+    full bandwidth).  Buckets are built from EVERY parameter that requires a gradient, in the order given, with
+    zeros standing in for a gradient this rank did not produce: the collectives and their sizes are the same on all
+    ranks whatever each rank's graph looked like.  Returns the number of collectives issued.
+
+    `average=True` divides the sum by the world size: the gradient of the mean of the per-rank mean losses.  With
+    UNEVEN shards (7 clouds over 2 ranks = 4 + 3) that is not the gradient of the global mean; pass
+    `weight = local_count / global_count` (and average=True) to scale each rank's gradient before the sum instead."""
     if not dist.is_initialized():
         return 0
     world = world or dist.get_world_size()
-    grads = [p.grad for p in params if p.grad is not None]
+    params = [p for p in params if p.requires_grad]
     calls, bucket, size = 0, [], 0
 
     def flush():
         nonlocal calls, bucket, size
         if not bucket:
             return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+        flat = _pack(bucket)
+        if weight is not None:
+            flat[:flat.numel() - len(bucket)] *= float(weight)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        if average:
-            flat /= world
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        _unpack(bucket, flat, 1.0 / world if (average and weight is None) else 1.0)
         calls += 1
         bucket, size = [], 0
 
-    for g in grads:
-        nbytes = g.numel() * g.element_size()
+    for p in params:
+        nbytes = p.numel() * p.element_size()
         if size + nbytes > bucket_bytes and bucket:
             flush()
-        bucket.append(g)
+        bucket.append(p)
         size += nbytes
     flush()
     return calls
@@ -91,11 +124,14 @@ def barrier():
 class OverlappedGradientAllReduce:
     """The gradient all-reduce of a data-parallel step, overlapped with the backward pass (what replaces
     nn.DataParallel's reduce-to-GPU-0, completion/train.py:49,141).  Parameters are assigned to buckets of
-    `bucket_bytes` up front, in REVERSE registration order (gradients arrive roughly last layer first); a bucket is
-    flattened and all-reduced asynchronously the moment its last gradient has been accumulated
-    (`register_post_accumulate_grad_hook`), while autograd keeps running; `finish()` — call it after `backward()` —
-    launches whatever is left (parameters that received no gradient in this step count as zeros, so every rank issues
-    the same collectives whatever its graph looked like), waits, and writes the averaged gradients back.
+    `bucket_bytes` up front, in REVERSE registration order (gradients arrive roughly last layer first).  A bucket is
+    flattened and all-reduced asynchronously once its last gradient has been accumulated
+    (`register_post_accumulate_grad_hook`) AND every bucket before it has been launched: collectives are matched
+    across ranks by issue order, so they are issued strictly in bucket order on every rank, whichever order a
+    rank's graph completes them in.  `finish()` — call it after `backward()` — launches what is left (a parameter
+    without a gradient on this rank counts as zeros), waits, and writes the averaged gradients back; a parameter
+    used by another rank only receives that rank's gradient, one used by no rank keeps grad None (a per-parameter
+    'used' flag travels with each bucket).
 
         reducer = OverlappedGradientAllReduce(model.parameters())
         loss.backward(); reducer.finish(); optimizer.step()
@@ -117,48 +153,40 @@ class OverlappedGradientAllReduce:
         if cur:
             self.buckets.append(cur)
         self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
-        self._pending = [len(b) for b in self.buckets]
-        self._work = [None] * len(self.buckets)
-        self._flat = [None] * len(self.buckets)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._reset()
 
-    def _launch(self, i):
-        bucket = self.buckets[i]
-        ref = next((p for p in bucket if p.grad is not None), bucket[0])
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket]) \
-            if len(bucket) > 1 or bucket[0].grad is None else bucket[0].grad.reshape(-1).clone()
-        flat = flat.to(ref.dtype)
-        self._flat[i] = flat
-        self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True) if dist.is_initialized() else None
-
-    def _on_grad(self, p):
-        i = self._bucket_of[id(p)]
-        self._pending[i] -= 1
-        if self._pending[i] == 0:
-            self._launch(i)
-
-    def finish(self):
-        """Launch the buckets that are still open, wait for all of them, write the (averaged) sums back.  Returns the
-        number of collectives of this step."""
-        world = dist.get_world_size() if dist.is_initialized() else 1
-        for i in range(len(self.buckets)):
-            if self._work[i] is None and self._flat[i] is None:
-                self._launch(i)
-        for i, bucket in enumerate(self.buckets):
-            if self._work[i] is not None:
-                self._work[i].wait()
-            flat = self._flat[i]
-            if self.average and world > 1:
-                flat /= world
-            off = 0
-            for p in bucket:
-                if p.grad is not None:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
+    def _reset(self):
         n = len(self.buckets)
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * n
         self._flat = [None] * n
+        self._next = 0  # buckets [0, _next) have been launched
+
+    def _launch(self, i):
+        flat = _pack(self.buckets[i])
+        self._flat[i] = flat
+        self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True) if dist.is_initialized() else None
+
+    def _on_grad(self, p):
+        self._pending[self._bucket_of[id(p)]] -= 1
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:  # strictly in bucket order
+            self._launch(self._next)
+            self._next += 1
+
+    def finish(self):
+        """Launch the buckets that are still open (in order), wait for all of them, write the (averaged) sums
+        back.  Returns the number of collectives of this step."""
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        while self._next < len(self.buckets):
+            self._launch(self._next)
+            self._next += 1
+        for i, bucket in enumerate(self.buckets):
+            if self._work[i] is not None:
+                self._work[i].wait()
+            _unpack(bucket, self._flat[i], 1.0 / world if (self.average and world > 1) else 1.0)
+        n = len(self.buckets)
+        self._reset()
         return n
 
     def remove(self):

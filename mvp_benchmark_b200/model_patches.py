@@ -42,7 +42,9 @@ def knn_point(pk, point_input, point_output):
     """model_utils.py:250-259: for every point of point_output (B, m, 3) its pk nearest points of point_input
     (B, n, 3) -> (dist (B, m, pk) = NEGATIVE squared distances, descending; idx (B, m, pk) int64)."""
     if (point_input.dim() != 3 or point_input.size(2) != 3 or not point_input.is_cuda
-            or point_input.dtype != torch.float32 or pk > min(point_input.size(1), 64)):
+            or point_input.dtype != torch.float32 or pk > min(point_input.size(1), 64)
+            or point_output.dim() != 3 or point_output.size(2) != 3 or not point_output.is_cuda
+            or point_output.dtype != torch.float32 or point_output.size(0) != point_input.size(0)):
         return _ORIGINAL["knn_point"](pk, point_input, point_output)
     _, idx = fused.knn_points(pk, point_input, point_output)
     return _neg_sqdist(point_output, point_input, idx), idx.long()

@@ -136,6 +136,13 @@ def emd_last_ambiguous():
     return int(lib().oracle_emd_last_ambiguous())
 
 
+def emd_last_ambiguous_per_cloud(b):
+    """The same count for each of the `b` clouds of the last emd_forward call (int64 array)."""
+    out = np.zeros(b, np.int64)
+    lib().oracle_emd_last_ambiguous_per_cloud(out.ctypes.data_as(ctypes.c_void_p), int(b))
+    return out
+
+
 def emd_set_tie_policy(p):
     """0 = highest source index wins GetMax near-ties (default, = the product), 1 = lowest."""
     lib().oracle_emd_set_tie_policy(int(p))

@@ -120,3 +120,74 @@ def test_two_rank_sharded_step_matches_single_process():
     for g0, g1, p in zip(res[0][4], res[1][4], model.parameters()):
         g0, g1 = torch.tensor(g0), torch.tensor(g1)
         assert torch.allclose(g0, g1) and torch.allclose(g0, p.grad, rtol=1e-5, atol=1e-5)
+
+
+def _worker_asymmetric(rank, world, port, q):
+    """Rank 0's graph uses the branch `extra` and rank 1's does not (a data-dependent branch): the ranks finish
+    their buckets in different orders, and rank 1 has no gradient for `extra` at all."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from mvp_benchmark_b200 import dist as mdist
+    r, w, _ = mdist.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    first, extra, last = torch.nn.Linear(3, 4), torch.nn.Linear(4, 4), torch.nn.Linear(4, 2)
+    never = torch.nn.Linear(2, 2)
+    params = [*first.parameters(), *extra.parameters(), *last.parameters(), *never.parameters()]
+    x = torch.arange(6, dtype=torch.float32).view(2, 3) / 10 + rank
+    out = {}
+    for mode in ("overlapped", "after"):
+        for p in params:
+            p.grad = None
+        reducer = mdist.OverlappedGradientAllReduce(params, bucket_bytes=16, average=True) if mode == "overlapped" else None
+        h = first(x)
+        if rank == 0:
+            h = extra(h)
+        last(h).square().sum().backward()
+        if reducer is not None:
+            reducer.finish()
+            reducer.remove()
+        else:
+            mdist.allreduce_gradients(params, bucket_bytes=16, average=True)
+        out[mode] = [None if p.grad is None else p.grad.tolist() for p in params]
+    mdist.barrier()
+    q.put((rank, out))
+    torch.distributed.destroy_process_group()
+
+
+def test_rank_asymmetric_unused_parameter():
+    """collectives must be issued in the same order on every rank, and a parameter only ONE rank used
+    must end up with the same averaged gradient on all ranks (else the replicas' weights diverge)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_asymmetric, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process expectation: mean of the two ranks' gradients, zeros standing in for rank 1's missing branch
+    torch.manual_seed(0)
+    first, extra, last = torch.nn.Linear(3, 4), torch.nn.Linear(4, 4), torch.nn.Linear(4, 2)
+    mods = [first, extra, last]
+    want = None
+    for rank in range(2):
+        for mod in mods:
+            mod.zero_grad(set_to_none=True)
+        x = torch.arange(6, dtype=torch.float32).view(2, 3) / 10 + rank
+        h = first(x)
+        if rank == 0:
+            h = extra(h)
+        last(h).square().sum().backward()
+        g = [torch.zeros_like(p) if p.grad is None else p.grad.clone() for mod in mods for p in mod.parameters()]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    want = [w / 2 for w in want]
+    for mode in ("overlapped", "after"):
+        g0, g1 = res[0][1][mode], res[1][1][mode]
+        assert g0[-2:] == [None, None] and g1[-2:] == [None, None]   # used by no rank: stays None
+        for a, b, w in zip(g0[:-2], g1[:-2], want):
+            assert a is not None and b is not None
+            a, b = torch.tensor(a), torch.tensor(b)
+            assert torch.equal(a, b), mode                           # identical on both ranks
+            assert torch.allclose(a, w, rtol=1e-5, atol=1e-6), mode
