@@ -58,15 +58,18 @@ int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz
                         mvp_stream_t stream);
 
 /* The same operator with the algorithm named explicitly (tests and benchmarks use it; results are
- * bit-identical for all three):
+ * bit-identical for all of them):
  *   MVP_CHAMFER_AUTO  what mvp_chamfer_forward does: GRID when the shape supports it, else BRUTE;
  *   MVP_CHAMFER_BRUTE every pair evaluated (tiled B*N*M argmin, both directions from one evaluation);
  *   MVP_CHAMFER_GRID  exact nearest neighbour through a uniform grid built per cloud, pruned with
- *                     conservative lower bounds, left-over points finished by brute force
- *                     (n, m >= 512; MVP_ERR_INVALID_ARGUMENT otherwise). */
+ *                     conservative lower bounds (n, m >= 512; MVP_ERR_INVALID_ARGUMENT otherwise): the
+ *                     warp-cooperative search of chamfer_dense.cu for clouds of up to 16384 points, the
+ *                     thread-per-query search of chamfer_grid.cu above that;
+ *   MVP_CHAMFER_GRID_THREAD  the thread-per-query grid search whatever the size (n, m >= 512). */
 #define MVP_CHAMFER_AUTO 0
 #define MVP_CHAMFER_BRUTE 1
 #define MVP_CHAMFER_GRID 2
+#define MVP_CHAMFER_GRID_THREAD 3
 int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
                              float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
                              size_t workspace_bytes, mvp_stream_t stream);

@@ -9,6 +9,8 @@
 // registers, targets staged through shared memory.  The large-cloud fast path (both directions from one
 // evaluation of each pair, packed fp32x2 math, TMA-staged tiles) lives in chamfer_fused.cu and is chosen
 // by mvp_chamfer_forward when the shapes allow.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mvp {
@@ -255,6 +257,209 @@ chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const 
   }
 }
 
+
+// ---- backward without global atomics: every gradient row is SUMMED by one thread ------------------------------------
+// gradxyz_s[j] = 2 g_s[j] (p_j - q_idx_s[j])  -  sum over { i : idx_o[i] == j } of 2 g_o[i] (q_i - p_j)
+// (chamfer3D.cu:155-174 accumulates the same terms with six float atomics per point into memset gradients).  A CTA
+// owns the rows j in [j0, j0 + R) of one side of one cloud.  It reads the OTHER side's index array once into
+// registers (coalesced), transposes the entries that point into its range with a counting sort in shared memory
+// (native integer atomics: histogram, block scan, scatter of 16-bit source indices), and then each thread produces
+// whole rows: own term + the listed terms, one coalesced 12-byte store per row.  No float atomics, no memset, xyz /
+// idx / grad read once from HBM (the gathers hit L2).  Lists of up to kCsrOrdered entries are summed in ascending
+// source order (deterministic); longer ones in arrival order.
+constexpr int kCsrThreads = 512;
+constexpr int kCsrRegs = 32;            // other-side indices per thread: clouds of up to 16384 points
+constexpr int kCsrMaxPts = kCsrThreads * kCsrRegs;
+constexpr int kCsrOrdered = 8;
+
+__global__ void __launch_bounds__(kCsrThreads)
+chamfer_grad_csr_kernel(int n, int m, int R, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                        const float *__restrict__ gd1, const float *__restrict__ gd2, const int *__restrict__ idx1,
+                        const int *__restrict__ idx2, float *__restrict__ gx1, float *__restrict__ gx2) {
+  extern __shared__ __align__(16) int csr_smem[];
+  __shared__ int s_warp[kCsrThreads / 32];
+  const int side = blockIdx.y, cloud = blockIdx.z;
+  const int nt = side ? m : n, no = side ? n : m;  // rows produced here / entries of the other side's index
+  const int j0 = blockIdx.x * R;
+  if (j0 >= nt) return;
+  const int rows = min(R, nt - j0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int *hist = csr_smem;                                                       // [R + 1]
+  unsigned short *perm = reinterpret_cast<unsigned short *>(csr_smem + R + 1);  // [no]
+  const float *Ps = (side ? xyz2 : xyz1) + (size_t)cloud * nt * 3;
+  const float *Po = (side ? xyz1 : xyz2) + (size_t)cloud * no * 3;
+  const float *Gs = (side ? gd2 : gd1) + (size_t)cloud * nt;
+  const float *Go = (side ? gd1 : gd2) + (size_t)cloud * no;
+  const int *Is = (side ? idx2 : idx1) + (size_t)cloud * nt;
+  const int *Io = (side ? idx1 : idx2) + (size_t)cloud * no;
+  float *Out = (side ? gx2 : gx1) + (size_t)cloud * nt * 3;
+
+  // the other side's neighbours, relative to this CTA's range (anything outside it becomes a huge unsigned)
+  int rel[kCsrRegs];
+#pragma unroll
+  for (int k = 0; k < kCsrRegs; k++) {
+    const int i = k * kCsrThreads + tid;
+    rel[k] = i < no ? __ldg(Io + i) - j0 : -1;
+  }
+  for (int c = tid; c <= R; c += kCsrThreads) hist[c] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kCsrRegs; k++)
+    if ((unsigned)rel[k] < (unsigned)rows) atomicAdd(&hist[rel[k]], 1);
+  __syncthreads();
+  // exclusive scan of hist[0, R) in place (R is a multiple of kCsrThreads: a contiguous chunk per thread)
+  const int per = R / kCsrThreads;
+  int sum = 0;
+  for (int c = 0; c < per; c++) sum += hist[tid * per + c];
+  int incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < kCsrThreads / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    if (lane < kCsrThreads / 32) s_warp[lane] = v;
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+  for (int c = 0; c < per; c++) {
+    const int cnt = hist[tid * per + c];
+    hist[tid * per + c] = run;  // fill cursor; after the scatter it is the END of row c's list
+    run += cnt;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kCsrRegs; k++)
+    if ((unsigned)rel[k] < (unsigned)rows) perm[atomicAdd(&hist[rel[k]], 1)] = (unsigned short)(k * kCsrThreads + tid);
+  __syncthreads();
+
+  // One row per thread and iteration.  The loads of a row form a chain three deep (own index -> neighbour's
+  // coordinates; list bounds -> list entries -> their gradients and coordinates), so the inputs of the NEXT row are
+  // requested before the current row's chain is walked, and the first four list entries (lists average one entry)
+  // are gathered together and then summed in ascending source order; longer lists continue one entry at a time.
+  struct Row {
+    float px, py, pz, g;
+    int q, e0, e1;
+  };
+  auto load_row = [&](int r) {
+    Row w;
+    const int j = j0 + r;
+    w.px = __ldg(Ps + (size_t)j * 3 + 0), w.py = __ldg(Ps + (size_t)j * 3 + 1), w.pz = __ldg(Ps + (size_t)j * 3 + 2);
+    w.q = __ldg(Is + j);
+    w.g = __ldg(Gs + j) * 2;
+    w.e0 = r ? hist[r - 1] : 0;
+    w.e1 = hist[r];
+    return w;
+  };
+  Row cur;
+  if (tid < rows) cur = load_row(tid);
+  for (int r = tid; r < rows; r += kCsrThreads) {
+    const Row w = cur;
+    if (r + kCsrThreads < rows) cur = load_row(r + kCsrThreads);
+    const int len = w.e1 - w.e0;
+    int ent[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) ent[t] = t < len ? (int)perm[w.e0 + t] : 0x7fffffff;
+    if (len > 4 && len <= kCsrOrdered) {  // keep the four smallest here, in order; the loop below continues above them
+#pragma unroll 1
+      for (int e = w.e0 + 4; e < w.e1; e++) {
+        int v = perm[e];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (v < ent[t]) { const int o = ent[t]; ent[t] = v; v = o; }
+      }
+    }
+    // ascending order of the four (sorting network; absent entries are INT_MAX and sink to the end)
+    auto cswap = [](int &a, int &c) { const int lo = min(a, c), hi = max(a, c); a = lo; c = hi; };
+    cswap(ent[0], ent[1]); cswap(ent[2], ent[3]); cswap(ent[0], ent[2]); cswap(ent[1], ent[3]); cswap(ent[1], ent[2]);
+    float ox = __ldg(Po + (size_t)w.q * 3 + 0), oy = __ldg(Po + (size_t)w.q * 3 + 1), oz = __ldg(Po + (size_t)w.q * 3 + 2);
+    float gi[4], qx[4], qy[4], qz[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int i = t < len ? ent[t] : 0;  // a valid address for absent entries; their terms are not added
+      gi[t] = __ldg(Go + i) * 2;
+      qx[t] = __ldg(Po + (size_t)i * 3 + 0), qy[t] = __ldg(Po + (size_t)i * 3 + 1), qz[t] = __ldg(Po + (size_t)i * 3 + 2);
+    }
+    float ax = w.g * (w.px - ox), ay = w.g * (w.py - oy), az = w.g * (w.pz - oz);
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+      if (t < len) {
+        ax -= gi[t] * (qx[t] - w.px);
+        ay -= gi[t] * (qy[t] - w.py);
+        az -= gi[t] * (qz[t] - w.pz);
+      }
+    if (len > 4) {
+      auto add = [&](int i) {
+        const float g2 = __ldg(Go + i) * 2;
+        ax -= g2 * (__ldg(Po + (size_t)i * 3 + 0) - w.px);
+        ay -= g2 * (__ldg(Po + (size_t)i * 3 + 1) - w.py);
+        az -= g2 * (__ldg(Po + (size_t)i * 3 + 2) - w.pz);
+      };
+      if (len <= kCsrOrdered) {
+        int last = ent[3];
+        for (int t = 4; t < len; t++) {  // the smallest entry above the previous one
+          int nxt = 0x7fffffff;
+          for (int e = w.e0; e < w.e1; e++) {
+            const int i = perm[e];
+            if (i > last && i < nxt) nxt = i;
+          }
+          add(nxt);
+          last = nxt;
+        }
+      } else {  // long list (many queries share one neighbour): arrival order, minus the four already added
+        for (int e = w.e0; e < w.e1; e++) {
+          const int i = perm[e];
+          if (i != ent[0] && i != ent[1] && i != ent[2] && i != ent[3]) add(i);
+        }
+      }
+    }
+    const int j = j0 + r;
+    Out[(size_t)j * 3 + 0] = ax;
+    Out[(size_t)j * 3 + 1] = ay;
+    Out[(size_t)j * 3 + 2] = az;
+  }
+}
+
+// rows per CTA: a multiple of kCsrThreads, sized for >= ~3 CTAs per SM where the problem allows
+static int chamfer_grad_csr_rows(int b, int n, int m) {
+  static const int forced = [] {
+    const char *e = getenv("MVP_CHAMFER_BWD_ROWS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced >= kCsrThreads && forced % kCsrThreads == 0) return forced;
+  int R = 4096;  // two CTAs of 512 threads are resident per SM: halve R until the grid fills one such wave
+  while (R > kCsrThreads && (long long)b * (((n + R - 1) / R) + ((m + R - 1) / R)) < (long long)kNumSMs) R >>= 1;
+  return R;
+}
+
+static bool chamfer_grad_csr_supported(int b, int n, int m) {
+  static const bool off = getenv("MVP_CHAMFER_BWD_ATOMIC") != nullptr;  // tuning aid: the two-pass reduction kernels
+  return !off && b <= 65535 && n <= kCsrMaxPts && m <= kCsrMaxPts;
+}
+
+static int chamfer_grad_csr_launch(int b, int n, int m, const float *xyz1, const float *xyz2, const float *gd1,
+                                   const float *gd2, const int *idx1, const int *idx2, float *gx1, float *gx2,
+                                   cudaStream_t s) {
+  const int R = chamfer_grad_csr_rows(b, n, m);
+  const size_t smem = sizeof(int) * (size_t)(R + 1) + sizeof(unsigned short) * (size_t)std::max(n, m);
+  static size_t granted[kMaxDevices];
+  const int rc = grant_dyn_smem(chamfer_grad_csr_kernel, smem, granted);
+  if (rc) return rc;
+  const int parts = (std::max(n, m) + R - 1) / R;
+  chamfer_grad_csr_kernel<<<dim3(parts, 2, b), kCsrThreads, smem, s>>>(n, m, R, xyz1, xyz2, gd1, gd2, idx1, idx2, gx1,
+                                                                      gx2);
+  count_launch();
+  return launch_status();
+}
+
 }  // namespace mvp
 
 using namespace mvp;
@@ -270,6 +475,11 @@ bool chamfer_grid_supported(int b, int n, int m);
 size_t chamfer_grid_workspace_bytes(int b, int n, int m);
 int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
                         float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
+// chamfer_dense.cu
+bool chamfer_dense_supported(int b, int n, int m);
+size_t chamfer_dense_workspace_bytes(int b, int n, int m);
+int chamfer_dense_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                         float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
 }  // namespace mvp
 
 MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
@@ -277,6 +487,7 @@ MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
   size_t need = 16;  // one size serves every algorithm, so the caller need not know which one runs
   if (chamfer_fused_supported(b, n, m)) need = std::max(need, chamfer_fused_workspace_bytes(b, n, m));
   if (chamfer_grid_supported(b, n, m)) need = std::max(need, chamfer_grid_workspace_bytes(b, n, m));
+  if (chamfer_dense_supported(b, n, m)) need = std::max(need, chamfer_dense_workspace_bytes(b, n, m));
   return need;
 }
 
@@ -284,13 +495,18 @@ MVP_API int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float 
                                      float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
                                      size_t workspace_bytes, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
-  if (algo < MVP_CHAMFER_AUTO || algo > MVP_CHAMFER_GRID) return MVP_ERR_INVALID_ARGUMENT;
+  if (algo < MVP_CHAMFER_AUTO || algo > MVP_CHAMFER_GRID_THREAD) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
   if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;  // the reference reads out of bounds here
   if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool grid_ok = chamfer_grid_supported(b, n, m);
-  if (algo == MVP_CHAMFER_GRID && !grid_ok) return MVP_ERR_INVALID_ARGUMENT;
+  const bool grid_ok = chamfer_grid_supported(b, n, m), dense_ok = chamfer_dense_supported(b, n, m);
+  if ((algo == MVP_CHAMFER_GRID && !grid_ok && !dense_ok) || (algo == MVP_CHAMFER_GRID_THREAD && !grid_ok))
+    return MVP_ERR_INVALID_ARGUMENT;
+  if (dense_ok && (algo == MVP_CHAMFER_AUTO || algo == MVP_CHAMFER_GRID)) {
+    if (!workspace || workspace_bytes < chamfer_dense_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
+    return chamfer_dense_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace, workspace_bytes, s);
+  }
   if (grid_ok && algo != MVP_CHAMFER_BRUTE) {
     if (!workspace || workspace_bytes < chamfer_grid_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
     return chamfer_grid_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace, workspace_bytes, s);
@@ -321,6 +537,8 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
   if (!xyz1 || !xyz2 || !graddist1 || !graddist2 || !idx1 || !idx2 || !gradxyz1 || !gradxyz2)
     return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
+  if (chamfer_grad_csr_supported(b, n, m))
+    return chamfer_grad_csr_launch(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1, gradxyz2, s);
   const long long total = (long long)b * (n + m);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
   auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

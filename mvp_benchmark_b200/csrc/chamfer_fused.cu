@@ -23,10 +23,9 @@
 //   takes the first one whose distance has exactly the winning bit pattern: the lowest index among equal minima,
 //   as the reference's strict `<` scan gives (chamfer3D.cu:36,126).  Costs kBlk/N of pass 1.
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace mvp {
-
-typedef unsigned long long u64;
 
 // Tuning knobs (tools/pair_variants.py builds the alternatives; the defaults are the measured best).
 #ifndef MVP_PAIR_ROWS
@@ -48,34 +47,6 @@ constexpr int kCps = MVP_PAIR_COLS;
 constexpr int kTN = 1024;         // columns per shared-memory tile
 constexpr float kPadRow = 2e19f, kPadCol = -2e19f;  // padding coordinates: any distance to them overflows to +inf
 
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-  u64 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float min3(float a, float b, float c) {
-  float r;
-  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
 // two columns (packed) against one row (duplicated): the reference's contraction, lane by lane
 __device__ __forceinline__ u64 dist2(u64 X, u64 Y, u64 Z, u64 qx, u64 qy, u64 qz) {
 #if MVP_PAIR_SCALAR
@@ -87,32 +58,6 @@ __device__ __forceinline__ u64 dist2(u64 X, u64 Y, u64 Z, u64 qx, u64 qy, u64 qz
   const u64 dx = sub2(X, qx), dy = sub2(Y, qy), dz = sub2(Z, qz);
   return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
 #endif
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 1-D bulk TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 
 template <int WARPS>

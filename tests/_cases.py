@@ -57,28 +57,44 @@ def emd_consistent(x1, x2, dist, asg):
     np.testing.assert_array_max_ulp(dist, ref, maxulp=1)
 
 
-EMD_RACE_RTOL = 1e-2  # mean sqrt(dist) when the reference's own result is a last-writer race (see below)
+# Per-cloud relative error of mean sqrt(dist) allowed where the reference's own result is a last-writer race.
+# MEASURED, not chosen: profiles/r2_emd_c5_parity.json (tools/emd_c5_parity.py on a B200 against the live reference
+# kernels, 264 clouds at C5 and at the models' size) — largest per-cloud error on a raced cloud 2.87e-3, largest
+# difference between two runs of the REFERENCE ITSELF 1.07e-3 (26 of 264 clouds), every race-free cloud bit-identical.
+# The bar is twice the largest measured value.
+EMD_RACE_RTOL = 6e-3
+
+
+def check_emd_clouds(x1, x2, eps, iters, d, a, ref_d, ref_a, name):
+    """Cloud by cloud: identical assignment and dist whenever the cloud is race-free for the reference.  The
+    reference's GetMax lets ANY bidder inside a +-1e-6 window of the target's best increment win — the last writer
+    (emd_cuda.cu:188-191).  The oracle counts those windows per cloud; where one occurred, one coin-flip reroutes the
+    rest of that cloud's auction, so only its mean transport cost is compared (EMD_RACE_RTOL above).  Returns
+    (race-free clouds, raced clouds, largest relative error seen on a raced cloud)."""
+    import oracle
+    oracle.emd_forward(x1, x2, float(eps), int(iters))
+    windows = oracle.emd_last_ambiguous_per_cloud(x1.shape[0])
+    emd_consistent(x1, x2, d, a)
+    worst = 0.0
+    for c in range(x1.shape[0]):
+        if windows[c] == 0:
+            bad = int((a[c] != ref_a[c]).sum())
+            assert bad == 0, f"{name}: race-free cloud {c} differs from the reference in {bad} assignments"
+            eq(d[c], ref_d[c], f"{name} dist of cloud {c}")
+        else:
+            m = np.sqrt(d[c].astype(np.float64)).mean()
+            r = np.sqrt(ref_d[c].astype(np.float64)).mean()
+            worst = max(worst, abs(m - r) / r)
+            assert abs(m - r) <= EMD_RACE_RTOL * r, \
+                f"{name}: cloud {c} mean sqrt(dist) {m} vs reference {r} ({windows[c]} race windows)"
+    return int((windows == 0).sum()), int((windows > 0).sum()), worst
 
 
 def check_emd(impl, c, name):
-    """Identical assignment and dist whenever the input is race-free for the reference.  The reference's
-    GetMax lets ANY bidder inside a +-1e-6 window of the target's best increment win — the last writer
-    (emd_cuda.cu:188-191).  The oracle counts those windows (`emd_last_ambiguous`); when one occurred, one
-    coin-flip reroutes the rest of the auction (198 of 2048 assignments in golden `emd_2048`, although two
-    reference runs agreed with each other), so only the mean transport cost is compared there."""
-    import oracle
-    oracle.emd_forward(c["xyz1"], c["xyz2"], float(c["eps"]), int(c["iters"]))
-    race_free = oracle.emd_last_ambiguous() == 0
     d, a = impl.emd_forward(c["xyz1"], c["xyz2"], c["eps"], c["iters"])
-    emd_consistent(c["xyz1"], c["xyz2"], d, a)
-    same = (a == c["assignment"]).all()
-    if race_free:
+    free, raced, _ = check_emd_clouds(c["xyz1"], c["xyz2"], c["eps"], c["iters"], d, a, c["dist"], c["assignment"], name)
+    if raced == 0:
         assert bool(c["stable"]), f"{name}: race-free input but the reference disagreed with itself"
-        assert same, f"{name}: assignment differs from the reference in {(a != c['assignment']).sum()} places"
-        eq(d, c["dist"], f"{name} dist")
-    elif not same:
-        m, r = np.sqrt(d).mean(), np.sqrt(c["dist"]).mean()
-        assert abs(m - r) <= EMD_RACE_RTOL * r, f"{name}: mean sqrt(dist) {m} vs reference {r} (reference races here)"
     gx = impl.emd_backward(c["xyz1"], c["xyz2"], c["graddist"], c["assignment"])
     close(gx, c["gradxyz1"], f"{name} gradxyz1")
 

@@ -70,7 +70,14 @@ def constant(b, n, seed):
     return np.repeat(p, n, axis=1)
 
 
-KINDS = {"clustered": clustered, "planar": planar, "outliers": outliers, "shifted": shifted, "tiny": tiny,
+def blob(b, n, seed):
+    """A small Gaussian blob inside the unit cube: what PCN's decoder emits at random initialisation (BASELINE config
+    C2) — against a ground-truth cloud that fills the cube, nearly every ground-truth point is far outside it."""
+    rng = np.random.default_rng(seed)
+    return (0.5 + 0.02 * rng.standard_normal((b, n, 3))).astype(np.float32)
+
+
+KINDS = {"blob": blob, "clustered": clustered, "planar": planar, "outliers": outliers, "shifted": shifted, "tiny": tiny,
          "constant": constant, "uniform": uniform, "sphere": sphere, "duplicates": duplicates, "lattice": lattice}
 
 

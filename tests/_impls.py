@@ -101,7 +101,7 @@ class CudaImpl:
         return r if len(r) > 1 else r[0]
 
     # -- ops
-    ALGOS = {"auto": 0, "brute": 1, "grid": 2}
+    ALGOS = {"auto": 0, "brute": 1, "grid": 2, "grid_thread": 3}
 
     def chamfer_forward(self, x1, x2, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr
@@ -131,7 +131,7 @@ class CudaImpl:
                                            self.S()), "mvp_chamfer_backward")
         return self.N(gx1, gx2)
 
-    EMD_ALGOS = {"auto": 0, "brute": 1, "grid": 2}
+    EMD_ALGOS = {"auto": 0, "brute": 1, "grid": 2, "grid_thread": 3}
 
     def emd_forward(self, x1, x2, eps, iters, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr

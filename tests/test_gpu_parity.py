@@ -89,7 +89,7 @@ def test_chamfer_grid_is_bit_identical_to_brute_force(gpu, kind, b, n, m):
     underflowing distances, identical points."""
     x1, x2 = _data.cloud(kind, b, n, 1), _data.cloud(kind, b, m, 2)
     want = gpu.chamfer_forward(x1, x2, algo="brute")
-    for algo in ("grid", "auto"):
+    for algo in ("grid", "grid_thread", "auto"):  # warp-cooperative search, thread-per-query search, the default
         got = gpu.chamfer_forward(x1, x2, algo=algo)
         for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
             _cases.eq(g, w, f"chamfer {algo} vs brute, {kind} {b}x{n}x{m} {nm}")
@@ -149,6 +149,23 @@ def test_chamfer_backward_vs_oracle(gpu, cpu, b, n, m):
     got, want = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2), cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
     _cases.close(got[0], want[0], "gradxyz1")
     _cases.close(got[1], want[1], "gradxyz2")
+
+
+@pytest.mark.parametrize("k1,k2,b,n,m", [("uniform", "constant", 2, 3000, 2048), ("constant", "uniform", 2, 16384, 700),
+                                         ("clustered", "uniform", 3, 4096, 4096), ("lattice", "lattice", 2, 2048, 1000),
+                                         ("uniform", "uniform", 2, 20000, 300), ("uniform", "uniform", 1, 16384, 16385)])
+def test_chamfer_backward_skewed_lists_vs_oracle(gpu, cpu, k1, k2, b, n, m):
+    """The atomic-free backward (one thread sums a gradient row from the transposed index): every query choosing
+    the SAME target (one list of n entries), dense clusters, exact ties — and clouds above 16384 points, which stay on
+    the reduction kernels."""
+    x1, x2 = _data.cloud(k1, b, n, 25), _data.cloud(k2, b, m, 26)
+    rng = np.random.default_rng(2)
+    g1, g2 = rng.random((b, n), dtype=np.float32), rng.random((b, m), dtype=np.float32)
+    _, _, i1, i2 = cpu.chamfer_forward(x1, x2)
+    got, want = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2), cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
+    # a row that sums thousands of terms: the tolerance scales with the magnitude of the terms, not of the result
+    _cases.close(got[0], want[0], "gradxyz1", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[0]).max())))
+    _cases.close(got[1], want[1], "gradxyz2", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[1]).max())))
 
 
 @pytest.mark.parametrize("b,n,m", [(36, 8192, 8192), (20, 16384, 12000), (40, 8191, 8193)])
@@ -256,20 +273,26 @@ def test_emd_grid_is_bit_identical_to_full_scan(gpu, kind1, kind2, b, n, eps, it
         _cases.eq(d, wd, f"emd {algo} vs full scan, {kind1}/{kind2} dist")
 
 
-def test_emd_c5_shape_properties_and_reference(gpu, ref, cuda):
-    """BASELINE config C5 (B=64 is scaled to 8 here to keep the reference leg short), n=8192."""
+def test_emd_c5_against_live_reference(gpu, ref, cuda):
+    """BASELINE config C5 as quoted: B=64, n=8192, eps 0.005, 50 rounds, against the live reference kernels, cloud by
+    cloud (_cases.check_emd_clouds): bit-identical on every race-free cloud, mean cost within the measured bar on the
+    others.  The reference is run twice: clouds on which it disagrees with ITSELF must all be ones the oracle
+    classified as raced."""
     import torch
-    b, n = 8, 8192
+    import oracle
+    b, n = 64, 8192
     x1, x2 = _data.uniform(b, n, 41), _data.uniform(b, n, 42)
     d, a = gpu.emd_forward(x1, x2, 0.005, 50)
-    _cases.emd_consistent(x1, x2, d, a)
-    rd, ra = ref.emd_forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), 0.005, 50)
-    rd, ra = rd.cpu().numpy(), ra.cpu().numpy()
-    frac = (a == ra).mean()
-    m, r = np.sqrt(d).mean(), np.sqrt(rd).mean()
-    print(f"\nEMD n=8192 iters=50: identical assignments {frac:.6f}; mean sqrt(dist) ours {m:.7f} reference {r:.7f}")
-    assert abs(m - r) <= 1e-3 * r
-    assert frac > 0.99
+    t1, t2 = torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)
+    (rd, ra), (rd2, ra2) = ref.emd_forward(t1, t2, 0.005, 50), ref.emd_forward(t1, t2, 0.005, 50)
+    rd, ra, ra2 = rd.cpu().numpy(), ra.cpu().numpy(), ra2.cpu().numpy()
+    free, raced, worst = _cases.check_emd_clouds(x1, x2, 0.005, 50, d, a, rd, ra, "EMD C5")
+    windows = oracle.emd_last_ambiguous_per_cloud(b)
+    unstable = [c for c in range(b) if not (ra[c] == ra2[c]).all()]
+    print(f"\nEMD C5 (64 x 8192, 50 rounds): {free} race-free clouds bit-identical, {raced} raced clouds with mean-cost "
+          f"error <= {worst:.2e}; the reference disagrees with itself on clouds {unstable}")
+    assert free >= 8                                  # the exact branch of the check is exercised
+    assert all(windows[c] > 0 for c in unstable)      # self-disagreement only where the oracle saw a race window
 
 
 def test_emd_input_errors(gpu):

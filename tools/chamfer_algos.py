@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _data  # noqa: E402
 from mvp_benchmark_b200 import _lib as L  # noqa: E402
 
-ALGO = {"brute": 1, "grid": 2}
+ALGO = {"brute": 1, "grid": 2, "grid_thread": 3}
 
 
 def run(algo, a, c, outs, ws):
@@ -53,12 +53,15 @@ def main():
     cases = [("uniform", 32, 16384, 16384), ("sphere", 32, 16384, 16384), ("clustered", 32, 16384, 16384),
              ("planar", 32, 16384, 16384), ("shifted", 32, 16384, 16384), ("constant", 8, 16384, 16384),
              ("uniform", 64, 2048, 2048), ("uniform", 64, 2048, 3072), ("uniform", 64, 2048, 1024),
-             ("sphere", 64, 2048, 2048), ("uniform", 32, 16384, 1024), ("uniform", 4, 2048, 2048)]
+             ("sphere", 64, 2048, 2048), ("uniform", 32, 16384, 1024), ("uniform", 4, 2048, 2048),
+             ("blob", 32, 16384, 16384), ("blob", 32, 16384, 1024)]
     if args.cases:
         cases = [(k, int(b), int(n), int(m)) for k, b, n, m in (c.split(":") for c in args.cases.split(","))]
     out = []
     for kind, b, n, m in cases:
-        a = torch.from_numpy(_data.cloud(kind, b, n, 1)).to(dev)
+        # "blob": PCN at initialisation (BASELINE config C2) — the ground truth fills the unit cube, the prediction is a
+        # small blob inside it
+        a = torch.from_numpy(_data.cloud("uniform" if kind == "blob" else kind, b, n, 1)).to(dev)
         c = torch.from_numpy(_data.cloud(kind, b, m, 2)).to(dev)
         ws = L.workspace(L.lib.mvp_chamfer_forward_workspace_bytes(b, n, m), dev)
         res = {}
@@ -67,8 +70,10 @@ def main():
                     torch.empty(b, n, device=dev, dtype=torch.int32), torch.empty(b, m, device=dev, dtype=torch.int32)]
             ms = time_ms(lambda: run(algo, a, c, outs, ws), reps=args.reps)
             res[algo] = (ms, [o.clone() for o in outs])
-        same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for x, y in zip(res["brute"][1], res["grid"][1]))
+        same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for algo in ("grid", "grid_thread")
+                   for x, y in zip(res["brute"][1], res[algo][1]))
         row = {"kind": kind, "b": b, "n": n, "m": m, "brute_ms": round(res["brute"][0], 4), "grid_ms": round(res["grid"][0], 4),
+               "grid_thread_ms": round(res["grid_thread"][0], 4),
                "speedup": round(res["brute"][0] / res["grid"][0], 2), "identical": bool(same)}
         print(row, flush=True)
         out.append(row)
