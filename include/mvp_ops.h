@@ -58,18 +58,16 @@ int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const float *xyz
                         mvp_stream_t stream);
 
 /* The same operator with the algorithm named explicitly (tests and benchmarks use it; results are
- * bit-identical for all of them):
+ * bit-identical for all three):
  *   MVP_CHAMFER_AUTO  what mvp_chamfer_forward does: GRID when the shape supports it, else BRUTE;
  *   MVP_CHAMFER_BRUTE every pair evaluated (tiled B*N*M argmin, both directions from one evaluation);
  *   MVP_CHAMFER_GRID  exact nearest neighbour through a uniform grid built per cloud, pruned with
- *                     conservative lower bounds (n, m >= 512; MVP_ERR_INVALID_ARGUMENT otherwise): the
- *                     warp-cooperative search of chamfer_dense.cu for clouds of up to 16384 points, the
- *                     thread-per-query search of chamfer_grid.cu above that;
- *   MVP_CHAMFER_GRID_THREAD  the thread-per-query grid search whatever the size (n, m >= 512). */
+ *                     conservative lower bounds; what the search does not finish (far / very dense
+ *                     surroundings, degenerate grids) is completed by a warp-cooperative pass over the rows
+ *                     of the grid (n, m >= 512; MVP_ERR_INVALID_ARGUMENT otherwise). */
 #define MVP_CHAMFER_AUTO 0
 #define MVP_CHAMFER_BRUTE 1
 #define MVP_CHAMFER_GRID 2
-#define MVP_CHAMFER_GRID_THREAD 3
 int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
                              float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
                              size_t workspace_bytes, mvp_stream_t stream);
@@ -81,6 +79,19 @@ int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float *xyz1, c
 int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
                          const float *graddist1, const float *graddist2, const int *idx1,
                          const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream);
+
+/* The same with the algorithm named explicitly:
+ *   MVP_CHAMFER_BWD_AUTO    what mvp_chamfer_backward does: own halves written, scattered halves added with vector
+ *                           reductions (red.global.add.v4/v2.f32) — summation order not deterministic, like the
+ *                           reference's atomics;
+ *   MVP_CHAMFER_BWD_SUMMED  no float atomics: the index is transposed in shared memory and every gradient row is
+ *                           summed by one thread, lists of up to 8 contributions in ascending source order
+ *                           (n, m <= 16384; MVP_ERR_INVALID_ARGUMENT otherwise). */
+#define MVP_CHAMFER_BWD_AUTO 0
+#define MVP_CHAMFER_BWD_SUMMED 1
+int mvp_chamfer_backward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
+                              const float *graddist1, const float *graddist2, const int *idx1,
+                              const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Earth mover's distance, auction approximation.

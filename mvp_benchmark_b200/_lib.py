@@ -37,6 +37,7 @@ def _load():
         "mvp_chamfer_forward": (_c_int, [_c_int] * 3 + [_p] * 7 + [_c_size_t, _p]),
         "mvp_chamfer_forward_algo": (_c_int, [_c_int] * 4 + [_p] * 7 + [_c_size_t, _p]),
         "mvp_chamfer_backward": (_c_int, [_c_int] * 3 + [_p] * 8 + [_p]),
+        "mvp_chamfer_backward_algo": (_c_int, [_c_int] * 4 + [_p] * 8 + [_p]),
         "mvp_emd_forward_workspace_bytes": (_c_size_t, [_c_int] * 2),
         "mvp_emd_forward": (_c_int, [_c_int] * 3 + [_p, _p, _c_float, _c_int, _p, _p, _p, _c_size_t, _p]),
         "mvp_emd_forward_algo": (_c_int, [_c_int] * 4 + [_p, _p, _c_float, _c_int, _p, _p, _p, _c_size_t, _p]),

@@ -118,36 +118,6 @@ int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2,
   return launch_status();
 }
 
-// The left-over pass of the grid path, both directions in one launch.  plan[kPlanNRest] lists (direction * b +
-// cloud) whose left-over points are finished here (clouds handed over wholesale to the fused kernels are not
-// listed); a 1-D grid strides over (list, chunk of 2*256 queries) and leaves at once when there is none.
-__global__ void __launch_bounds__(kChThreads)
-chamfer_rest_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                    float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
-                    int *__restrict__ idx2, const int *__restrict__ list1, const int *__restrict__ list2,
-                    const int *__restrict__ count, const int *__restrict__ plan) {
-  const int nrest = __ldg(plan + kPlanNRest);
-  if (nrest == 0) return;
-  const int big = n > m ? n : m;
-  const int chunks = (big + kChThreads * 2 - 1) / (kChThreads * 2);
-  for (long long w = blockIdx.x; w < (long long)nrest * chunks; w += gridDim.x) {
-    const int e = __ldg(plan + kPlanMap + b + (int)(w / chunks)), chunk = (int)(w % chunks);
-    if (e < b)
-      chamfer_dir_body<2, true>(chunk, e, n, m, xyz1, xyz2, dist1, idx1, list1, count);
-    else
-      chamfer_dir_body<2, true>(chunk, e - b, m, n, xyz2, xyz1, dist2, idx2, list2, count + b);
-  }
-}
-
-int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, const int *plan,
-                        cudaStream_t s) {
-  chamfer_rest_kernel<<<kNumSMs * 4, kChThreads, 0, s>>>(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, list1, list2,
-                                                         count, plan);
-  count_launch();
-  return launch_status();
-}
-
 // Backward (chamfer3D.cu:155-174: g = grad*2; six float atomics per point into pre-zeroed gradients).  Point i of
 // one cloud contributes  v = g (p_i - q_nn(i))  to its OWN gradient row and -v to its neighbour's row in the OTHER
 // cloud.  Every row receives exactly one own contribution, so pass 1 WRITES it with a plain coalesced store (which
@@ -266,7 +236,10 @@ chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const 
 // (native integer atomics: histogram, block scan, scatter of 16-bit source indices), and then each thread produces
 // whole rows: own term + the listed terms, one coalesced 12-byte store per row.  No float atomics, no memset, xyz /
 // idx / grad read once from HBM (the gathers hit L2).  Lists of up to kCsrOrdered entries are summed in ascending
-// source order (deterministic); longer ones in arrival order.
+// source order (deterministic); longer ones in arrival order.  MEASURED SLOWER than the reduction kernels at the headline
+// size (40 us against 32 us at B = 32, N = M = 16384: shared-memory atomics cost 2 cycles per lane, and this kernel needs
+// two per point where the reductions need 1.5 vector REDG) — so it is the opt-in MVP_CHAMFER_BWD_SUMMED, for callers
+// who want gradients without float atomics, not the default.
 constexpr int kCsrThreads = 512;
 constexpr int kCsrRegs = 32;            // other-side indices per thread: clouds of up to 16384 points
 constexpr int kCsrMaxPts = kCsrThreads * kCsrRegs;
@@ -441,8 +414,7 @@ static int chamfer_grad_csr_rows(int b, int n, int m) {
 }
 
 static bool chamfer_grad_csr_supported(int b, int n, int m) {
-  static const bool off = getenv("MVP_CHAMFER_BWD_ATOMIC") != nullptr;  // tuning aid: the two-pass reduction kernels
-  return !off && b <= 65535 && n <= kCsrMaxPts && m <= kCsrMaxPts;
+  return b <= 65535 && n <= kCsrMaxPts && m <= kCsrMaxPts;
 }
 
 static int chamfer_grad_csr_launch(int b, int n, int m, const float *xyz1, const float *xyz2, const float *gd1,
@@ -475,11 +447,6 @@ bool chamfer_grid_supported(int b, int n, int m);
 size_t chamfer_grid_workspace_bytes(int b, int n, int m);
 int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
                         float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
-// chamfer_dense.cu
-bool chamfer_dense_supported(int b, int n, int m);
-size_t chamfer_dense_workspace_bytes(int b, int n, int m);
-int chamfer_dense_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
-                         float *dist2, int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s);
 }  // namespace mvp
 
 MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
@@ -487,7 +454,6 @@ MVP_API size_t mvp_chamfer_forward_workspace_bytes(int b, int n, int m) {
   size_t need = 16;  // one size serves every algorithm, so the caller need not know which one runs
   if (chamfer_fused_supported(b, n, m)) need = std::max(need, chamfer_fused_workspace_bytes(b, n, m));
   if (chamfer_grid_supported(b, n, m)) need = std::max(need, chamfer_grid_workspace_bytes(b, n, m));
-  if (chamfer_dense_supported(b, n, m)) need = std::max(need, chamfer_dense_workspace_bytes(b, n, m));
   return need;
 }
 
@@ -495,18 +461,13 @@ MVP_API int mvp_chamfer_forward_algo(int algo, int b, int n, int m, const float 
                                      float *dist1, float *dist2, int *idx1, int *idx2, void *workspace,
                                      size_t workspace_bytes, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
-  if (algo < MVP_CHAMFER_AUTO || algo > MVP_CHAMFER_GRID_THREAD) return MVP_ERR_INVALID_ARGUMENT;
+  if (algo < MVP_CHAMFER_AUTO || algo > MVP_CHAMFER_GRID) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
   if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;  // the reference reads out of bounds here
   if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool grid_ok = chamfer_grid_supported(b, n, m), dense_ok = chamfer_dense_supported(b, n, m);
-  if ((algo == MVP_CHAMFER_GRID && !grid_ok && !dense_ok) || (algo == MVP_CHAMFER_GRID_THREAD && !grid_ok))
-    return MVP_ERR_INVALID_ARGUMENT;
-  if (dense_ok && (algo == MVP_CHAMFER_AUTO || algo == MVP_CHAMFER_GRID)) {
-    if (!workspace || workspace_bytes < chamfer_dense_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
-    return chamfer_dense_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace, workspace_bytes, s);
-  }
+  const bool grid_ok = chamfer_grid_supported(b, n, m);
+  if (algo == MVP_CHAMFER_GRID && !grid_ok) return MVP_ERR_INVALID_ARGUMENT;
   if (grid_ok && algo != MVP_CHAMFER_BRUTE) {
     if (!workspace || workspace_bytes < chamfer_grid_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
     return chamfer_grid_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, workspace, workspace_bytes, s);
@@ -528,17 +489,20 @@ MVP_API int mvp_chamfer_forward(int b, int n, int m, const float *xyz1, const fl
                                   workspace_bytes, stream);
 }
 
-MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
-                                 const float *graddist1, const float *graddist2, const int *idx1,
-                                 const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream) {
+MVP_API int mvp_chamfer_backward_algo(int algo, int b, int n, int m, const float *xyz1, const float *xyz2,
+                                      const float *graddist1, const float *graddist2, const int *idx1,
+                                      const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (algo < MVP_CHAMFER_BWD_AUTO || algo > MVP_CHAMFER_BWD_SUMMED) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || (n == 0 && m == 0)) return MVP_OK;
   if (n == 0 || m == 0) return MVP_ERR_INVALID_ARGUMENT;
   if (!xyz1 || !xyz2 || !graddist1 || !graddist2 || !idx1 || !idx2 || !gradxyz1 || !gradxyz2)
     return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  if (chamfer_grad_csr_supported(b, n, m))
+  if (algo == MVP_CHAMFER_BWD_SUMMED) {
+    if (!chamfer_grad_csr_supported(b, n, m)) return MVP_ERR_INVALID_ARGUMENT;
     return chamfer_grad_csr_launch(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1, gradxyz2, s);
+  }
   const long long total = (long long)b * (n + m);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
   auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -558,4 +522,11 @@ MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const f
   }
   count_launch(2);
   return launch_status();
+}
+
+MVP_API int mvp_chamfer_backward(int b, int n, int m, const float *xyz1, const float *xyz2,
+                                 const float *graddist1, const float *graddist2, const int *idx1,
+                                 const int *idx2, float *gradxyz1, float *gradxyz2, mvp_stream_t stream) {
+  return mvp_chamfer_backward_algo(MVP_CHAMFER_BWD_AUTO, b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                   gradxyz2, stream);
 }

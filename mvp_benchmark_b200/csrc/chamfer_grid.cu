@@ -57,17 +57,6 @@ constexpr int kGridQThreads = MVP_GRID_QTHREADS;  // query CTA
 #endif
 constexpr int kScanUnroll = MVP_GRID_SCAN_UNROLL;
 
-struct GridWs {  // carved out of the caller's workspace by grid_plan()
-  GridHdr *hdr;        // [2][b]
-  int *count;          // [2][b]  left-over list lengths
-  int *plan;           // kPlan* words (common.cuh): ticket, nflag, nrest, b cloud ids, 2b list ids
-  int *start[2];       // [b][cap_side + 1]
-  float4 *sorted[2];   // [b][n] / [b][m]
-  int *list[2];        // [b][n] / [b][m]
-  unsigned long long *key[2];  // the fused kernels' row / column keys: all-ones here, used only on hand-over
-  int cap[2];
-};
-
 static int grid_cap(int npts) {
   int c = npts / MVP_GRID_PPC;
   c = std::max(c, 8);
@@ -90,7 +79,6 @@ static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
   t.cap[1] = cap1;
   t.hdr = reinterpret_cast<GridHdr *>(take(sizeof(GridHdr) * 2 * (size_t)b));
   t.count = reinterpret_cast<int *>(take(sizeof(int) * 2 * (size_t)b));
-  t.plan = reinterpret_cast<int *>(take(sizeof(int) * (kPlanMap + 3 * (size_t)b)));
   t.start[0] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap0 + 1)));
   t.start[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * (cap1 + 1)));
   t.sorted[0] = reinterpret_cast<float4 *>(take(sizeof(float4) * (size_t)b * n));
@@ -255,12 +243,6 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
   }
   if (tid == 0) start[ncell] = np;
   __syncthreads();
-  {  // keys of the fused brute-force kernels, in case this cloud pair is handed over to them
-    unsigned long long *key = side ? W.key[1] : W.key[0];  // null for three_nn: nothing is handed over wholesale
-    if (key)
-      for (int i = tid; i < np; i += kGridThreads) key[(size_t)cloud * np + i] = ~0ull;
-  }
-
   // ---- pass 3: scatter (order inside a cell is arbitrary; the query's tie rule is explicit)
   float4 *S = (side ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * np;
   for (int i0 = tid; i0 < np; i0 += kBatch * kGridThreads) {
@@ -498,11 +480,6 @@ chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, 
   if (rank == 0 && tid == 0) start[ncell] = np;
   __syncthreads();
   MVP_B2_STAMP(7);
-  {  // keys of the fused brute-force kernels, in case this cloud pair is handed over to them
-    unsigned long long *key = side ? W.key[1] : W.key[0];
-    if (key)
-      for (int j = tid; j < mine; j += kGridThreads) key[(size_t)cloud * np + first + j] = ~0ull;
-  }
 
   MVP_B2_STAMP(8);
   // ---- pass 3: scatter this half (order inside a cell is arbitrary; the query's tie rule is explicit)
@@ -768,6 +745,10 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
       }
     }
   } else {
+    if (K == 1 && !kRT) {  // what was found before giving up: the completion pass (chamfer_rest.cu) starts from this bound
+      dist[orig] = bd[0];
+      idx[orig] = bk[0];
+    }
     // append to the left-over list of (direction, cloud): one atomic per group of lanes sharing the list
     const int li = dir * b + cloud;
     const unsigned peers = __match_any_sync(__activemask(), li);
@@ -781,58 +762,21 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
 
 }
 
-// ------------------------------------------------------------------------------------------------ plan
-// Decides who completes the left-over points (one small CTA; a separate launch because finding "the last CTA of
-// the query kernel" needs a device-scope fence per CTA, which measured +100 us on the query kernel).
-__global__ void __launch_bounds__(256)
-chamfer_grid_plan_kernel(int b, int n, int m, GridWs W) {
-  __shared__ int s_nflag, s_nrest;
-  if (threadIdx.x == 0) s_nflag = s_nrest = 0;
-  __syncthreads();
-  // a cloud pair with more than a quarter of its points left over is cheaper in the fused brute-force kernels
-  // (each pair evaluated once for both directions) than in the per-direction left-over pass
-  const int thresh = (int)(((long long)n + m) / 4);
-  for (int c = threadIdx.x; c < b; c += 256) {
-    const int l0 = W.count[c], l1 = W.count[b + c];
-    if (l0 + l1 > thresh) {
-      W.plan[kPlanMap + atomicAdd(&s_nflag, 1)] = c;
-    } else {
-      if (l0) W.plan[kPlanMap + b + atomicAdd(&s_nrest, 1)] = c;
-      if (l1) W.plan[kPlanMap + b + atomicAdd(&s_nrest, 1)] = b + c;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    W.plan[kPlanNFlag] = s_nflag;
-    W.plan[kPlanNRest] = s_nrest;
-  }
-}
-
-// chamfer.cu
-int chamfer_rest_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                        int *idx1, int *idx2, const int *list1, const int *list2, const int *count, const int *plan,
-                        cudaStream_t s);
-// chamfer_fused.cu
-size_t chamfer_fused_workspace_bytes(int b, int n, int m);
-int chamfer_fused_launch_plan(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                              int *idx1, int *idx2, void *ws, size_t ws_bytes, const int *plan, cudaStream_t s);
+// chamfer_rest.cu: the completion pass over the left-over lists
+int chamfer_rest_launch(int b, int n, int m, const GridWs &W, const float *xyz1, const float *xyz2, float *dist1,
+                        float *dist2, int *idx1, int *idx2, cudaStream_t s);
 
 bool chamfer_grid_supported(int b, int n, int m) {
   return b > 0 && b <= 65535 && n >= 512 && m >= 512 && n <= (1 << 20) && m <= (1 << 20) &&
          (long long)b * ((long long)n + m) < (1LL << 31);
 }
 
-size_t chamfer_grid_workspace_bytes(int b, int n, int m) {
-  return grid_plan(b, n, m, nullptr, nullptr) + chamfer_fused_workspace_bytes(b, n, m);  // + the hand-over's keys
-}
+size_t chamfer_grid_workspace_bytes(int b, int n, int m) { return grid_plan(b, n, m, nullptr, nullptr); }
 
 int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
                         int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
   GridWs W;
-  const size_t grid_bytes = grid_plan(b, n, m, ws, &W), key_bytes = chamfer_fused_workspace_bytes(b, n, m);
-  if (ws_bytes < grid_bytes + key_bytes) return MVP_ERR_WORKSPACE;
-  W.key[0] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ws) + grid_bytes);
-  W.key[1] = W.key[0] + (size_t)b * n;
+  if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
   {
     const int rc = grid_build_launch(b, n, m, xyz1, xyz2, W, s);
     if (rc) return rc;
@@ -840,16 +784,11 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
   const long long total = (long long)b * ((long long)n + m);
   chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
       b, n, m, W, dist1, dist2, idx1, idx2, 1);
-  chamfer_grid_plan_kernel<<<1, 256, 0, s>>>(b, n, m, W);
-  count_launch(3);
-  int rc = launch_status();
+  count_launch(2);
+  const int rc = launch_status();
   if (rc) return rc;
-  // hand-over: whole cloud pairs to the fused brute-force kernels, scattered left-over points to the tiled pass;
-  // all of these leave at once when the plan is empty
-  rc = chamfer_fused_launch_plan(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2,
-                                 reinterpret_cast<unsigned char *>(ws) + grid_bytes, key_bytes, W.plan, s);
-  if (rc) return rc;
-  return chamfer_rest_launch(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, W.list[0], W.list[1], W.count, W.plan, s);
+  // what the search did not finish (normally nothing: the kernel leaves at once)
+  return chamfer_rest_launch(b, n, m, W, xyz1, xyz2, dist1, dist2, idx1, idx2, s);
 }
 
 // ---- three_nn through the same grid (pointnet2.cu: mvp_three_nn_ws) --------------------------------------------------
@@ -870,7 +809,6 @@ int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float 
                          size_t ws_bytes, cudaStream_t s) {
   GridWs W;
   if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
-  W.key[0] = W.key[1] = nullptr;
   {
     const int rc = grid_build_launch(b, n, m, unknown, known, W, s);
     if (rc) return rc;
@@ -961,8 +899,7 @@ static int knn_points_launch_k(int b, int n, int m, int k, const float *queries,
   if (knn_points_grid_supported(b, n, m, k) && ws && ws_bytes >= grid_plan(b, n, m, nullptr, nullptr)) {
     GridWs W;
     grid_plan(b, n, m, ws, &W);
-    W.key[0] = W.key[1] = nullptr;
-    {
+      {
       const int rc = grid_build_launch(b, n, m, queries, cloud, W, s);
       if (rc) return rc;
     }

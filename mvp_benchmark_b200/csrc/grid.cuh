@@ -12,7 +12,7 @@ struct __align__(16) GridHdr {
   int g[3];      // cells per axis; x is the fastest-varying cell coordinate
   int ncell;
   int valid;     // 0: non-finite coordinates or degenerate extent -> one cell, no pruning possible
-  int pad[6];
+  int pad[6];    // pad[0] = 1: every point of the cloud is the same (finite) point
 };
 static_assert(sizeof(GridHdr) == 64, "GridHdr layout");
 
@@ -82,7 +82,19 @@ __device__ inline GridHdr grid_header(const float lo[3], const float hi[3], int 
   h.ncell = h.g[0] * h.g[1] * h.g[2];
 #pragma unroll
   for (int a = 0; a < 6; a++) h.pad[a] = 0;
+  h.pad[0] = (fin && emax == 0.f) ? 1 : 0;
   return h;
 }
+
+// Workspace of the grid-pruned searches (chamfer_grid.cu: Chamfer, three_nn, mvp_knn_points), carved out of the
+// caller's buffer by grid_plan(); also what the completion pass (chamfer_rest.cu) works on.
+struct GridWs {  // carved out of the caller's workspace by grid_plan()
+  GridHdr *hdr;        // [2][b]
+  int *count;          // [2][b]  left-over list lengths
+  int *start[2];       // [b][cap_side + 1]
+  float4 *sorted[2];   // [b][n] / [b][m]
+  int *list[2];        // [b][n] / [b][m]
+  int cap[2];
+};
 
 }  // namespace mvp

@@ -101,7 +101,7 @@ class CudaImpl:
         return r if len(r) > 1 else r[0]
 
     # -- ops
-    ALGOS = {"auto": 0, "brute": 1, "grid": 2, "grid_thread": 3}
+    ALGOS = {"auto": 0, "brute": 1, "grid": 2}
 
     def chamfer_forward(self, x1, x2, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr
@@ -120,18 +120,20 @@ class CudaImpl:
         L.check(rc, "mvp_chamfer_forward")
         return self.N(d1, d2, i1, i2)
 
-    def chamfer_backward(self, x1, x2, g1, g2, i1, i2):
+    BWD_ALGOS = {"auto": 0, "summed": 1}
+
+    def chamfer_backward(self, x1, x2, g1, g2, i1, i2, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr
         a, c = self.T(x1), self.T(x2)
         b, n, _ = a.shape
         m = c.shape[1]
         gx1, gx2 = self.E((b, n, 3), t.float32), self.E((b, m, 3), t.float32)
         tg1, tg2, ti1, ti2 = self.T(g1), self.T(g2), self.T(i1), self.T(i2)  # keep alive across the call
-        L.check(L.lib.mvp_chamfer_backward(b, n, m, p(a), p(c), p(tg1), p(tg2), p(ti1), p(ti2), p(gx1), p(gx2),
-                                           self.S()), "mvp_chamfer_backward")
+        L.check(L.lib.mvp_chamfer_backward_algo(self.BWD_ALGOS[algo], b, n, m, p(a), p(c), p(tg1), p(tg2), p(ti1), p(ti2),
+                                                p(gx1), p(gx2), self.S()), "mvp_chamfer_backward")
         return self.N(gx1, gx2)
 
-    EMD_ALGOS = {"auto": 0, "brute": 1, "grid": 2, "grid_thread": 3}
+    EMD_ALGOS = {"auto": 0, "brute": 1, "grid": 2}
 
     def emd_forward(self, x1, x2, eps, iters, algo="auto"):
         t, L, p = self.torch, self.L, self.L.ptr

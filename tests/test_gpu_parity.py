@@ -89,7 +89,7 @@ def test_chamfer_grid_is_bit_identical_to_brute_force(gpu, kind, b, n, m):
     underflowing distances, identical points."""
     x1, x2 = _data.cloud(kind, b, n, 1), _data.cloud(kind, b, m, 2)
     want = gpu.chamfer_forward(x1, x2, algo="brute")
-    for algo in ("grid", "grid_thread", "auto"):  # warp-cooperative search, thread-per-query search, the default
+    for algo in ("grid", "auto"):
         got = gpu.chamfer_forward(x1, x2, algo=algo)
         for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
             _cases.eq(g, w, f"chamfer {algo} vs brute, {kind} {b}x{n}x{m} {nm}")
@@ -101,6 +101,18 @@ def test_chamfer_grid_vs_oracle_hostile(gpu, cpu, kind):
     got, want = gpu.chamfer_forward(x1, x2, algo="grid"), cpu.chamfer_forward(x1, x2)
     for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
         _cases.eq(g, w, f"chamfer grid vs oracle {kind} {nm}")
+
+
+@pytest.mark.parametrize("b,n,m", [(4, 16384, 1024), (3, 16384, 16384), (2, 2048, 2048), (2, 1024, 16384)])
+def test_chamfer_grid_pcn_initialisation_geometry(gpu, b, n, m):
+    """BASELINE config C2's Chamfer calls with the geometry PCN has at random initialisation: the ground truth fills the
+    unit cube, the prediction is a small blob inside it — nearly every ground-truth point is far outside the blob's
+    grid and is finished by the completion pass (chamfer_rest.cu), not by the grid search."""
+    x1, x2 = _data.uniform(b, n, 71), _data.blob(b, m, 72)
+    want = gpu.chamfer_forward(x1, x2, algo="brute")
+    got = gpu.chamfer_forward(x1, x2, algo="grid")
+    for g, w, nm in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+        _cases.eq(g, w, f"chamfer grid vs brute, cube vs blob {b}x{n}x{m} {nm}")
 
 
 def test_chamfer_grid_mixed_pair_kinds(gpu):
@@ -155,17 +167,24 @@ def test_chamfer_backward_vs_oracle(gpu, cpu, b, n, m):
                                          ("clustered", "uniform", 3, 4096, 4096), ("lattice", "lattice", 2, 2048, 1000),
                                          ("uniform", "uniform", 2, 20000, 300), ("uniform", "uniform", 1, 16384, 16385)])
 def test_chamfer_backward_skewed_lists_vs_oracle(gpu, cpu, k1, k2, b, n, m):
-    """The atomic-free backward (one thread sums a gradient row from the transposed index): every query choosing
-    the SAME target (one list of n entries), dense clusters, exact ties — and clouds above 16384 points, which stay on
-    the reduction kernels."""
+    """Both backward algorithms — the default (vector reductions) and MVP_CHAMFER_BWD_SUMMED (no float atomics: one
+    thread sums a gradient row from the transposed index) — on skewed neighbour lists: every query choosing the SAME
+    target (one list of n entries), dense clusters, exact ties; above 16384 points only the default exists."""
     x1, x2 = _data.cloud(k1, b, n, 25), _data.cloud(k2, b, m, 26)
     rng = np.random.default_rng(2)
     g1, g2 = rng.random((b, n), dtype=np.float32), rng.random((b, m), dtype=np.float32)
     _, _, i1, i2 = cpu.chamfer_forward(x1, x2)
-    got, want = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2), cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
-    # a row that sums thousands of terms: the tolerance scales with the magnitude of the terms, not of the result
-    _cases.close(got[0], want[0], "gradxyz1", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[0]).max())))
-    _cases.close(got[1], want[1], "gradxyz2", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[1]).max())))
+    want = cpu.chamfer_backward(x1, x2, g1, g2, i1, i2)
+    for algo in ("auto", "summed") if max(n, m) <= 16384 else ("auto",):
+        got = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2, algo=algo)
+        # a row that sums thousands of terms: the tolerance scales with the magnitude of the terms, not of the result
+        _cases.close(got[0], want[0], f"gradxyz1 {algo}", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[0]).max())))
+        _cases.close(got[1], want[1], f"gradxyz2 {algo}", rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(want[1]).max())))
+    if max(n, m) <= 16384:  # summed twice: bit-identical (ascending source order for lists of up to 8 entries)
+        again = gpu.chamfer_backward(x1, x2, g1, g2, i1, i2, algo="summed")
+        if (k1, k2) == ("uniform", "uniform"):  # (longer lists — clusters, coincident points — are summed in arrival order)
+            _cases.eq(again[0], got[0], "summed backward is reproducible (gradxyz1)")
+            _cases.eq(again[1], got[1], "summed backward is reproducible (gradxyz2)")
 
 
 @pytest.mark.parametrize("b,n,m", [(36, 8192, 8192), (20, 16384, 12000), (40, 8191, 8193)])

@@ -14,8 +14,8 @@ for kind, b, n, m in [("uniform", 32, 16384, 16384), ("uniform", 64, 2048, 2048)
     P = L.ptr
     L.check(L.lib.mvp_chamfer_forward_algo(2, b, n, m, P(a), P(c), P(d1), P(d2), P(i1), P(i2), P(ws), ws.numel(), s), "f")
     torch.cuda.synchronize()
-    raw = ws[: 2 * b * 64 + 2 * b * 4].cpu().numpy()
-    hdr = raw[: 2 * b * 64].view(np.int32).reshape(2 * b, 16)
-    cnt = raw[2 * b * 64:].view(np.int32)
+    raw = ws[: b * 64 + 2 * b * 4].cpu().numpy()
+    hdr = raw[: b * 64].view(np.int32).reshape(b, 16)
+    cnt = raw[b * 64:].view(np.int32)
     print(kind, b, n, m, "leftover total", cnt.sum(), "max", cnt.max(), "first", cnt[:6])
-    print(" hdr0 g", hdr[0, 5:8], "ncell", hdr[0, 8], "valid", hdr[0, 9], "blocks", hdr[0, 10:13], "s", hdr[0, 4:5].view(np.float32))
+    print(" hdr0 g", hdr[0, 5:8], "ncell", hdr[0, 8], "valid", hdr[0, 9], "blocks", hdr[0, 10:16], "s", hdr[0, 4:5].view(np.float32))

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _data  # noqa: E402
 from mvp_benchmark_b200 import _lib as L  # noqa: E402
 
-ALGO = {"brute": 1, "grid": 2, "grid_thread": 3}
+ALGO = {"brute": 1, "grid": 2}
 
 
 def run(algo, a, c, outs, ws):
@@ -70,10 +70,8 @@ def main():
                     torch.empty(b, n, device=dev, dtype=torch.int32), torch.empty(b, m, device=dev, dtype=torch.int32)]
             ms = time_ms(lambda: run(algo, a, c, outs, ws), reps=args.reps)
             res[algo] = (ms, [o.clone() for o in outs])
-        same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for algo in ("grid", "grid_thread")
-                   for x, y in zip(res["brute"][1], res[algo][1]))
+        same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for x, y in zip(res["brute"][1], res["grid"][1]))
         row = {"kind": kind, "b": b, "n": n, "m": m, "brute_ms": round(res["brute"][0], 4), "grid_ms": round(res["grid"][0], 4),
-               "grid_thread_ms": round(res["grid_thread"][0], 4),
                "speedup": round(res["brute"][0] / res["grid"][0], 2), "identical": bool(same)}
         print(row, flush=True)
         out.append(row)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _data  # noqa: E402
 from mvp_benchmark_b200 import _lib as L  # noqa: E402
 
-ALGO = {"auto": 0, "brute": 1, "grid": 2, "grid_thread": 3}
+ALGO = {"auto": 0, "brute": 1, "grid": 2}
 
 
 def main():
