@@ -85,6 +85,12 @@ static size_t grid_plan(int b, int n, int m, void *base, GridWs *w) {
   t.sorted[1] = reinterpret_cast<float4 *>(take(sizeof(float4) * (size_t)b * m));
   t.list[0] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * n));
   t.list[1] = reinterpret_cast<int *>(take(sizeof(int) * (size_t)b * m));
+  for (int side = 0; side < 2; side++) {
+    const int nleaf = ((side ? m : n) + 31) / 32, nl1 = (nleaf + 31) / 32, nl2 = (nl1 + 31) / 32;
+    t.nleaf[side] = nleaf;
+    t.box[side] = reinterpret_cast<float4 *>(take(sizeof(float4) * 2 * (size_t)b * (nleaf + nl1 + nl2)));
+  }
+  t.plan = reinterpret_cast<int *>(take(sizeof(int) * (kPlanItems + 2 * (size_t)rest_plan_cap(b, n, m))));
   if (w) *w = t;
   return off;
 }
@@ -172,6 +178,7 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
     s_hdr = h;
     W.hdr[side * b + cloud] = h;
     W.count[side * b + cloud] = 0;
+    if (cloud == 0 && side == 0) W.plan[kPlanTotal] = 0, W.plan[kPlanTicket2] = 0, W.plan[kPlanTotalB] = 0, W.plan[kPlanTicketB] = 0;
   }
   __syncthreads();
   const GridHdr h = s_hdr;
@@ -377,6 +384,7 @@ chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, 
     if (rank == 0) {
       W.hdr[side * b + cloud] = h;
       W.count[side * b + cloud] = 0;
+      if (cloud == 0 && side == 0) W.plan[kPlanTotal] = 0, W.plan[kPlanTicket2] = 0, W.plan[kPlanTotalB] = 0, W.plan[kPlanTicketB] = 0;
     }
   }
   __syncthreads();

@@ -88,6 +88,10 @@ __device__ inline GridHdr grid_header(const float lo[3], const float hi[3], int 
 
 // Workspace of the grid-pruned searches (chamfer_grid.cu: Chamfer, three_nn, mvp_knn_points), carved out of the
 // caller's buffer by grid_plan(); also what the completion pass (chamfer_rest.cu) works on.
+// plan words of the completion pass: two lists of work items (A: lanes over queries, B: a warp per query), each with
+// its length and the number of items drawn so far; list A's items at kPlanItems, list B's rest_plan_cap() further on
+constexpr int kPlanTotal = 0, kPlanTicket2 = 1, kPlanTotalB = 2, kPlanTicketB = 3, kPlanItems = 4;
+inline int rest_plan_cap(int b, int n, int m) { return b * (n / 32 + m / 32 + 2); }
 struct GridWs {  // carved out of the caller's workspace by grid_plan()
   GridHdr *hdr;        // [2][b]
   int *count;          // [2][b]  left-over list lengths
@@ -95,6 +99,10 @@ struct GridWs {  // carved out of the caller's workspace by grid_plan()
   float4 *sorted[2];   // [b][n] / [b][m]
   int *list[2];        // [b][n] / [b][m]
   int cap[2];
+  // completion pass (chamfer_rest.cu): bounding boxes over runs of the sorted array and the list of work items
+  float4 *box[2];      // [b][2 * (nleaf + nl1 + nl2)]  (lo, hi) pairs: leaves, then level 1, then level 2
+  int *plan;           // [kPlanTotal] number of work items, [kPlanTicket2] items drawn, [kPlanItems...] (list << 15) | chunk of 32 list entries
+  int nleaf[2];        // leaves per cloud: ceil(points / 32)
 };
 
 }  // namespace mvp

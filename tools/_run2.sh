@@ -1,3 +1,7 @@
-python tools/chamfer_step.py --kind uniform --kind2 blob --steps 1 --b 2 --no-backward 2>&1 | tail -3
-compute-sanitizer --tool memcheck --print-limit 3 python tools/chamfer_step.py --kind uniform --kind2 blob --steps 1 --b 2 --no-backward 2>&1 | grep -v "Host Frame\|^=========$" | head -24
-compute-sanitizer --tool racecheck --print-limit 3 python tools/chamfer_step.py --kind uniform --kind2 blob --steps 1 --b 1 --no-backward 2>&1 | grep -v "Host Frame\|^=========$" | head -24
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "chamfer" 2>&1 | tail -3
+CASES=clustered:32:16384:16384,shifted:32:16384:16384,blob:32:16384:16384,blob:32:16384:1024,outliers:32:16384:16384,constant:8:16384:16384,uniform:32:16384:16384,sphere:32:16384:16384,planar:32:16384:16384
+timeout 300 python tools/chamfer_algos.py --reps 10 --cases $CASES --json gpurun_out/r2_chamfer_algos_d.json 2>&1 | tail -9
+for k in shifted:shifted uniform:blob clustered:clustered; do
+k1=${k%%:*}; k2=${k##*:}
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_$k2.csv python tools/chamfer_step.py --steps 2 --no-backward --kind $k1 --kind2 $k2 > /dev/null 2>&1
+done
