@@ -250,6 +250,25 @@ def run(dev, hbm_gbs=None):
     entry("chamfer_fwd_bwd_vrcnet_4calls_B64", _time(ours_cd4), _time(ref_cd4) if have_ref else None,
           64.0 * 2048 * (1024 + 3072 + 2048 + 2048), "point-pairs/s")
 
+    # ---- BASELINE config C2 with the geometry PCN has at random initialisation: the ground truth fills the unit cube,
+    # the prediction is a small blob inside it (completion/models/pcn.py:99-100: CD(gt 16384, coarse 1024) +
+    # CD(gt 16384, fine 16384)) — nearly every ground-truth point is far outside the prediction's grid and is finished
+    # by the bounding-box hierarchy of chamfer_rest.cu.  Forward only (the backward does not depend on the geometry).
+    gt16 = R(32, 16384, 3)
+    for tag, mm_ in (("coarse1024", 1024), ("fine16384", 16384)):
+        blob = (0.5 + 0.02 * torch.randn(32, mm_, 3, device=dev, generator=g)).contiguous()
+        entry(f"chamfer_fwd_pcn_init_32x16384_{tag}", _time(lambda: cd(gt16, blob), 10),
+              _time(lambda: ref_cuda.chamfer_forward(gt16, blob), 5) if have_ref else None,
+              32.0 * 16384 * mm_, "point-pairs/s", 20.0 * 32 * (16384 + mm_))
+    # ... and two more hostile geometries at the headline size: disjoint clouds, a sphere surface
+    far = (R(32, 16384, 3) + 3.0).contiguous()
+    entry("chamfer_fwd_disjoint_32x16384x16384", _time(lambda: cd(x1, far), 10),
+          _time(lambda: ref_cuda.chamfer_forward(x1, far), 5) if have_ref else None,
+          32.0 * 16384 * 16384, "point-pairs/s", 20.0 * 32 * 2 * 16384)
+    sp = [torch.nn.functional.normalize(torch.randn(32, 16384, 3, device=dev, generator=g), dim=2) * 0.5 + 0.5 for _ in range(2)]
+    entry("chamfer_fwd_sphere_32x16384x16384", _time(lambda: cd(sp[0].contiguous(), sp[1].contiguous()), 10), None,
+          32.0 * 16384 * 16384, "point-pairs/s", 20.0 * 32 * 2 * 16384)
+
     # ---- EMD, config C5: B=64, n=8192, eps 0.005, 50 rounds (forward; the backward is a trivial gather)
     e1, e2 = R(64, 8192, 3), R(64, 8192, 3)
     emd = metrics.emd()
@@ -264,6 +283,12 @@ def run(dev, hbm_gbs=None):
     entry("emd_forward_32x2048_iters50", _time(lambda: emd(e1s, e2s, 0.005, 50), 5, 2),
           _time(lambda: ref_cuda.emd_forward(e1s, e2s, 0.005, 50), 5, 2) if have_ref else None,
           32.0 * 2048 * 2048, "point-pairs/s", 32.0 * 32 * 2048)
+
+    # ---- mm3d knn (QueryAndGroup's neighbourhood when max_radius is None): centres = the cloud
+    for (bb, nn, pp, kk) in [(64, 2048, 512, 16), (32, 4096, 1024, 32), (16, 8192, 2048, 64), (16, 4096, 1024, 100)]:
+        x, c = R(bb, nn, 3), R(bb, pp, 3)
+        entry(f"knn_{bb}x{nn}_centres{pp}_k{kk}", _time(lambda: mm.knn(kk, x, c, False), 5),
+              _time(lambda: ref_cuda.knn(kk, x, c), 5) if have_ref else None, float(bb) * pp * nn, "point-pairs/s")
 
     # ---- FPS at the VRCNet sizes
     for (bb, nn, mm_) in [(32, 2048, 2048), (64, 3072, 2048), (64, 3072, 1536), (64, 1536, 768), (64, 768, 384)]:

@@ -475,6 +475,175 @@ fps_big_kernel(int n, int m, int log2T, const float *__restrict__ data, float *_
   }
 }
 
+// ---- one cloud split over a CLUSTER of C CTAs (xyz input) ------------------------------------------------------------------
+// One CTA per cloud leaves 148 - B SMs idle and makes every pick wait for P distance updates per thread.  Here C CTAs
+// share a cloud: CTA r owns the points k = (i C + r) TB + tid, so a pick costs P / C updates per thread; every warp
+// then sends its (max, key) slot to ALL C CTAs through distributed shared memory — st.async with mbarrier complete_tx,
+// so the data and its arrival signal travel together — and every CTA reduces the C x TB/32 slots redundantly after
+// waiting on its OWN mbarrier: no cluster-wide barrier (380 cycles + an L1 flush), one DSMEM hop (~215 cycles) per pick.
+// Slots and mbarriers are double-buffered by pick parity: a CTA can be at most one pick ahead of its peers.
+// Same picks, bit for bit (keys are those of the original indices).  MVP_FPS_CLUSTER=2|4 selects it; the measured
+// table is in DESIGN.md §4.4: the hop costs more than the halved update saves at these cloud sizes.
+template <int TB, int P, int C>
+__global__ void __launch_bounds__(TB)
+fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
+                   int *__restrict__ idxs) {
+  static_assert(P % 2 == 0 && C * (TB / 32) <= 32, "packed pairs; the slots of a pick fit one warp");
+  constexpr int NW = TB / 32;
+  extern __shared__ __align__(16) float4 s_pts[];
+  __shared__ __align__(8) unsigned long long s_slot[2][32];  // (max bits << 32) | key, one per warp of the cluster
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cloud = blockIdx.x / C;
+  const float *dataset = data + (size_t)cloud * n * 3;
+  idxs += (size_t)cloud * m;
+
+  for (int k = tid; k < n; k += TB)
+    s_pts[k] = make_float4(__ldg(dataset + k * 3 + 0), __ldg(dataset + k * 3 + 1), __ldg(dataset + k * 3 + 2), 0.f);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) s_slot[0][lane] = s_slot[1][lane] = 0x80000000ffffffffULL;  // sentinel: below every real maximum
+  __syncthreads();
+  fps_u64 PX[P / 2], PY[P / 2], PZ[P / 2];
+  float td[P];
+  uint32_t pkey[P];
+#pragma unroll
+  for (int h = 0; h < P / 2; h++) {
+    float x[2] = {0.f, 0.f}, y[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = 2 * h + e, k = (i * C + (int)rank) * TB + tid;
+      if (k < n) {
+        const float4 q = s_pts[k];
+        x[e] = q.x, y[e] = q.y, z[e] = q.z;
+        td[i] = 1e10f;
+        pkey[i] = fps_key(k, log2T);
+      } else {
+        td[i] = -1.f;
+        pkey[i] = 0xffffffffu;
+      }
+    }
+    PX[h] = fps_pack2(x[0], x[1]), PY[h] = fps_pack2(y[0], y[1]), PZ[h] = fps_pack2(z[0], z[1]);
+  }
+  // remote addresses of this warp's slot and of the mbarrier in every CTA of the cluster
+  uint32_t r_slot[2][C], r_bar[2][C];
+#pragma unroll
+  for (int bf = 0; bf < 2; bf++) {
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const uint32_t ls = (uint32_t)__cvta_generic_to_shared(&s_slot[bf][rank * NW + warp]);
+      const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&s_bar[bf]);
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_slot[bf][c]) : "r"(ls), "r"(c));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar[bf][c]) : "r"(lb), "r"(c));
+    }
+  }
+  // every CTA's barriers and sentinels are initialised before anyone's first remote store lands
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  int old = 0;
+  if (tid == 0 && rank == 0) idxs[0] = 0;
+
+  for (int j = 1; j < m; j++) {
+    const int buf = j & 1;
+    if (tid == 0)  // this pick's slots: C * NW stores of 8 bytes are expected on the local barrier
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[buf])),
+                   "r"(C * NW * 8)
+                   : "memory");
+    const float4 o = s_pts[old];
+    const fps_u64 qx = fps_pack2(o.x, o.x), qy = fps_pack2(o.y, o.y), qz = fps_pack2(o.z, o.z);
+    float vmax = -1.f;
+#pragma unroll
+    for (int h = 0; h < P / 2; h++) {
+      float d0, d1;
+      fps_unpack2(fps_dist2(PX[h], PY[h], PZ[h], qx, qy, qz), d0, d1);
+      td[2 * h] = fminf(d0, td[2 * h]);
+      td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+      vmax = fps_max3(vmax, td[2 * h], td[2 * h + 1]);
+    }
+    const int vbits = __float_as_int(vmax);
+    const int wbits = redux_max_s32(vbits);
+    uint32_t key = 0xffffffffu;
+    if (vbits == wbits) {
+#pragma unroll
+      for (int i = 0; i < P; i++)
+        if (__float_as_int(td[i]) == wbits) key = min(key, pkey[i]);
+    }
+    const uint32_t wkey = redux_min_u32(key);
+    if (lane < C) {  // lane c sends this warp's slot to CTA c
+      const unsigned long long v = ((unsigned long long)(uint32_t)wbits << 32) | wkey;
+      uint32_t dst = r_slot[buf][0], bar = r_bar[buf][0];
+#pragma unroll
+      for (int c = 1; c < C; c++)
+        if (lane == c) dst = r_slot[buf][c], bar = r_bar[buf][c];
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(v), "r"(bar)
+                   : "memory");
+    }
+    {  // wait for all C * NW slots of this pick
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf]);
+      const uint32_t parity = (uint32_t)(j >> 1) & 1u;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "FPSW_%=:\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra FPSD_%=;\n\t"
+          "bra FPSW_%=;\n\t"
+          "FPSD_%=:\n\t}" ::"r"(bar),
+          "r"(parity)
+          : "memory");
+    }
+    const unsigned long long sv = s_slot[buf][lane];  // slots >= C * NW hold the sentinel
+    const int v = (int)(uint32_t)(sv >> 32);
+    const uint32_t kk = (uint32_t)sv;
+    const int bv = redux_max_s32(v);
+    const uint32_t bk = redux_min_u32(v == bv ? kk : 0xffffffffu);
+    old = fps_unkey(bk, log2T);
+    if (tid == 0 && rank == 0) idxs[j] = old;
+  }
+  if (temp != nullptr) {
+    temp += (size_t)cloud * n;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = (i * C + (int)rank) * TB + tid;
+      if (k < n) temp[k] = td[i];
+    }
+  }
+  // no CTA leaves while a peer may still address its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int TB, int P, int C>
+static int fps_cluster_launch(int b, int n, int m, int log2T, const float *data, float *temp, int *idx, cudaStream_t s) {
+  const size_t smem = (size_t)n * sizeof(float4);
+  static size_t granted[kMaxDevices];
+  int rc = grant_dyn_smem(fps_cluster_kernel<TB, P, C>, smem > 40 * 1024 ? (size_t)TB * P * C * sizeof(float4) : smem, granted);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(b * C);
+  cfg.blockDim = dim3(TB);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<TB, P, C>, n, m, log2T, data, temp, idx);
+  return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+static int fps_cluster_size() {  // MVP_FPS_CLUSTER=2|4: split every cloud of 512..8192 points over a cluster (A/B timing)
+  static const int c = [] {
+    const char *e = getenv("MVP_FPS_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    return (v == 2 || v == 4) ? v : 0;
+  }();
+  return c;
+}
+
 // furthest_point_sample_cuda.cu:11-15 — evaluated with the same double expression so that the tie order
 // matches the block size the reference would have launched.
 static int ref_block_size(int work_size) {
@@ -528,6 +697,26 @@ static int fps_dispatch(int b, int n, int m, const float *data, float *temp, int
   const int T = ref_block_size(n);
   int log2T = 0;
   while ((1 << log2T) < T) log2T++;
+  if (!WD && fps_cluster_size() && n >= 512 && n <= 8192) {
+    const int c = fps_cluster_size();
+    int rc;
+    // TB * P * C >= n
+    if (c == 2) {
+      if (n <= 1024) rc = fps_cluster_launch<128, 4, 2>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 2048) rc = fps_cluster_launch<256, 4, 2>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 3072) rc = fps_cluster_launch<256, 6, 2>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 4096) rc = fps_cluster_launch<256, 8, 2>(b, n, m, log2T, data, temp, idx, s);
+      else rc = fps_cluster_launch<512, 8, 2>(b, n, m, log2T, data, temp, idx, s);
+    } else {
+      if (n <= 1024) rc = fps_cluster_launch<128, 2, 4>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 2048) rc = fps_cluster_launch<128, 4, 4>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 3072) rc = fps_cluster_launch<128, 6, 4>(b, n, m, log2T, data, temp, idx, s);
+      else if (n <= 4096) rc = fps_cluster_launch<256, 4, 4>(b, n, m, log2T, data, temp, idx, s);
+      else rc = fps_cluster_launch<256, 8, 4>(b, n, m, log2T, data, temp, idx, s);
+    }
+    count_launch();
+    return rc ? rc : launch_status();
+  }
   // (TB, P) with TB*P >= n: at most MVP_FPS_PMAX points per thread while warps are left, then grow P.
   if (n > 4096 && n <= 512 * 16) fps_launch_one<WD, 512, 16>(b, n, m, log2T, data, temp, idx, s);  // measured best
   else

@@ -142,69 +142,97 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
 }
 
 // ------------------------------------------------------------------------------------------------
-// knn: one thread per centre; the heap procedure is the reference's, step for step, so that the order
-// among equal distances is identical (knn_cuda.cu:26-53,72-93).
+// knn (replaces knn_cuda.cu:58-94: one thread per centre, a 100-slot max-heap in local memory, heap sort).
+// One thread per centre, the searched cloud broadcast from a shared-memory tile; the nsample best so far live in an
+// ORDERED LIST IN REGISTERS, ascending in (distance, index): a candidate that does not precede the last entry — nearly
+// every candidate once the list has warmed up — costs one compare, an insertion is a chain of compile-time-indexed
+// compare-exchanges (no local memory, no heap sort at the end).  The list has K in {8, 16, 32, 64} slots; a smaller
+// nsample puts K - nsample phantoms at -inf in front so that the last real entry is always slot K - 1.  nsample > 64
+// (the reference allows 100) runs a second pass that keeps only candidates AFTER the 64th of the first pass in
+// (distance, index) order.
+// Same result as the reference: the k smallest by (distance, index) — its strict `d2 < best_dist[0]` keeps the
+// earlier index among equal distances at the boundary (knn_cuda.cu:83) — in ascending distance; entries of EQUAL
+// distance come out in index order here and in heap order there (set-equal on ties).  Slots the
+// cloud cannot fill (n < nsample) keep the reference's initial (1e10, 0) (knn_cuda.cu:74-77).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void knn_reheap(float *dist, int *idx, int k) {
-  int root = 0;
-  int child = root * 2 + 1;
-  while (child < k) {
-    if (child + 1 < k && dist[child + 1] > dist[child]) child++;
-    if (dist[root] > dist[child]) return;
-    const float tf = dist[root]; dist[root] = dist[child]; dist[child] = tf;
-    const int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
-    root = child;
-    child = root * 2 + 1;
+template <int K>
+__device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bk)[K], float d, int qi) {
+  bd[K - 1] = d;
+  bk[K - 1] = qi;
+#pragma unroll
+  for (int k = K - 1; k > 0; k--) {
+    if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bk[k] < bk[k - 1])) {
+      const float td_ = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td_;
+      const int tk_ = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk_;
+    }
   }
 }
 
+// output slots [done, done + kk) of every centre; done > 0: only candidates after slot done - 1 in (distance, index) order
+template <int K>
 __global__ void __launch_bounds__(128)
-knn_kernel(int n, int m, int nsample, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
-           int *__restrict__ idx, float *__restrict__ dist2) {
-  __shared__ float tile[kTile * 3];
+knn_list_kernel(int n, int m, int nsample, int done, int kk, const float *__restrict__ xyz,
+                const float *__restrict__ new_xyz, int *__restrict__ idx, float *__restrict__ dist2) {
+  __shared__ float4 tile[kTile];
   const int b = blockIdx.y;
   const int p = blockIdx.x * 128 + threadIdx.x;
   const bool active = p < m;
   const float *pts = xyz + (size_t)b * n * 3;
   float cx = 0, cy = 0, cz = 0;
+  int *oi = idx + ((size_t)b * m + (active ? p : 0)) * nsample;
+  float *od = dist2 + ((size_t)b * m + (active ? p : 0)) * nsample;
+  const float inf = __int_as_float(0x7f800000);
+  float ld = -inf;  // the last entry of the previous pass
+  int li = -1;
   if (active) {
     const float *c = new_xyz + ((size_t)b * m + p) * 3;
-    cx = __ldg(c + 0);
-    cy = __ldg(c + 1);
-    cz = __ldg(c + 2);
+    cx = __ldg(c + 0), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    if (done) ld = od[done - 1], li = oi[done - 1];
   }
-  float best_dist[100];
-  int best_idx[100];
-  for (int i = 0; i < nsample; i++) {
-    best_dist[i] = 1e10f;
-    best_idx[i] = 0;
+  float bd[K];
+  int bk[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    bd[k] = k < K - kk ? -inf : 1e10f;
+    bk[k] = k < K - kk ? -1 : 0;
   }
-  for (int k2 = 0; k2 < n; k2 += kTile) {
-    const int tcnt = min(kTile, n - k2);
+  for (int j0 = 0; j0 < n; j0 += kTile) {
+    const int cnt = min(kTile, n - j0);
     __syncthreads();
-    load_tile(tile, pts + (size_t)k2 * 3, tcnt, threadIdx.x, 128);
+    for (int j = threadIdx.x; j < cnt; j += 128) {
+      const float *c = pts + (size_t)(j0 + j) * 3;
+      tile[j] = make_float4(__ldg(c + 0), __ldg(c + 1), __ldg(c + 2), 0.f);
+    }
     __syncthreads();
     if (!active) continue;
-    for (int i = 0; i < tcnt; i++) {
-      const float d2 = sqdist(cx - tile[i * 3 + 0], cy - tile[i * 3 + 1], cz - tile[i * 3 + 2]);
-      if (d2 < best_dist[0]) {
-        best_dist[0] = d2;
-        best_idx[0] = k2 + i;
-        knn_reheap(best_dist, best_idx, nsample);
+    for (int j = 0; j < cnt; j++) {
+      const float4 c = tile[j];
+      const float d = sqdist(cx - c.x, cy - c.y, cz - c.z);
+      // (NaN distances are never kept, as in the reference)
+      if (d < bd[K - 1] || (d == bd[K - 1] && j0 + j < bk[K - 1])) {
+        if (d > ld || (d == ld && j0 + j > li)) knn_insert<K>(bd, bk, d, j0 + j);
       }
     }
   }
   if (!active) return;
-  for (int i = nsample - 1; i > 0; i--) {
-    const float tf = best_dist[0]; best_dist[0] = best_dist[i]; best_dist[i] = tf;
-    const int ti = best_idx[0]; best_idx[0] = best_idx[i]; best_idx[i] = ti;
-    knn_reheap(best_dist, best_idx, i);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (k >= K - kk) {
+      od[done + k - (K - kk)] = bd[k];
+      oi[done + k - (K - kk)] = bk[k];
+    }
   }
-  int *oi = idx + ((size_t)b * m + p) * nsample;
-  float *od = dist2 + ((size_t)b * m + p) * nsample;
-  for (int i = 0; i < nsample; i++) {
-    oi[i] = best_idx[i];
-    od[i] = best_dist[i];
+}
+
+template <int K>
+static void knn_list_launch(int b, int n, int m, int nsample, int done, int kk, const float *xyz, const float *new_xyz,
+                            int *idx, float *dist2, cudaStream_t s) {
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = min(65535, b - b0);
+    knn_list_kernel<K><<<dim3((m + 127) / 128, bb), 128, 0, s>>>(
+        n, m, nsample, done, kk, xyz + (size_t)b0 * n * 3, new_xyz + (size_t)b0 * m * 3, idx + (size_t)b0 * m * nsample,
+        dist2 + (size_t)b0 * m * nsample);
+    count_launch();
   }
 }
 
@@ -444,12 +472,12 @@ MVP_API int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const fl
   if (b == 0 || m == 0) return MVP_OK;
   if (!new_xyz || !idx || !dist2 || (n > 0 && !xyz)) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  for (int b0 = 0; b0 < b; b0 += 65535) {
-    const int bb = min(65535, b - b0);
-    dim3 grid((m + 127) / 128, bb);
-    knn_kernel<<<grid, 128, 0, s>>>(n, m, nsample, xyz + (size_t)b0 * n * 3, new_xyz + (size_t)b0 * m * 3,
-                                    idx + (size_t)b0 * m * nsample, dist2 + (size_t)b0 * m * nsample);
-    count_launch();
+  for (int done = 0; done < nsample; done += 64) {
+    const int kk = min(64, nsample - done);
+    if (kk <= 8) knn_list_launch<8>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
+    else if (kk <= 16) knn_list_launch<16>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
+    else if (kk <= 32) knn_list_launch<32>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
+    else knn_list_launch<64>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
   }
   return launch_status();
 }

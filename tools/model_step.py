@@ -140,6 +140,42 @@ def run_arm(a):
            "wall_ms_per_step": wall,
            "samples_per_s": B * world / ms * 1e3, "loss": float(loss.item()),
            "params": sum(p.numel() for p in net.parameters())}
+    if world > 1:
+        # The one collective of the step on its own: the same buckets, all-reduced back to back with nothing else on
+        # the device, timed with events on the stream the collective synchronises with (torch's NCCL process group
+        # makes the current stream wait for its own).  bus bandwidth = 2 (N - 1) / N x bytes / time (ring convention).
+        from mvp_benchmark_b200 import dist as mdist2
+        nbytes = sum(p.numel() * p.element_size() for p in params if p.requires_grad)
+        flats = []
+        cur, size = [], 0
+        for p in params:
+            if not p.requires_grad:
+                continue
+            if cur and size + p.numel() * 4 > (a.bucket_mb << 20):
+                flats.append(torch.zeros(sum(q.numel() for q in cur), device=dev))
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel() * 4
+        if cur:
+            flats.append(torch.zeros(sum(q.numel() for q in cur), device=dev))
+        for _ in range(3):
+            for f in flats:
+                dist.all_reduce(f)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a0.record()
+        for _ in range(reps):
+            for f in flats:
+                dist.all_reduce(f)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = mdist2.max_over_ranks(a0.elapsed_time(a1) / reps, dev)
+        out["allreduce"] = {"bytes": nbytes, "buckets": len(flats), "standalone_ms": ar_ms,
+                            "bus_GBps": 2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                            "note": "the step's gradient all-reduce alone (same buckets, nothing else on the device); "
+                                    "inside the step it overlaps the backward pass"}
     if a.profile:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

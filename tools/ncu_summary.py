@@ -109,10 +109,36 @@ def full(path, pattern=None):
         print()
 
 
+def traffic(path, pattern):
+    """DRAM bytes (read + written) of ONE launch of every kernel matching `pattern`, summed: the measured traffic of
+    one Chamfer forward.  Prints the JSON that bench.py reads (profiles/chamfer_forward_traffic.json)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    seen, kernels, total = set(), [], 0.0
+    for r in data:
+        name = short(r[col["Kernel Name"]])
+        if not re.search(pattern, name) or name in seen:
+            continue
+        seen.add(name)
+        by = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            by += float(r[col[m]].replace(",", "")) * scale[units[col[m]]]
+        kernels.append({"kernel": name, "dram_bytes": by, "time_us": r[col["gpu__time_duration.sum"]]})
+        total += by
+    print(json.dumps({"bytes_per_forward": total, "source": path.replace("gpurun_out/", "") + " (ncu --set full, one launch of each kernel)",
+                      "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "full"):
+    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "full", "traffic"):
         sys.exit(__doc__)
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "chamfer_grid|chamfer_rest")
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
