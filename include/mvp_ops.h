@@ -201,6 +201,22 @@ int mvp_chamfer_loss_grad(int b, int n, int m, const float *dist1, const float *
  * any other order).  Opt-in (model_patches rebinds three_nn_upsampling). */
 int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight, mvp_stream_t stream);
 
+/* three_nn (workspace variant above) AND those weights from the same launches: the kernel that finds a target's three
+ * neighbours writes its weights too.  Outputs dist2, idx, weight, each (b,n,3). */
+int mvp_three_nn_weights_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                            float *weight, void *workspace, size_t workspace_bytes, mvp_stream_t stream);
+
+/* furthest_point_sample followed by gather_points on the transposed cloud (completion/model_utils.py:91-93,
+ * completion/models/vrcnet.py:451) as ONE launch: idx (b,m) as mvp_furthest_point_sampling, and the sampled points
+ * themselves, (b,m,3) or — channels_first != 0 — (b,3,m), the layout gather_points returns. */
+int mvp_furthest_point_sampling_gather(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                       float *sampled_xyz, int channels_first, mvp_stream_t stream);
+
+/* ball_query followed by grouping_operation on the coordinates and permute(0,2,3,1) (completion/model_utils.py:211-214)
+ * as ONE launch: idx (b,m,nsample) as mvp_ball_query, and the neighbours' coordinates (b,m,nsample,3). */
+int mvp_ball_query_group(int b, int n, int m, float min_radius, float max_radius, int nsample, const float *new_xyz,
+                         const float *xyz, int *idx, float *grouped_xyz, mvp_stream_t stream);
+
 /* SURVEY.md §8(f) row 1 — the k-nearest-neighbour search the completion MODELS run in torch
  * (completion/model_utils.py:242-259 `knn` / `knn_point` / `knn_point_all`: a (B,N,M) matrix of
  * -|x|^2 + 2 x.y - |y|^2 by matmul, then torch.topk), as one fused exact search for 3-D points.

@@ -752,6 +752,9 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
         idx[(size_t)orig * ko + o] = (kRT && bk[k] == 0x7fffffff) ? o : bk[k];
       }
     }
+    if constexpr (K == 3 && !kRT) {  // three_nn: dist2 doubles as the (b, n, 3) weights of three_nn_upsampling
+      if (dist2 != nullptr) three_nn_weights_of(bd[0], bd[1], bd[2], dist2 + ((size_t)cloud * nq + orig) * 3);
+    }
   } else {
     if (K == 1 && !kRT) {  // what was found before giving up: the completion pass (chamfer_rest.cu) starts from this bound
       dist[orig] = bd[0];
@@ -768,216 +771,6 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
   }
   }  // t < total
 
-}
-
-// ---- Chamfer (K = 1), the same search with the 3x3x3 cube FLATTENED ------------------------------------------------------
-// chamfer_grid_query_kernel<1> walks the nine rows of the cube one after the other, and every row's candidate loop
-// runs for as long as the longest row among the 32 lanes: 13 of 32 lanes active per issued instruction (ncu, round 1).
-// Here a thread scans the centre row (which gives it a good bound), then decides for the other eight rows at once —
-// skipped by their lower bound, clipped in x, all sixteen cell-start loads in flight together — and leaves the
-// surviving ranges in shared memory; ONE loop then walks the concatenation of a thread's ranges, so that a warp runs
-// for the longest TOTAL among its lanes instead of the sum of the longest rows.  Same candidates' arithmetic, same
-// conservative bounds, same tie rule: bit-identical results.  Rings 2 and 3 (a few queries in ten thousand) and the
-// give-up rules are those of the generic kernel.
-#ifndef MVP_GRID_Q1MINB
-#define MVP_GRID_Q1MINB 10
-#endif
-__global__ void __launch_bounds__(kGridQThreads, MVP_GRID_Q1MINB)
-chamfer_grid_query1_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
-                           int *__restrict__ idx1, int *__restrict__ idx2) {
-  constexpr int kBudget = MVP_GRID_BUDGET;
-  constexpr int kMaxRing = MVP_GRID_MAXRING;
-  __shared__ int2 s_rng[8][kGridQThreads];
-  const long long total1 = (long long)b * n, total = total1 + (long long)b * m;
-  const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
-  if (t >= total) return;
-  const int tid = threadIdx.x;
-  const int dir = t >= total1 ? 1 : 0;       // 0: points of xyz1 against xyz2's grid; 1: the other way round
-  const long long pi = dir ? t - total1 : t;
-  const int nq = dir ? m : n, nt = dir ? n : m;
-  const int cloud = (int)(pi / nq);
-  const float4 self = __ldg((dir ? W.sorted[1] : W.sorted[0]) + pi);
-  const int orig = __float_as_int(self.w);
-  const int ts = 1 - dir;  // target side
-  const GridHdr *hp = W.hdr + ts * b + cloud;
-  const int4 h0 = __ldg(reinterpret_cast<const int4 *>(hp));      // lo.xyz, inv_s
-  const int4 h1 = __ldg(reinterpret_cast<const int4 *>(hp) + 1);  // s, g.xyz
-  const int4 h2 = __ldg(reinterpret_cast<const int4 *>(hp) + 2);  // ncell, valid
-  const float inv_s = __int_as_float(h0.w), s = __int_as_float(h1.x);
-  const int gx = h1.y, gy = h1.z, gz = h1.w;
-  const int *start = (ts ? W.start[1] : W.start[0]) + (size_t)cloud * ((ts ? W.cap[1] : W.cap[0]) + 1);
-  const float4 *T = (ts ? W.sorted[1] : W.sorted[0]) + (size_t)cloud * nt;
-  float *dist = (dir ? dist2 : dist1) + (size_t)cloud * nq;
-  int *idx = (dir ? idx2 : idx1) + (size_t)cloud * nq;
-
-  const float inf = __int_as_float(0x7f800000);
-  float best = inf;
-  int bestk = 0x7fffffff;
-  bool done = false;
-  auto eval = [&](int i) {
-    const float4 q = __ldg(T + i);
-    const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
-    const int qi = __float_as_int(q.w);
-    if (d < best || (d == best && qi < bestk)) best = d, bestk = qi;
-  };
-  if (h2.y) {
-    const float ux = (self.x - __int_as_float(h0.x)) * inv_s;
-    const float uy = (self.y - __int_as_float(h0.y)) * inv_s;
-    const float uz = (self.z - __int_as_float(h0.z)) * inv_s;
-    const int cx = cell_coord(ux, gx), cy = cell_coord(uy, gy), cz = cell_coord(uz, gz);
-    // rounding slack of the cell coordinates, in cells (derivation in DESIGN.md §4.1): 2^-23 (|u| + g), 8x margin
-    const float slx = 1e-4f + 1e-6f * (fabsf(ux) + (float)gx);
-    const float sly = 1e-4f + 1e-6f * (fabsf(uy) + (float)gy);
-    const float slz = 1e-4f + 1e-6f * (fabsf(uz) + (float)gz);
-    const float s2 = s * s * (1.f - 1e-5f);  // (cells -> squared distance), rounded DOWN generously
-    const float out = fmaxf(fmaxf(fmaxf(-ux, ux - (float)gx), fmaxf(-uy, uy - (float)gy)), fmaxf(-uz, uz - (float)gz));
-    const bool finite = fabsf(ux) + fabsf(uy) + fabsf(uz) < 3.0e38f;  // false for NaN / inf
-    int budget = (finite && out <= (float)(kMaxRing + 1)) ? kBudget : -1;
-    auto gap = [](float u, int c, float slack) {
-      const float g = fmaxf((float)c - u, u - (float)(c + 1));
-      return fmaxf(g - slack, 0.f);
-    };
-
-    if (budget >= 0) {
-      // ---- ring 1, centre row: cells cx-1 .. cx+1 of row (cy, cz), one contiguous range
-      float gxs[3], gys[3], gzs[3];
-      gxs[1] = gys[1] = gzs[1] = 0.f;
-      { const float g = gap(ux, cx - 1, slx); gxs[0] = cx > 0 ? g * g : inf; }
-      { const float g = gap(ux, cx + 1, slx); gxs[2] = cx + 1 < gx ? g * g : inf; }
-      { const float g = gap(uy, cy - 1, sly); gys[0] = cy > 0 ? g * g : inf; }
-      { const float g = gap(uy, cy + 1, sly); gys[2] = cy + 1 < gy ? g * g : inf; }
-      { const float g = gap(uz, cz - 1, slz); gzs[0] = cz > 0 ? g * g : inf; }
-      { const float g = gap(uz, cz + 1, slz); gzs[2] = cz + 1 < gz ? g * g : inf; }
-      const int xlo = cx > 0 ? cx - 1 : cx, xhi = cx + 1 < gx ? cx + 1 : cx;
-      {
-        const int base = (cz * gy + cy) * gx;
-        const int a = __ldg(start + base + xlo), e = __ldg(start + base + xhi + 1);
-        if (e - a > budget) budget = -1;
-        else {
-          budget -= e - a;
-#pragma unroll 2
-          for (int i = a; i < e; i++) eval(i);
-        }
-      }
-      if (budget >= 0) {
-        // ---- the other eight rows: skip / clip with the bound of the centre row, loads first
-        constexpr int oy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
-        constexpr int oz[8] = {0, 0, -1, 1, -1, -1, 1, 1};
-        int ia[8], ie[8];
-        bool use[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          const float lbyz = gys[oy[r] + 1] + gzs[oz[r] + 1];  // inf for a row outside the grid
-          use[r] = !(lbyz * s2 > best) && lbyz < inf;          // (best == inf keeps every row inside the grid)
-          const int x0 = (gxs[0] + lbyz) * s2 > best ? cx : xlo;
-          const int x1 = (gxs[2] + lbyz) * s2 > best ? cx : xhi;
-          const int base = ((cz + oz[r]) * gy + (cy + oy[r])) * gx;
-          ia[r] = use[r] ? base + x0 : 0;
-          ie[r] = use[r] ? base + x1 + 1 : 0;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          ia[r] = __ldg(start + ia[r]);
-          ie[r] = __ldg(start + ie[r]);
-        }
-        int cnt = 0, sum = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          if (use[r] && ie[r] > ia[r]) {
-            s_rng[cnt][tid] = make_int2(ia[r], ie[r]);
-            cnt++;
-            sum += ie[r] - ia[r];
-          }
-        }
-        if (sum > budget) budget = -1;
-        else {
-          budget -= sum;
-          // ---- one loop over the concatenated ranges
-          int r = 0, i = 0, e = 0;
-          for (;;) {
-            if (i == e) {
-              if (r == cnt) break;
-              const int2 ae = s_rng[r][tid];
-              r++;
-              i = ae.x, e = ae.y;
-            }
-            eval(i);
-            i++;
-          }
-        }
-      }
-    }
-    // ---- rings 2 .. kMaxRing, as in the generic kernel
-    auto scan = [&](int a, int e) {
-      if (e - a > budget) {
-        budget = -1;
-        return;
-      }
-      budget -= e - a;
-      for (int i = a; i < e; i++) eval(i);
-    };
-    auto row = [&](int x0, int x1, int yy, int zz, float lbyz) {
-      x0 = max(x0, 0);
-      x1 = min(x1, gx - 1);
-      while (x0 <= x1) {
-        const float g = gap(ux, x0, slx);
-        if (fmaf(g, g, lbyz) * s2 > best) x0++; else break;
-      }
-      while (x1 >= x0) {
-        const float g = gap(ux, x1, slx);
-        if (fmaf(g, g, lbyz) * s2 > best) x1--; else break;
-      }
-      if (x0 > x1) return;
-      const int base = (zz * gy + yy) * gx;
-      scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
-    };
-    for (int r = 1; r <= kMaxRing && !done && budget >= 0; r++) {
-      if (r > 1) {
-        for (int dz = -r; dz <= r && budget >= 0; dz++) {
-          const int zz = cz + dz;
-          if (zz < 0 || zz >= gz) continue;
-          const float gzz = gap(uz, zz, slz);
-          if (gzz * gzz * s2 > best) continue;
-          for (int dy = -r; dy <= r; dy++) {
-            const int yy = cy + dy;
-            if (yy < 0 || yy >= gy) continue;
-            const float gyy = gap(uy, yy, sly);
-            const float lbyz = fmaf(gyy, gyy, gzz * gzz);
-            if (lbyz * s2 > best) continue;
-            if (dz == -r || dz == r || dy == -r || dy == r) {
-              row(cx - r, cx + r, yy, zz, lbyz);
-            } else {  // interior row: only its two new end cells
-              row(cx - r, cx - r, yy, zz, lbyz);
-              row(cx + r, cx + r, yy, zz, lbyz);
-            }
-          }
-        }
-        if (budget < 0) break;
-      }
-      // everything outside the cube of radius r is at least `ext` cells away
-      float ext = inf;
-      if (cx - r > 0) ext = fminf(ext, ux - (float)(cx - r) - slx);
-      if (cx + r + 1 < gx) ext = fminf(ext, (float)(cx + r + 1) - ux - slx);
-      if (cy - r > 0) ext = fminf(ext, uy - (float)(cy - r) - sly);
-      if (cy + r + 1 < gy) ext = fminf(ext, (float)(cy + r + 1) - uy - sly);
-      if (cz - r > 0) ext = fminf(ext, uz - (float)(cz - r) - slz);
-      if (cz + r + 1 < gz) ext = fminf(ext, (float)(cz + r + 1) - uz - slz);
-      ext = fmaxf(ext, 0.f);
-      if (ext == inf || best < ext * ext * s2) done = true;
-    }
-  }
-  dist[orig] = best;  // final, or what the completion pass (chamfer_rest.cu) starts from
-  idx[orig] = bestk;
-  if (!done) {
-    // append to the left-over list of (direction, cloud): one atomic per group of lanes sharing the list
-    const int li = dir * b + cloud;
-    const unsigned peers = __match_any_sync(__activemask(), li);
-    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-    int pos = 0;
-    if (lane == leader) pos = atomicAdd(W.count + li, __popc(peers));
-    pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
-    ((dir ? W.list[1] : W.list[0]) + (size_t)cloud * nq)[pos] = orig;
-  }
 }
 
 // chamfer_rest.cu: the completion pass over the left-over lists
@@ -1000,16 +793,8 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
     if (rc) return rc;
   }
   const long long total = (long long)b * ((long long)n + m);
-  static const int flat = [] {  // measuring aid: MVP_GRID_FLAT=0 selects the row-by-row kernel
-    const char *e = getenv("MVP_GRID_FLAT");
-    return e ? atoi(e) : 1;
-  }();
-  if (flat)
-    chamfer_grid_query1_kernel<<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-        b, n, m, W, dist1, dist2, idx1, idx2);
-  else
-    chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-        b, n, m, W, dist1, dist2, idx1, idx2, 1);
+  chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+      b, n, m, W, dist1, dist2, idx1, idx2, 1);
   count_launch(2);
   const int rc = launch_status();
   if (rc) return rc;
@@ -1020,7 +805,7 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
 // ---- three_nn through the same grid (pointnet2.cu: mvp_three_nn_ws) --------------------------------------------------
 // pointnet2.cu
 int three_nn_rest_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
-                         const int *list, const int *count, cudaStream_t s);
+                         float *weight, const int *list, const int *count, cudaStream_t s);
 
 bool three_nn_grid_supported(int b, int n, int m) {
   return b > 0 && b <= 65535 && n >= 256 && m >= 256 && n <= (1 << 20) && m <= (1 << 20) &&
@@ -1031,8 +816,8 @@ size_t three_nn_grid_workspace_bytes(int b, int n, int m) { return grid_plan(b, 
 
 // unknown (b,n,3) against known (b,m,3): grid over `known`, queries in the sorted order of `unknown`; queries that do
 // not finish within the ring / candidate budget are finished by the tiled brute-force kernel through a list.
-int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *ws,
-                         size_t ws_bytes, cudaStream_t s) {
+int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                         float *weight, void *ws, size_t ws_bytes, cudaStream_t s) {
   GridWs W;
   if (ws_bytes < grid_plan(b, n, m, ws, &W)) return MVP_ERR_WORKSPACE;
   {
@@ -1041,11 +826,11 @@ int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float 
   }
   const long long total = (long long)b * n;
   chamfer_grid_query_kernel<3><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-      b, n, m, W, dist2, nullptr, idx, nullptr, 3);
+      b, n, m, W, dist2, weight, idx, nullptr, 3);  // (the second distance output carries the weights for K = 3)
   count_launch(2);
   int rc = launch_status();
   if (rc) return rc;
-  return three_nn_rest_launch(b, n, m, unknown, known, dist2, idx, W.list[0], W.count, s);
+  return three_nn_rest_launch(b, n, m, unknown, known, dist2, idx, weight, W.list[0], W.count, s);
 }
 
 

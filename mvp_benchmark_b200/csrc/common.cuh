@@ -49,6 +49,17 @@ __device__ __forceinline__ float sqdist(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Inverse-distance weights of the three nearest sources (completion/model_utils.py:286-293: sqrt of three_nn's squared
+// distances, clamp at 1e-10, reciprocal, sum over the three, divide), every operation the IEEE one torch performs, in
+// the order torch 2.11's reduction adds three elements (first + third, then second: measured, tests pin it).
+__device__ __forceinline__ void three_nn_weights_of(float d0, float d1, float d2, float *w) {
+  const float r0 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(d0), 1e-10f));
+  const float r1 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(d1), 1e-10f));
+  const float r2 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(d2), 1e-10f));
+  const float norm = __fadd_rn(__fadd_rn(r0, r2), r1);
+  w[0] = __fdiv_rn(r0, norm), w[1] = __fdiv_rn(r1, norm), w[2] = __fdiv_rn(r2, norm);
+}
+
 __device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
   uint32_t r;
   asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));

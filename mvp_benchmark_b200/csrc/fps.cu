@@ -76,13 +76,35 @@ __device__ __forceinline__ float fps_max3(float a, float b, float c) {
   return r;
 }
 
+// Outputs of a sampling call: the indices, and optionally the sampled POINTS themselves — the sampling idiom of the
+// completion models is furthest_point_sample followed by gather_points on the transposed cloud and a transpose back
+// (completion/model_utils.py:91-93, vrcnet.py:451); with `xyz` set the kernel that chose the points also writes their
+// coordinates, (b, m, 3) or channels-first (b, 3, m), as an epilogue of the CTA that owns the cloud.
+struct FpsOut {
+  int *idx;
+  float *xyz;  // nullptr: indices only
+  int cf;      // 1: (b, 3, m), what gather_points returns; 0: (b, m, 3)
+};
+__device__ __forceinline__ void fps_write_points(const FpsOut &O, int cloud, int m, const int *idxs,
+                                                 const float *__restrict__ dataset, int tid, int nthreads) {
+  if (O.xyz == nullptr) return;
+  __syncthreads();  // thread 0's index stores are visible to the CTA
+  float *out = O.xyz + (size_t)cloud * m * 3;
+  for (int j = tid; j < m; j += nthreads) {
+    const int k = idxs[j];
+    const float x = __ldg(dataset + (size_t)k * 3), y = __ldg(dataset + (size_t)k * 3 + 1), z = __ldg(dataset + (size_t)k * 3 + 2);
+    if (O.cf) out[j] = x, out[m + j] = y, out[2 * m + j] = z;
+    else out[j * 3] = x, out[j * 3 + 1] = y, out[j * 3 + 2] = z;
+  }
+}
+
 // TB threads, P points per thread (k = tid + i*TB).  WITH_DIST: `data` is the (n,n) distance matrix.
 // SMEM_PTS: the cloud also lives in shared memory as float4, so the coordinates of the point just selected — the
 // head of every iteration's dependency chain — cost one LDS.128 instead of three global loads.
 template <int TB, int P, bool WITH_DIST, bool SMEM_PTS>
 __global__ void __launch_bounds__(TB)
 fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
-           int *__restrict__ idxs) {
+           FpsOut O) {
   static_assert(P % 2 == 0, "points are processed in packed pairs");
   constexpr int NW = TB / 32;
   extern __shared__ __align__(16) float4 s_pts[];
@@ -90,7 +112,7 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
   __shared__ uint32_t s_key[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *dataset = data + (size_t)blockIdx.x * (WITH_DIST ? (size_t)n * n : (size_t)n * 3);
-  idxs += (size_t)blockIdx.x * m;
+  int *idxs = O.idx + (size_t)blockIdx.x * m;
 
   fps_u64 PX[P / 2], PY[P / 2], PZ[P / 2];  // points 2h and 2h+1 of this thread, packed
   float td[P];
@@ -205,6 +227,7 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
            TB, P, n, m, fps_acc[0] / (m - 1), fps_acc[1] / (m - 1), fps_acc[2] / (m - 1), fps_acc[3] / (m - 1),
            fps_acc[4] / (m - 1));
 #endif
+  if (!WITH_DIST) fps_write_points(O, blockIdx.x, m, idxs, dataset, tid, TB);
   if (temp != nullptr) {
     temp += (size_t)blockIdx.x * n;
 #pragma unroll
@@ -227,7 +250,7 @@ fps_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__res
 template <int TB, int P>
 __global__ void __launch_bounds__(TB)
 fps_sorted_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
-                  int *__restrict__ idxs) {
+                  FpsOut O) {
   static_assert(P % 2 == 0, "points are processed in packed pairs");
   extern __shared__ __align__(16) float4 s_pts[];   // [n] by original index | order[n] | hist[cap]
   __shared__ float s_red[6][32];
@@ -239,7 +262,7 @@ fps_sorted_kernel(int n, int m, int log2T, const float *__restrict__ data, float
   int *s_hist = s_order + n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *dataset = data + (size_t)blockIdx.x * n * 3;
-  idxs += (size_t)blockIdx.x * m;
+  int *idxs = O.idx + (size_t)blockIdx.x * m;
   const float inf = __int_as_float(0x7f800000);
 
   // ---- the cloud into shared memory; bounding box
@@ -408,6 +431,7 @@ fps_sorted_kernel(int n, int m, int log2T, const float *__restrict__ data, float
     old = fps_unkey(bk, log2T);
     if (tid == 0) idxs[j] = old;
   }
+  fps_write_points(O, blockIdx.x, m, idxs, dataset, tid, TB);
   if (temp != nullptr) {
     temp += (size_t)blockIdx.x * n;
 #pragma unroll
@@ -422,12 +446,12 @@ fps_sorted_kernel(int n, int m, int log2T, const float *__restrict__ data, float
 template <bool WITH_DIST>
 __global__ void __launch_bounds__(1024)
 fps_big_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
-               int *__restrict__ idxs) {
+               FpsOut O) {
   __shared__ int s_val[2][32];
   __shared__ uint32_t s_key[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *dataset = data + (size_t)blockIdx.x * (WITH_DIST ? (size_t)n * n : (size_t)n * 3);
-  idxs += (size_t)blockIdx.x * m;
+  int *idxs = O.idx + (size_t)blockIdx.x * m;
   temp += (size_t)blockIdx.x * n;
   for (int k = tid; k < n; k += 1024) temp[k] = 1e10f;
   int old = 0;
@@ -473,6 +497,7 @@ fps_big_kernel(int n, int m, int log2T, const float *__restrict__ data, float *_
     old = fps_unkey(bk, log2T);
     if (tid == 0) idxs[j] = old;
   }
+  if (!WITH_DIST) fps_write_points(O, blockIdx.x, m, idxs, dataset, tid, 1024);
 }
 
 // ---- one cloud split over a CLUSTER of C CTAs (xyz input) ------------------------------------------------------------------
@@ -482,12 +507,11 @@ fps_big_kernel(int n, int m, int log2T, const float *__restrict__ data, float *_
 // so the data and its arrival signal travel together — and every CTA reduces the C x TB/32 slots redundantly after
 // waiting on its OWN mbarrier: no cluster-wide barrier (380 cycles + an L1 flush), one DSMEM hop (~215 cycles) per pick.
 // Slots and mbarriers are double-buffered by pick parity: a CTA can be at most one pick ahead of its peers.
-// Same picks, bit for bit (keys are those of the original indices).  MVP_FPS_CLUSTER=2|4 selects it; the measured
-// table is in DESIGN.md §4.4: the hop costs more than the halved update saves at these cloud sizes.
+// Same picks, bit for bit (keys are those of the original indices).  Used where it measured faster: fps_cluster_size().
 template <int TB, int P, int C>
 __global__ void __launch_bounds__(TB)
 fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, float *__restrict__ temp,
-                   int *__restrict__ idxs) {
+                   FpsOut O) {
   static_assert(P % 2 == 0 && C * (TB / 32) <= 32, "packed pairs; the slots of a pick fit one warp");
   constexpr int NW = TB / 32;
   extern __shared__ __align__(16) float4 s_pts[];
@@ -498,7 +522,7 @@ fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, floa
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int cloud = blockIdx.x / C;
   const float *dataset = data + (size_t)cloud * n * 3;
-  idxs += (size_t)cloud * m;
+  int *idxs = O.idx + (size_t)cloud * m;
 
   for (int k = tid; k < n; k += TB)
     s_pts[k] = make_float4(__ldg(dataset + k * 3 + 0), __ldg(dataset + k * 3 + 1), __ldg(dataset + k * 3 + 2), 0.f);
@@ -584,7 +608,7 @@ fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, floa
     }
     {  // wait for all C * NW slots of this pick
       const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf]);
-      const uint32_t parity = (uint32_t)(j >> 1) & 1u;
+      const uint32_t parity = (uint32_t)((j - 1) >> 1) & 1u;  // picks 1, 2 are the first use of either barrier
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
           "FPSW_%=:\n\t"
@@ -603,6 +627,7 @@ fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, floa
     old = fps_unkey(bk, log2T);
     if (tid == 0 && rank == 0) idxs[j] = old;
   }
+  if (rank == 0) fps_write_points(O, cloud, m, idxs, dataset, tid, TB);
   if (temp != nullptr) {
     temp += (size_t)cloud * n;
 #pragma unroll
@@ -616,7 +641,7 @@ fps_cluster_kernel(int n, int m, int log2T, const float *__restrict__ data, floa
 }
 
 template <int TB, int P, int C>
-static int fps_cluster_launch(int b, int n, int m, int log2T, const float *data, float *temp, int *idx, cudaStream_t s) {
+static int fps_cluster_launch(int b, int n, int m, int log2T, const float *data, float *temp, FpsOut idx, cudaStream_t s) {
   const size_t smem = (size_t)n * sizeof(float4);
   static size_t granted[kMaxDevices];
   int rc = grant_dyn_smem(fps_cluster_kernel<TB, P, C>, smem > 40 * 1024 ? (size_t)TB * P * C * sizeof(float4) : smem, granted);
@@ -635,13 +660,20 @@ static int fps_cluster_launch(int b, int n, int m, int log2T, const float *data,
   return e == cudaSuccess ? MVP_OK : (int)e;
 }
 
-static int fps_cluster_size() {  // MVP_FPS_CLUSTER=2|4: split every cloud of 512..8192 points over a cluster (A/B timing)
-  static const int c = [] {
+// Cluster size for a problem: MVP_FPS_CLUSTER=0|2|4 forces it (A/B timing).  Measured (tools/fps_sizes.py, ns per pick,
+// 1 / 2 / 4 CTAs per cloud): 32x2048 242 / 302 / 295, 64x3072 304 / 320 / 310, 64x1536 249 / 320 / 308, 64x768 231 /
+// 286 / 288, 16x8192 458 (sorted kernel) / 464 / 418 — the DSMEM hop costs more than the shorter update saves until a
+// thread would own sixteen points, so only clouds above 4096 points are split, four ways, while the clusters fit the
+// machine in one wave.
+static int fps_cluster_size(int b, int n) {
+  static const int forced = [] {
     const char *e = getenv("MVP_FPS_CLUSTER");
-    const int v = e ? atoi(e) : 0;
-    return (v == 2 || v == 4) ? v : 0;
+    const int v = e ? atoi(e) : -1;
+    return (v == 0 || v == 2 || v == 4) ? v : -1;
   }();
-  return c;
+  if (n < 512 || n > 8192) return 0;
+  if (forced >= 0) return forced;
+  return (n > 4096 && b * 4 <= kNumSMs) ? 4 : 0;
 }
 
 // furthest_point_sample_cuda.cu:11-15 — evaluated with the same double expression so that the tie order
@@ -663,7 +695,7 @@ static bool fps_use_sorted() {  // MVP_FPS_SORTED=0: the unsorted kernel (A/B ti
 }
 
 template <bool WD, int TB, int P>
-static void fps_launch_one(int b, int n, int m, int log2T, const float *data, float *temp, int *idx,
+static void fps_launch_one(int b, int n, int m, int log2T, const float *data, float *temp, FpsOut idx,
                            cudaStream_t s) {
   if constexpr (!WD && TB * P <= 8192) {
     // measured (tools/fps_sizes.py): 457 against 601 ns per pick at n = 8192, but 318 against 242 at n = 2048 — with
@@ -690,15 +722,15 @@ static void fps_launch_one(int b, int n, int m, int log2T, const float *data, fl
 }
 
 template <bool WD>
-static int fps_dispatch(int b, int n, int m, const float *data, float *temp, int *idx, cudaStream_t s) {
+static int fps_dispatch(int b, int n, int m, const float *data, float *temp, FpsOut idx, cudaStream_t s) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || m == 0) return MVP_OK;  // reference kernel returns immediately when m <= 0 (:34)
-  if (n == 0 || !data || !idx) return MVP_ERR_INVALID_ARGUMENT;
+  if (n == 0 || !data || !idx.idx) return MVP_ERR_INVALID_ARGUMENT;
   const int T = ref_block_size(n);
   int log2T = 0;
   while ((1 << log2T) < T) log2T++;
-  if (!WD && fps_cluster_size() && n >= 512 && n <= 8192) {
-    const int c = fps_cluster_size();
+  if (!WD && fps_cluster_size(b, n)) {
+    const int c = fps_cluster_size(b, n);
     int rc;
     // TB * P * C >= n
     if (c == 2) {
@@ -755,10 +787,19 @@ static int fps_dispatch(int b, int n, int m, const float *data, float *temp, int
 
 MVP_API int mvp_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                         mvp_stream_t stream) {
-  return mvp::fps_dispatch<false>(b, n, m, xyz, temp, idx, (cudaStream_t)stream);
+  return mvp::fps_dispatch<false>(b, n, m, xyz, temp, mvp::FpsOut{idx, nullptr, 0}, (cudaStream_t)stream);
 }
 
 MVP_API int mvp_furthest_point_sampling_with_dist(int b, int n, int m, const float *dist, float *temp,
                                                   int *idx, mvp_stream_t stream) {
-  return mvp::fps_dispatch<true>(b, n, m, dist, temp, idx, (cudaStream_t)stream);
+  return mvp::fps_dispatch<true>(b, n, m, dist, temp, mvp::FpsOut{idx, nullptr, 0}, (cudaStream_t)stream);
+}
+
+// furthest_point_sample + gather_points of the sampled coordinates in one launch (SURVEY.md §8(f) row 2:
+// completion/model_utils.py:91-93, vrcnet.py:451): idx (b, m) as above and sampled_xyz (b, m, 3), or (b, 3, m) — the
+// layout gather_points returns — when channels_first != 0.
+MVP_API int mvp_furthest_point_sampling_gather(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                               float *sampled_xyz, int channels_first, mvp_stream_t stream) {
+  if (!sampled_xyz && b > 0 && m > 0) return MVP_ERR_INVALID_ARGUMENT;
+  return mvp::fps_dispatch<false>(b, n, m, xyz, temp, mvp::FpsOut{idx, sampled_xyz, channels_first ? 1 : 0}, (cudaStream_t)stream);
 }

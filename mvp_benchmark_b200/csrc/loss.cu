@@ -76,13 +76,7 @@ chamfer_loss_grad_kernel(int b, int n, int m, const float *__restrict__ dist1, c
 __global__ void __launch_bounds__(256)
 three_nn_weights_kernel(long long total, const float *__restrict__ dist2, float *__restrict__ weight) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    float r[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      r[k] = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(__ldg(dist2 + i * 3 + k)), 1e-10f));
-    const float norm = __fadd_rn(__fadd_rn(r[0], r[2]), r[1]);  // the order torch 2.11's reduce kernel adds three elements in (measured)
-#pragma unroll
-    for (int k = 0; k < 3; k++) weight[i * 3 + k] = __fdiv_rn(r[k], norm);
+    three_nn_weights_of(__ldg(dist2 + i * 3), __ldg(dist2 + i * 3 + 1), __ldg(dist2 + i * 3 + 2), weight + i * 3);
   }
 }
 

@@ -32,7 +32,8 @@ constexpr int kBqWarps = 8;
 
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(int n, int m, float min_radius2, float max_radius2, int nsample,
-                  const float *__restrict__ new_xyz, const float *__restrict__ xyz, int *__restrict__ idx) {
+                  const float *__restrict__ new_xyz, const float *__restrict__ xyz, int *__restrict__ idx,
+                  float *__restrict__ grouped) {
   __shared__ float tile[kTile * 3];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,6 +78,18 @@ ball_query_kernel(int n, int m, float min_radius2, float max_radius2, int nsampl
     // Rows are zero when nothing was hit (ball_query.py:35); otherwise padded with the first hit (:44-48).
     const int filled = min(cnt, nsample);
     for (int l = filled + lane; l < nsample; l += 32) out[l] = first;
+    if (grouped != nullptr) {
+      // ball_query -> grouping_operation on the coordinates -> permute(0, 2, 3, 1) (completion/model_utils.py:211-214)
+      // in the same launch: the neighbours' coordinates as (b, m, nsample, 3); a row without a hit groups point 0
+      __syncwarp();
+      float *g = grouped + ((size_t)b * m + p) * nsample * 3;
+      for (int l = lane; l < nsample; l += 32) {
+        const int k = cnt ? out[l] : 0;
+        g[l * 3 + 0] = __ldg(pts + (size_t)k * 3 + 0);
+        g[l * 3 + 1] = __ldg(pts + (size_t)k * 3 + 1);
+        g[l * 3 + 2] = __ldg(pts + (size_t)k * 3 + 2);
+      }
+    }
   }
 }
 
@@ -89,7 +102,7 @@ template <bool kRest>
 __global__ void __launch_bounds__(256)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
                 float *__restrict__ dist2, int *__restrict__ idx, const int *__restrict__ list,
-                const int *__restrict__ count) {
+                const int *__restrict__ count, float *__restrict__ weight) {
   __shared__ float tile[kTile * 3];
   const int b = blockIdx.y;
   const int nq = kRest ? __ldg(count + b) : n;
@@ -138,6 +151,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     int *oi = idx + ((size_t)b * n + p) * 3;
     od[0] = best1; od[1] = best2; od[2] = best3;
     oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    if (weight != nullptr) three_nn_weights_of(best1, best2, best3, weight + ((size_t)b * n + p) * 3);
   }
 }
 
@@ -398,15 +412,15 @@ static int gather_grad_launch(int b, int c, int n, int mpts, const float *grad_o
 
 using namespace mvp;
 
-MVP_API int mvp_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
-                           const float *new_xyz, const float *xyz, int *idx, mvp_stream_t stream) {
+static int ball_query_launch(int b, int n, int m, float min_radius, float max_radius, int nsample, const float *new_xyz,
+                             const float *xyz, int *idx, float *grouped, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0 || nsample < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || m == 0 || nsample == 0) return MVP_OK;
   if (!new_xyz || !idx || (n > 0 && !xyz)) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)b * m * nsample, s);  // ball_query.py:35
   if (e != cudaSuccess) return (int)e;
-  if (n == 0) return MVP_OK;
+  if (n == 0) return grouped ? MVP_ERR_INVALID_ARGUMENT : MVP_OK;  // nothing to group from
   // Radii are squared in fp32 exactly as ball_query_cuda.cu:30-31 does.
   const float max_radius2 = max_radius * max_radius;
   const float min_radius2 = min_radius * min_radius;
@@ -415,14 +429,28 @@ MVP_API int mvp_ball_query(int b, int n, int m, float min_radius, float max_radi
     dim3 grid((m + kBqWarps - 1) / kBqWarps, bb);
     ball_query_kernel<<<grid, kBqWarps * 32, 0, s>>>(n, m, min_radius2, max_radius2, nsample,
                                                      new_xyz + (size_t)b0 * m * 3, xyz + (size_t)b0 * n * 3,
-                                                     idx + (size_t)b0 * m * nsample);
+                                                     idx + (size_t)b0 * m * nsample,
+                                                     grouped ? grouped + (size_t)b0 * m * nsample * 3 : nullptr);
     count_launch();
   }
   return launch_status();
 }
 
-MVP_API int mvp_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
-                         int *idx, mvp_stream_t stream) {
+MVP_API int mvp_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                           const float *new_xyz, const float *xyz, int *idx, mvp_stream_t stream) {
+  return ball_query_launch(b, n, m, min_radius, max_radius, nsample, new_xyz, xyz, idx, nullptr, stream);
+}
+
+// ball_query + the neighbours' coordinates (b, m, nsample, 3) in one launch
+MVP_API int mvp_ball_query_group(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                                 const float *new_xyz, const float *xyz, int *idx, float *grouped_xyz,
+                                 mvp_stream_t stream) {
+  if (!grouped_xyz && b > 0 && m > 0 && nsample > 0) return MVP_ERR_INVALID_ARGUMENT;
+  return ball_query_launch(b, n, m, min_radius, max_radius, nsample, new_xyz, xyz, idx, grouped_xyz, stream);
+}
+
+static int three_nn_exhaustive(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                               float *weight, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || n == 0) return MVP_OK;
   if (!unknown || !dist2 || !idx || (m > 0 && !known)) return MVP_ERR_INVALID_ARGUMENT;
@@ -431,22 +459,28 @@ MVP_API int mvp_three_nn(int b, int n, int m, const float *unknown, const float 
     const int bb = min(65535, b - b0);
     dim3 grid((n + 255) / 256, bb);
     three_nn_kernel<false><<<grid, 256, 0, s>>>(n, m, unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
-                                                dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3, nullptr, nullptr);
+                                                dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3, nullptr, nullptr,
+                                                weight ? weight + (size_t)b0 * n * 3 : nullptr);
     count_launch();
   }
   return launch_status();
+}
+
+MVP_API int mvp_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                         int *idx, mvp_stream_t stream) {
+  return three_nn_exhaustive(b, n, m, unknown, known, dist2, idx, nullptr, stream);
 }
 
 namespace mvp {
 // chamfer_grid.cu
 bool three_nn_grid_supported(int b, int n, int m);
 size_t three_nn_grid_workspace_bytes(int b, int n, int m);
-int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *ws,
-                         size_t ws_bytes, cudaStream_t s);
+int three_nn_grid_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                         float *weight, void *ws, size_t ws_bytes, cudaStream_t s);
 
 int three_nn_rest_launch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
-                         const int *list, const int *count, cudaStream_t s) {
-  three_nn_kernel<true><<<dim3((n + 255) / 256, b), 256, 0, s>>>(n, m, unknown, known, dist2, idx, list, count);
+                         float *weight, const int *list, const int *count, cudaStream_t s) {
+  three_nn_kernel<true><<<dim3((n + 255) / 256, b), 256, 0, s>>>(n, m, unknown, known, dist2, idx, list, count, weight);
   count_launch();
   return launch_status();
 }
@@ -456,13 +490,27 @@ MVP_API size_t mvp_three_nn_workspace_bytes(int b, int n, int m) {
   return three_nn_grid_supported(b, n, m) ? three_nn_grid_workspace_bytes(b, n, m) : 16;
 }
 
-MVP_API int mvp_three_nn_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
-                            void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+static int three_nn_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                       float *weight, void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (three_nn_grid_supported(b, n, m) && unknown && known && dist2 && idx && workspace &&
       workspace_bytes >= three_nn_grid_workspace_bytes(b, n, m))
-    return three_nn_grid_launch(b, n, m, unknown, known, dist2, idx, workspace, workspace_bytes, (cudaStream_t)stream);
-  return mvp_three_nn(b, n, m, unknown, known, dist2, idx, stream);
+    return three_nn_grid_launch(b, n, m, unknown, known, dist2, idx, weight, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
+  return three_nn_exhaustive(b, n, m, unknown, known, dist2, idx, weight, stream);
+}
+
+MVP_API int mvp_three_nn_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                            void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+  return three_nn_ws(b, n, m, unknown, known, dist2, idx, nullptr, workspace, workspace_bytes, stream);
+}
+
+// three_nn and the inverse-distance weights of three_nn_upsampling (completion/model_utils.py:286-293) from the same
+// launches: the kernel that finds a target's three neighbours also writes its weights.
+MVP_API int mvp_three_nn_weights_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                                    float *weight, void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
+  if (!weight && b > 0 && n > 0) return MVP_ERR_INVALID_ARGUMENT;
+  return three_nn_ws(b, n, m, unknown, known, dist2, idx, weight, workspace, workspace_bytes, stream);
 }
 
 MVP_API int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,

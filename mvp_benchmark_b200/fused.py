@@ -89,8 +89,81 @@ def three_nn_weights(target, source):
     weight = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         ws = _lib.workspace(_lib.lib.mvp_three_nn_workspace_bytes(B, N, m), dev)
-        _lib.check(_lib.lib.mvp_three_nn_ws(B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2), _lib.ptr(idx),
-                                            _lib.ptr(ws), ws.numel(), _lib.stream_of(target)), "mvp_three_nn")
-        _lib.check(_lib.lib.mvp_three_nn_weights(B, N, _lib.ptr(dist2), _lib.ptr(weight), _lib.stream_of(target)),
-                   "mvp_three_nn_weights")
+        # the kernel that finds a target's neighbours also writes its weights: no second pass over the distances
+        _lib.check(_lib.lib.mvp_three_nn_weights_ws(B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2), _lib.ptr(idx),
+                                                    _lib.ptr(weight), _lib.ptr(ws), ws.numel(), _lib.stream_of(target)),
+                   "mvp_three_nn_weights_ws")
     return idx, weight
+
+
+class _FpsGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, m, channels_first):
+        pts = points.contiguous()
+        dev = _lib.require_cuda(pts, dtype=torch.float32, what="fps_gather")
+        B, N, _ = pts.shape
+        idx = torch.empty(B, m, device=dev, dtype=torch.int32)
+        out = torch.empty((B, 3, m) if channels_first else (B, m, 3), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.mvp_furthest_point_sampling_gather(B, N, m, _lib.ptr(pts), None, _lib.ptr(idx), _lib.ptr(out),
+                                                                   1 if channels_first else 0, _lib.stream_of(pts)),
+                       "mvp_furthest_point_sampling_gather")
+        ctx.mark_non_differentiable(idx)
+        ctx.save_for_backward(idx)
+        ctx.shape, ctx.cf = pts.shape, channels_first
+        return idx, out
+
+    @staticmethod
+    def backward(ctx, _g_idx, g_out):
+        (idx,) = ctx.saved_tensors
+        if g_out is None:
+            return None, None, None
+        g = g_out.transpose(1, 2) if ctx.cf else g_out  # (B, m, 3)
+        grad = torch.zeros(ctx.shape, device=g_out.device, dtype=g_out.dtype)
+        grad.scatter_add_(1, idx.long().unsqueeze(-1).expand(-1, -1, 3), g.contiguous())  # a point may be picked twice
+        return grad, None, None
+
+
+def fps_gather(points, m, channels_first=False):
+    """furthest_point_sample(points, m) and the sampled points themselves from ONE launch — the sampling idiom of the
+    completion models (completion/model_utils.py:91-93 and :209-210: FPS, transpose, gather_points, transpose back;
+    completion/models/vrcnet.py:451 with channels_first=True).  points (B, N, 3) -> (idx (B, m) int32,
+    sampled (B, m, 3) or (B, 3, m)).  Same indices and coordinates bit for bit; differentiable in `points`."""
+    return _FpsGather.apply(points, int(m), bool(channels_first))
+
+
+def ball_query_group(min_radius, max_radius, nsample, xyz, new_xyz):
+    """ball_query and the neighbours' coordinates from ONE launch (completion/model_utils.py:211-214: ball_query,
+    grouping_operation on the transposed cloud, permute(0, 2, 3, 1).contiguous()).  xyz (B, N, 3), new_xyz (B, P, 3) ->
+    (idx (B, P, nsample) int32, grouped (B, P, nsample, 3)).  Differentiable in `xyz` (get_uniform_loss differentiates
+    through the grouped points): the gradient is scattered back by index, as grouping_operation's backward does."""
+    return _BallQueryGroup.apply(float(min_radius), float(max_radius), int(nsample), xyz, new_xyz)
+
+
+class _BallQueryGroup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, min_radius, max_radius, nsample, xyz, new_xyz):
+        x, c = xyz.contiguous(), new_xyz.detach().contiguous()
+        dev = _lib.require_cuda(x, c, dtype=torch.float32, what="ball_query_group")
+        B, N, _ = x.shape
+        P = c.size(1)
+        idx = torch.empty(B, P, nsample, device=dev, dtype=torch.int32)
+        grouped = torch.empty(B, P, nsample, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.mvp_ball_query_group(B, N, P, min_radius, max_radius, nsample, _lib.ptr(c), _lib.ptr(x),
+                                                     _lib.ptr(idx), _lib.ptr(grouped), _lib.stream_of(x)),
+                       "mvp_ball_query_group")
+        ctx.mark_non_differentiable(idx)
+        ctx.save_for_backward(idx)
+        ctx.shape = x.shape
+        return idx, grouped
+
+    @staticmethod
+    def backward(ctx, _g_idx, g_grouped):
+        (idx,) = ctx.saved_tensors
+        if g_grouped is None:
+            return None, None, None, None, None
+        B, N, _ = ctx.shape
+        grad = torch.zeros(ctx.shape, device=g_grouped.device, dtype=g_grouped.dtype)
+        grad.scatter_add_(1, idx.long().view(B, -1, 1).expand(-1, -1, 3), g_grouped.reshape(B, -1, 3))
+        return None, None, None, grad, None

@@ -71,6 +71,55 @@ def three_nn_upsampling(target_points, source_points):
     return fused.three_nn_weights(target_points, source_points)
 
 
+def edge_preserve_sampling(feature_input, point_input, num_samples, k=10):
+    """model_utils.py:86-108 with its first two statements (furthest_point_sample, then transpose + gather_points +
+    transpose back) as ONE launch (fused.fps_gather); everything after that is the original's
+    sequence of operator calls, through whatever knn_point / gather_points / grouping_operation the module has."""
+    if not point_input.is_cuda or point_input.dtype != torch.float32 or point_input.dim() != 3 or point_input.size(2) != 3:
+        return _ORIGINAL["edge_preserve_sampling"](feature_input, point_input, num_samples, k)
+    import mm3d_pn2
+    batch_size, feature_size, num_points = feature_input.size()
+    p_idx, point_output = fused.fps_gather(point_input, num_samples)
+    pk = int(min(k, num_points))
+    _, pn_idx = knn_point(pk, point_input, point_output)
+    pn_idx = pn_idx.detach().int()
+    neighbor_feature = mm3d_pn2.gather_points(feature_input, pn_idx.view(batch_size, num_samples * pk)).view(
+        batch_size, feature_size, num_samples, pk)
+    neighbor_feature, _ = torch.max(neighbor_feature, 3)
+    center_feature = mm3d_pn2.grouping_operation(feature_input, p_idx.unsqueeze(2)).view(batch_size, -1, num_samples)
+    net = torch.cat((center_feature, neighbor_feature), 1)
+    return net, p_idx, pn_idx, point_output
+
+
+def get_uniform_loss(pcd, percentages=[0.004, 0.006, 0.008, 0.010, 0.012], radius=1.0):
+    """model_utils.py:201-227 (ECG's uniformity loss) with FPS + gather as one launch (fused.fps_gather) and
+    ball_query + grouping_operation + permute as one launch (fused.ball_query_group); the arithmetic after the grouping
+    is the original's, statement for statement."""
+    import math
+    if not pcd.is_cuda or pcd.dtype != torch.float32:
+        return _ORIGINAL["get_uniform_loss"](pcd, percentages, radius)
+    B, N, C = pcd.size()
+    npoint = int(N * 0.05)
+    loss = 0
+    for p in percentages:
+        nsample = int(N * p)
+        r = math.sqrt(p * radius)
+        disk_area = math.pi * (radius ** 2) * p / nsample
+        _, new_xyz = fused.fps_gather(pcd, npoint)
+        _, grouped_pcd = fused.ball_query_group(0, r, nsample, pcd, new_xyz)
+        expect_len = math.sqrt(disk_area)
+        grouped_pcd = grouped_pcd.view(-1, nsample, 3)
+        var, _ = knn_point(2, grouped_pcd, grouped_pcd)
+        uniform_dis = -var[:, :, 1:]
+        uniform_dis = torch.sqrt(torch.abs(uniform_dis + 1e-8))
+        uniform_dis = torch.mean(uniform_dis, dim=-1)
+        uniform_dis = ((uniform_dis - expect_len) ** 2 / (expect_len + 1e-8))
+        mean = torch.mean(uniform_dis)
+        mean = mean * math.pow(p * 100, 2)
+        loss += mean
+    return loss / len(percentages)
+
+
 def calc_cd(output, gt, calc_f1=False):
     """model_utils.py:67-77: the Chamfer operator, then its loss epilogue (two sqrt, four means, three elementwise
     torch kernels) as ONE reduction kernel (fused.chamfer_loss).  Same returns."""
@@ -86,7 +135,8 @@ def calc_cd(output, gt, calc_f1=False):
 
 
 def apply(*modules):
-    """Rebind knn / knn_point / knn_point_all / get_edge_features / calc_cd in the given (already imported) modules.
+    """Rebind knn / knn_point / knn_point_all / get_edge_features / calc_cd / three_nn_upsampling /
+    edge_preserve_sampling / get_uniform_loss in the given (already imported) modules.
     Returns the number of names replaced."""
     from . import install
     install()  # `mm3d_pn2` must resolve to this repository's package
@@ -94,7 +144,8 @@ def apply(*modules):
     for mod in modules:
         for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
                          ("get_edge_features", get_edge_features), ("calc_cd", calc_cd),
-                         ("three_nn_upsampling", three_nn_upsampling)):
+                         ("three_nn_upsampling", three_nn_upsampling),
+                         ("edge_preserve_sampling", edge_preserve_sampling), ("get_uniform_loss", get_uniform_loss)):
             cur = getattr(mod, name, None)
             if cur is None or cur is fn:
                 continue

@@ -328,7 +328,10 @@ FPS_CASES = [("uniform", 32, 2048, 2048), ("uniform", 4, 3072, 1536), ("uniform"
              ("duplicates", 1, 4096, 4096), ("uniform", 2, 6000, 50), ("uniform", 2, 20000, 40),
              # above 4096 points: the spatially sorted kernel (box skip test) — ties, dense cells, degenerate grids
              ("lattice", 2, 8192, 600), ("duplicates", 2, 5000, 700), ("clustered", 2, 8000, 300), ("planar", 2, 6144, 200),
-             ("constant", 1, 5000, 20), ("tiny", 1, 5000, 50), ("outliers", 2, 7000, 400), ("uniform", 3, 8192, 2048)]
+             ("constant", 1, 5000, 20), ("tiny", 1, 5000, 50), ("outliers", 2, 7000, 400), ("uniform", 3, 8192, 2048),
+             # up to 37 such clouds are split over clusters of four CTAs (fps_cluster_kernel); more of them stay on the
+             # spatially sorted one-CTA kernel
+             ("lattice", 40, 4500, 60), ("clustered", 38, 5000, 40), ("uniform", 37, 4097, 33)]
 
 
 @pytest.mark.parametrize("kind,b,n,m", FPS_CASES)
@@ -397,19 +400,8 @@ def test_three_nn_grid_is_bit_identical_to_exhaustive(gpu, kind_u, kind_k, b, n,
 def test_knn_vs_oracle(gpu, cpu, kind, b, n, p, k):
     x, c = _data.cloud(kind, b, n, 81), _data.cloud(kind, b, p, 82)
     got, want = gpu.knn(k, x, c), cpu.knn(k, x, c)
-    _cases.eq(got[1], want[1], "knn dist2")
-    # indices bit-exact where a row's distances are distinct, set-equal inside a run of equal
-    # distances (the reference's order there is an artefact of its heap sort; ours is ascending index)
-    gi, wi, d = got[0], want[0], want[1]
-    run_start = np.concatenate([np.ones(d.shape[:2] + (1,), bool), d[..., 1:] != d[..., :-1]], axis=2)
-    run_id = np.cumsum(run_start, axis=2)
-    in_tie = np.zeros_like(run_start)
-    in_tie[..., 1:] |= ~run_start[..., 1:]
-    in_tie[..., :-1] |= ~run_start[..., 1:]
-    assert (gi[~in_tie] == wi[~in_tie]).all(), "knn idx differs where distances are distinct"
-    key_g = np.sort(run_id.astype(np.int64) * (1 << 32) + gi, axis=2)
-    key_w = np.sort(run_id.astype(np.int64) * (1 << 32) + wi, axis=2)
-    assert (key_g == key_w).all(), "knn idx: runs of equal distance are not set-equal"
+    run_start = _cases.knn_same(got[0], got[1], want[0], want[1], x, c, f"knn {kind}", cut_exact=(kind == "uniform"))
+    gi = got[0]
     if kind == "lattice":  # ties everywhere: ours come out in ascending index
         assert ((np.diff(gi, axis=2) > 0) | run_start[..., 1:]).all()
 

@@ -332,3 +332,62 @@ def test_three_nn_weights_chain(ops, cuda):
         assert torch.equal(gi, wi) and gw.shape == (4, n, 3)
         # bit-equal with torch 2.11 (same IEEE operations, its order of adding the three reciprocals); 2 ulp otherwise
         torch.testing.assert_close(gw, ww, rtol=3e-7, atol=0)
+
+
+def test_fps_gather_and_ball_query_group_chains(ops, cuda):
+    """The remaining fused chains of SURVEY.md §8f row 2 against the sequences of operator calls they replace:
+    FPS -> transpose -> gather_points -> transpose (completion/model_utils.py:91-93, :209-210; vrcnet.py:451 keeps the
+    (B, 3, m) layout) and ball_query -> grouping_operation -> permute (:211-214).  Same bits forward; gradients equal to
+    the operators' own scatters."""
+    import types
+    from mvp_benchmark_b200 import fused, model_patches as mp
+    _, mm = ops
+    for kind, b, n, m in (("uniform", 4, 2048, 512), ("lattice", 2, 700, 700), ("duplicates", 3, 5000, 300), ("uniform", 2, 20000, 64),
+                          ("uniform", 70, 96, 33)):
+        pts = T(_data.cloud(kind, b, n, 41), cuda)
+        a, c = pts.clone().requires_grad_(True), pts.clone().requires_grad_(True)
+        idx, out = fused.fps_gather(a, m)
+        widx = mm.furthest_point_sample(c, m)
+        want = mm.gather_points(c.transpose(1, 2).contiguous(), widx).transpose(1, 2).contiguous()
+        assert torch.equal(idx, widx) and idx.dtype == torch.int32 and out.shape == (b, m, 3) and torch.equal(out, want)
+        _, out_cf = fused.fps_gather(pts, m, channels_first=True)
+        assert out_cf.shape == (b, 3, m) and torch.equal(out_cf, want.transpose(1, 2))
+        g = torch.randn_like(out)
+        out.backward(g), want.backward(g)
+        torch.testing.assert_close(a.grad, c.grad, rtol=1e-5, atol=1e-6)
+    for kind, b, n, p, r, ns in (("uniform", 4, 2048, 102, 0.0632455532, 8), ("lattice", 2, 1500, 33, 0.13, 24),
+                                 ("uniform", 2, 3000, 257, 1e-6, 4), ("uniform", 3, 40, 9, 5.0, 50)):
+        pcd = T(_data.cloud(kind, b, n, 42), cuda)
+        centres = pcd[:, :p].contiguous()
+        a, c = pcd.clone().requires_grad_(True), pcd.clone().requires_grad_(True)
+        idx, grouped = fused.ball_query_group(0, r, ns, a, centres)
+        widx = mm.ball_query(0, r, ns, c, centres)
+        want = mm.grouping_operation(c.transpose(1, 2).contiguous(), widx).permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(idx, widx) and grouped.shape == (b, p, ns, 3) and torch.equal(grouped, want)
+        g = torch.randn_like(grouped)
+        grouped.backward(g), want.backward(g)
+        torch.testing.assert_close(a.grad, c.grad, rtol=1e-5, atol=1e-5)
+
+    # the two callers, patched, against their originals restated on the reference-facing operators
+    def orig_knn_point(pk, point_input, point_output):
+        return _torch_knn_point(pk, point_input, point_output)
+
+    def orig_eps(feature_input, point_input, num_samples, k=10):   # model_utils.py:86-108, restated
+        batch_size, feature_size, num_points = feature_input.size()
+        p_idx = mm.furthest_point_sample(point_input, num_samples)
+        point_output = mm.gather_points(point_input.transpose(1, 2).contiguous(), p_idx).transpose(1, 2).contiguous()
+        pk = int(min(k, num_points))
+        _, pn_idx = fake.knn_point(pk, point_input, point_output)
+        pn_idx = pn_idx.detach().int()
+        neighbor_feature = mm.gather_points(feature_input, pn_idx.view(batch_size, num_samples * pk)).view(
+            batch_size, feature_size, num_samples, pk)
+        neighbor_feature, _ = torch.max(neighbor_feature, 3)
+        center_feature = mm.grouping_operation(feature_input, p_idx.unsqueeze(2)).view(batch_size, -1, num_samples)
+        return torch.cat((center_feature, neighbor_feature), 1), p_idx, pn_idx, point_output
+
+    fake = types.SimpleNamespace(edge_preserve_sampling=orig_eps, knn_point=orig_knn_point)
+    assert mp.apply(fake) == 2
+    pts, feat = T(_data.uniform(4, 3072, 43), cuda), torch.randn(4, 64, 3072, device=cuda)
+    got, want = fake.edge_preserve_sampling(feat, pts, 1536, 10), orig_eps(feat, pts, 1536, 10)
+    for g_, w_ in zip(got, want):
+        assert torch.equal(g_, w_)
