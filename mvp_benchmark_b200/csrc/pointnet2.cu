@@ -157,96 +157,79 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
 
 // ------------------------------------------------------------------------------------------------
 // knn (replaces knn_cuda.cu:58-94: one thread per centre, a 100-slot max-heap in local memory, heap sort).
-// One thread per centre, the searched cloud broadcast from a shared-memory tile; the nsample best so far live in an
-// ORDERED LIST IN REGISTERS, ascending in (distance, index): a candidate that does not precede the last entry — nearly
-// every candidate once the list has warmed up — costs one compare, an insertion is a chain of compile-time-indexed
-// compare-exchanges (no local memory, no heap sort at the end).  The list has K in {8, 16, 32, 64} slots; a smaller
-// nsample puts K - nsample phantoms at -inf in front so that the last real entry is always slot K - 1.  nsample > 64
-// (the reference allows 100) runs a second pass that keeps only candidates AFTER the 64th of the first pass in
-// (distance, index) order.
+// A WARP per centre, LANES OVER CANDIDATES: the searched cloud goes through a shared-memory tile (structure of
+// arrays) shared by the eight centres of a CTA; a lane evaluates one candidate per step, and the (up to) 32 best so far
+// are an ORDERED LIST HELD ACROSS THE LANES — lane i keeps the i-th nearest (distance, index).  A step first filters
+// its 32 candidates against the current k-th entry (one ballot: nearly always empty once the list has warmed up); a
+// survivor is inserted with one ballot (its rank = how many entries precede it) and one shuffle-up of the tail.
+// No local memory, no heap sort at the end, m x 32 threads instead of m.  nsample > 32 (the reference allows 100) runs
+// further passes, each keeping only candidates AFTER the last entry of the previous pass in (distance, index) order.
 // Same result as the reference: the k smallest by (distance, index) — its strict `d2 < best_dist[0]` keeps the
 // earlier index among equal distances at the boundary (knn_cuda.cu:83) — in ascending distance; entries of EQUAL
-// distance come out in index order here and in heap order there (set-equal on ties).  Slots the
-// cloud cannot fill (n < nsample) keep the reference's initial (1e10, 0) (knn_cuda.cu:74-77).
+// distance come out in index order here and in heap order there.  Slots the cloud cannot fill
+// (n < nsample) keep the reference's initial (1e10, 0) (knn_cuda.cu:74-77).  NaN distances are never kept, as there.
 // ------------------------------------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bk)[K], float d, int qi) {
-  bd[K - 1] = d;
-  bk[K - 1] = qi;
-#pragma unroll
-  for (int k = K - 1; k > 0; k--) {
-    if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bk[k] < bk[k - 1])) {
-      const float td_ = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td_;
-      const int tk_ = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk_;
-    }
-  }
-}
+constexpr int kKnnWarps = 8;
 
-// output slots [done, done + kk) of every centre; done > 0: only candidates after slot done - 1 in (distance, index) order
-template <int K>
-__global__ void __launch_bounds__(128)
-knn_list_kernel(int n, int m, int nsample, int done, int kk, const float *__restrict__ xyz,
+// output slots [done, done + kk) of every centre, kk <= 32; done > 0: only candidates after slot done - 1
+__global__ void __launch_bounds__(kKnnWarps * 32)
+knn_warp_kernel(int n, int m, int nsample, int done, int kk, const float *__restrict__ xyz,
                 const float *__restrict__ new_xyz, int *__restrict__ idx, float *__restrict__ dist2) {
-  __shared__ float4 tile[kTile];
-  const int b = blockIdx.y;
-  const int p = blockIdx.x * 128 + threadIdx.x;
+  __shared__ float tx[kTile], ty[kTile], tz[kTile];
+  const unsigned full = 0xffffffffu;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * kKnnWarps + warp;
   const bool active = p < m;
   const float *pts = xyz + (size_t)b * n * 3;
-  float cx = 0, cy = 0, cz = 0;
+  const float inf = __int_as_float(0x7f800000);
+  float cx = 0, cy = 0, cz = 0, ld0 = -inf;
+  int li0 = -1;
   int *oi = idx + ((size_t)b * m + (active ? p : 0)) * nsample;
   float *od = dist2 + ((size_t)b * m + (active ? p : 0)) * nsample;
-  const float inf = __int_as_float(0x7f800000);
-  float ld = -inf;  // the last entry of the previous pass
-  int li = -1;
   if (active) {
     const float *c = new_xyz + ((size_t)b * m + p) * 3;
     cx = __ldg(c + 0), cy = __ldg(c + 1), cz = __ldg(c + 2);
-    if (done) ld = od[done - 1], li = oi[done - 1];
+    if (done) ld0 = od[done - 1], li0 = oi[done - 1];
   }
-  float bd[K];
-  int bk[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    bd[k] = k < K - kk ? -inf : 1e10f;
-    bk[k] = k < K - kk ? -1 : 0;
-  }
+  float ld = 1e10f, thr_d = 1e10f;  // this lane's entry of the list; the kk-th entry
+  int li = 0, thr_i = 0;
   for (int j0 = 0; j0 < n; j0 += kTile) {
     const int cnt = min(kTile, n - j0);
     __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += 128) {
+    for (int j = threadIdx.x; j < cnt; j += kKnnWarps * 32) {
       const float *c = pts + (size_t)(j0 + j) * 3;
-      tile[j] = make_float4(__ldg(c + 0), __ldg(c + 1), __ldg(c + 2), 0.f);
+      tx[j] = __ldg(c + 0), ty[j] = __ldg(c + 1), tz[j] = __ldg(c + 2);
     }
     __syncthreads();
     if (!active) continue;
-    for (int j = 0; j < cnt; j++) {
-      const float4 c = tile[j];
-      const float d = sqdist(cx - c.x, cy - c.y, cz - c.z);
-      // (NaN distances are never kept, as in the reference)
-      if (d < bd[K - 1] || (d == bd[K - 1] && j0 + j < bk[K - 1])) {
-        if (d > ld || (d == ld && j0 + j > li)) knn_insert<K>(bd, bk, d, j0 + j);
+    for (int t0 = 0; t0 < cnt; t0 += 32) {
+      const int t = t0 + lane, j = j0 + t;
+      bool pass = false;
+      float d = 0.f;
+      if (t < cnt) {
+        d = sqdist(cx - tx[t], cy - ty[t], cz - tz[t]);
+        pass = (d < thr_d || (d == thr_d && j < thr_i)) && (d > ld0 || (d == ld0 && j > li0));
+      }
+      unsigned mask = __ballot_sync(full, pass);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cd = __shfl_sync(full, d, src);
+        const int cj = j0 + t0 + src;
+        if (!(cd < thr_d || (cd == thr_d && cj < thr_i))) continue;  // the k-th entry has moved since the filter
+        const int pos = __popc(__ballot_sync(full, ld < cd || (ld == cd && li < cj)));
+        const float ud = __shfl_up_sync(full, ld, 1);
+        const int ui = __shfl_up_sync(full, li, 1);
+        if (lane > pos) ld = ud, li = ui;
+        else if (lane == pos) ld = cd, li = cj;
+        thr_d = __shfl_sync(full, ld, kk - 1);
+        thr_i = __shfl_sync(full, li, kk - 1);
       }
     }
   }
-  if (!active) return;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    if (k >= K - kk) {
-      od[done + k - (K - kk)] = bd[k];
-      oi[done + k - (K - kk)] = bk[k];
-    }
-  }
-}
-
-template <int K>
-static void knn_list_launch(int b, int n, int m, int nsample, int done, int kk, const float *xyz, const float *new_xyz,
-                            int *idx, float *dist2, cudaStream_t s) {
-  for (int b0 = 0; b0 < b; b0 += 65535) {
-    const int bb = min(65535, b - b0);
-    knn_list_kernel<K><<<dim3((m + 127) / 128, bb), 128, 0, s>>>(
-        n, m, nsample, done, kk, xyz + (size_t)b0 * n * 3, new_xyz + (size_t)b0 * m * 3, idx + (size_t)b0 * m * nsample,
-        dist2 + (size_t)b0 * m * nsample);
-    count_launch();
+  if (active && lane < kk) {
+    od[done + lane] = ld;
+    oi[done + lane] = li;
   }
 }
 
@@ -520,12 +503,15 @@ MVP_API int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const fl
   if (b == 0 || m == 0) return MVP_OK;
   if (!new_xyz || !idx || !dist2 || (n > 0 && !xyz)) return MVP_ERR_INVALID_ARGUMENT;
   cudaStream_t s = (cudaStream_t)stream;
-  for (int done = 0; done < nsample; done += 64) {
-    const int kk = min(64, nsample - done);
-    if (kk <= 8) knn_list_launch<8>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
-    else if (kk <= 16) knn_list_launch<16>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
-    else if (kk <= 32) knn_list_launch<32>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
-    else knn_list_launch<64>(b, n, m, nsample, done, kk, xyz, new_xyz, idx, dist2, s);
+  for (int done = 0; done < nsample; done += 32) {
+    const int kk = min(32, nsample - done);
+    for (int b0 = 0; b0 < b; b0 += 65535) {
+      const int bb = min(65535, b - b0);
+      knn_warp_kernel<<<dim3((m + kKnnWarps - 1) / kKnnWarps, bb), kKnnWarps * 32, 0, s>>>(
+          n, m, nsample, done, kk, xyz + (size_t)b0 * n * 3, new_xyz + (size_t)b0 * m * 3, idx + (size_t)b0 * m * nsample,
+          dist2 + (size_t)b0 * m * nsample);
+      count_launch();
+    }
   }
   return launch_status();
 }
