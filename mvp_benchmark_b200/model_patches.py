@@ -120,6 +120,75 @@ def get_uniform_loss(pcd, percentages=[0.004, 0.006, 0.008, 0.010, 0.012], radiu
     return loss / len(percentages)
 
 
+def sa_module_forward(self, input):
+    """completion/models/vrcnet.py:43-57 (SA_module.forward) with the two convolutions of the NEIGHBOUR tensor moved
+    in front of the gather.  The original gathers the k neighbours' features first — xn = get_edge_features(x, idx), a
+    (B, C, k, N) tensor, 1 GB at the first level — and then applies conv2 and conv3, both 1x1, to it.  A 1x1 convolution
+    acts on every (b, :, j, n) column independently, so it commutes with the gather:
+        conv(get_edge_features(x, idx)) == get_edge_features(conv(x), idx)          (bias included)
+    Here conv2 and conv3 run once per POINT on (B, C, 1, N) — k times fewer multiply-adds, no 1 GB tensor, and their
+    weight / data gradients shrink by the same factor (cuDNN's weight-gradient kernel over (B, C, k, N) is the largest
+    single kernel of the step otherwise) — and the gathers move C/16 and C/4 channels instead of C (SURVEY.md §8f row 4:
+    the grouped-feature MLP; no tensor-core kernel is needed for work that is not done).  Same arithmetic per output
+    element (one dot product over the C input channels); everything after the gathers is the original's code."""
+    import sys
+    x, idx = input
+    if not x.is_cuda or x.dtype != torch.float32:
+        return _ORIGINAL["SA_module.forward"](self, input)
+    gef = sys.modules[type(self).__module__].get_edge_features
+    batch_size, _, _, num_points = x.size()
+    identity = x  # B C 1 N
+    x = self.activation_fn(x)
+    x1, y2, y3 = self.conv1(x), self.conv2(x), self.conv3(x)     # all three on (B, C, 1, N)
+    x2 = gef(y2, idx)                                              # B C/16 K N
+    x3 = gef(y3, idx)                                              # B C/4 K N
+    x2 = x2.contiguous().view(batch_size, -1, 1, num_points)       # B kC 1 N
+    w = self.conv_w(torch.cat([x1, x2], 1)).view(batch_size, -1, self.k, num_points)
+    w = w.repeat(1, self.share_planes, 1, 1)
+    out = w * x3
+    out = torch.sum(out, dim=2, keepdim=True)
+    out = self.activation_fn(out)
+    out = self.conv_out(out)  # B C 1 N
+    out += identity
+    return [out, idx]
+
+
+def _pointwise_conv_forward(self, x):
+    """A THIN nn.Conv1d / nn.Conv2d with a 1x1 kernel as what it is — a matrix product over the channel axis — through
+    torch.baddbmm (a library GEMM: cuBLAS / CUTLASS; NOT a kernel of this repository).  Why: for the thin 1x1
+    convolutions of the completion models ((64, 64, 1, 3072) -> 4, 16 or 64 channels; 68 -> 2; 3 -> 128) cuDNN's
+    heuristics pick `wgrad2d_grouped_direct_kernel` for the weight gradient, 0.5-1.6 ms per call for 0.1-1.6 GFLOP of
+    work: 8.8 ms of a 36 ms VRCNet training step (profiles/r2_model_step.json).  As batched matmuls the same gradients
+    are two small GEMMs.  torch.matmul computes in full fp32 by default where cuDNN uses TF32: a little MORE accurate."""
+    shp = x.shape
+    xs = x.reshape(shp[0], shp[1], -1)
+    w = self.weight.view(1, self.out_channels, self.in_channels).expand(shp[0], -1, -1)
+    if self.bias is not None:
+        y = torch.baddbmm(self.bias.view(1, -1, 1), w, xs)
+    else:
+        y = torch.bmm(w, xs)
+    return y.view(shp[0], self.out_channels, *shp[2:])
+
+
+kPointwiseMaxWeights = 16384  # in_channels * out_channels up to 64 x 256: above that cuDNN's TF32 kernels are the faster ones
+
+
+def apply_pointwise_convs(model, max_weights=kPointwiseMaxWeights):
+    """Route the THIN 1x1, stride-1, ungrouped nn.Conv1d / nn.Conv2d modules of an instantiated model (in_channels x
+    out_channels <= max_weights) through _pointwise_conv_forward (same parameters, same state_dict; opt-in like
+    everything in this file).  Returns the number of modules switched."""
+    import types
+    count = 0
+    for mod in model.modules():
+        if (isinstance(mod, (torch.nn.Conv1d, torch.nn.Conv2d)) and all(k == 1 for k in mod.kernel_size)
+                and all(s_ == 1 for s_ in mod.stride) and not isinstance(mod.padding, str)
+                and all(p_ == 0 for p_ in mod.padding) and all(d == 1 for d in mod.dilation) and mod.groups == 1
+                and mod.in_channels * mod.out_channels <= max_weights):
+            mod.forward = types.MethodType(_pointwise_conv_forward, mod)
+            count += 1
+    return count
+
+
 def calc_cd(output, gt, calc_f1=False):
     """model_utils.py:67-77: the Chamfer operator, then its loss epilogue (two sqrt, four means, three elementwise
     torch kernels) as ONE reduction kernel (fused.chamfer_loss).  Same returns."""
@@ -151,5 +220,11 @@ def apply(*modules):
                 continue
             _ORIGINAL.setdefault("knn_point" if name == "knn_point_all" else name, cur)
             setattr(mod, name, fn)
+            count += 1
+        cls = getattr(mod, "SA_module", None)  # models.vrcnet: the class's forward, not a module-level function
+        if isinstance(cls, type) and cls.forward is not sa_module_forward and all(
+                hasattr(cls, a) for a in ("forward",)):
+            _ORIGINAL.setdefault("SA_module.forward", cls.forward)
+            cls.forward = sa_module_forward
             count += 1
     return count

@@ -391,3 +391,117 @@ def test_fps_gather_and_ball_query_group_chains(ops, cuda):
     got, want = fake.edge_preserve_sampling(feat, pts, 1536, 10), orig_eps(feat, pts, 1536, 10)
     for g_, w_ in zip(got, want):
         assert torch.equal(g_, w_)
+
+
+def test_model_patches_sa_module_conv_commutes_with_gather(ops, cuda):
+    """SA_module.forward with conv2 / conv3 applied before the neighbour gather instead of after
+    it (a 1x1 convolution commutes with the gather) against the original order of operations (vrcnet.py:21-57,
+    restated): same output and gradients up to the rounding of the convolution algorithm cuDNN picks per shape."""
+    import types
+    from torch import nn
+    from mvp_benchmark_b200 import model_patches as mp
+    _, mm = ops
+
+    def get_edge_features(x, idx):                         # model_utils.py:113-124, restated
+        batch_size, num_points, k = idx.size()
+        idx = (idx + torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points).view(-1)
+        x = x.squeeze(2)
+        num_dims = x.size(1)
+        x = x.transpose(2, 1).contiguous()
+        feature = x.view(batch_size * num_points, -1)[idx, :]
+        return feature.view(batch_size, num_points, k, num_dims).permute(0, 3, 2, 1)
+
+    class SA_module(nn.Module):                            # vrcnet.py:21-57, restated
+        def __init__(self, in_planes, rel_planes, mid_planes, out_planes, share_planes=8, k=16):
+            super().__init__()
+            self.share_planes, self.k = share_planes, k
+            self.conv1 = nn.Conv2d(in_planes, rel_planes, kernel_size=1)
+            self.conv2 = nn.Conv2d(in_planes, rel_planes, kernel_size=1)
+            self.conv3 = nn.Conv2d(in_planes, mid_planes, kernel_size=1)
+            self.conv_w = nn.Sequential(nn.ReLU(inplace=False),
+                                        nn.Conv2d(rel_planes * (k + 1), mid_planes // share_planes, kernel_size=1, bias=False),
+                                        nn.ReLU(inplace=False),
+                                        nn.Conv2d(mid_planes // share_planes, k * mid_planes // share_planes, kernel_size=1))
+            self.activation_fn = nn.ReLU(inplace=False)
+            self.conv_out = nn.Conv2d(mid_planes, out_planes, kernel_size=1)
+
+        def forward(self, input):
+            x, idx = input
+            batch_size, _, _, num_points = x.size()
+            identity = x
+            x = self.activation_fn(x)
+            xn = get_edge_features(x, idx)
+            x1, x2, x3 = self.conv1(x), self.conv2(xn), self.conv3(xn)
+            x2 = x2.view(batch_size, -1, 1, num_points).contiguous()
+            w = self.conv_w(torch.cat([x1, x2], 1)).view(batch_size, -1, self.k, num_points)
+            w = w.repeat(1, self.share_planes, 1, 1)
+            out = torch.sum(w * x3, dim=2, keepdim=True)
+            out = self.conv_out(self.activation_fn(out))
+            out = out + identity
+            return [out, idx]
+
+    fake = types.ModuleType("fake_vrcnet")
+    fake.SA_module, fake.get_edge_features = SA_module, get_edge_features
+    SA_module.__module__ = "fake_vrcnet"
+    import sys
+    sys.modules["fake_vrcnet"] = fake
+    try:
+        original_forward = SA_module.forward
+        torch.manual_seed(0)
+        net = SA_module(64, 4, 16, 64, 8, 10).to(cuda)
+        B, N = 3, 768
+        x0 = torch.randn(B, 64, 1, N, device=cuda)
+        idx = torch.randint(0, N, (B, N, 10), device=cuda)
+        a = x0.clone().requires_grad_(True)
+        want = original_forward(net, [a, idx])[0]
+        want.sum().backward()
+        gw = {n_: p.grad.clone() for n_, p in net.named_parameters()}
+        net.zero_grad()
+        assert mp.apply(fake) == 2 and SA_module.forward is mp.sa_module_forward   # get_edge_features and the class
+        b = x0.clone().requires_grad_(True)
+        got = net([b, idx])[0]
+        got.sum().backward()
+        scale = want.abs().max().item()
+        assert (got - want).abs().max().item() <= 2e-3 * scale
+        assert (a.grad - b.grad).abs().max().item() <= 2e-3 * a.grad.abs().max().item()
+        for n_, p in net.named_parameters():
+            assert (p.grad - gw[n_]).abs().max().item() <= 3e-3 * max(gw[n_].abs().max().item(), 1e-6), n_
+    finally:
+        del sys.modules["fake_vrcnet"]
+
+
+def test_model_patches_pointwise_convs(cuda):
+    """1x1 convolutions through torch.matmul (model_patches.apply_pointwise_convs): same module parameters, outputs and
+    gradients equal to nn.Conv1d / nn.Conv2d up to the rounding of the two libraries' algorithms; other convolutions
+    are left alone."""
+    from torch import nn
+    from mvp_benchmark_b200 import model_patches as mp
+    torch.manual_seed(1)
+    net = nn.Sequential(nn.Conv2d(64, 4, 1), nn.ReLU(), nn.Conv2d(4, 40, kernel_size=1, bias=False)).to(cuda)
+    other = nn.Sequential(nn.Conv2d(8, 8, 3, padding=1), nn.Conv1d(8, 8, 1, groups=2)).to(cuda)
+    assert mp.apply_pointwise_convs(other) == 0
+    x = torch.randn(5, 64, 3, 700, device=cuda)
+    a = x.clone().requires_grad_(True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                 # the reference in full fp32, like torch.bmm's default
+    try:
+        want = net(a)
+        want.square().sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    ref = {n_: p.grad.clone() for n_, p in net.named_parameters()}
+    net.zero_grad()
+    assert mp.apply_pointwise_convs(net) == 2
+    b = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2).clone().requires_grad_(True)   # a non-contiguous view works too
+    got = net(b)
+    got.square().sum().backward()
+    assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    assert (a.grad - b.grad).abs().max().item() <= 1e-4 * a.grad.abs().max().item()
+    for n_, p in net.named_parameters():
+        assert (p.grad - ref[n_]).abs().max().item() <= 1e-3 * ref[n_].abs().max().item(), n_
+    big = nn.Conv1d(512, 1024, 1).to(cuda)
+    assert mp.apply_pointwise_convs(big) == 0               # wide ones stay on cuDNN
+    c1 = nn.Conv1d(16, 3, 1).to(cuda)
+    y0 = c1(torch.ones(2, 16, 9, device=cuda))
+    assert mp.apply_pointwise_convs(c1) == 1
+    torch.testing.assert_close(c1(torch.ones(2, 16, 9, device=cuda)), y0, rtol=1e-3, atol=1e-4)

@@ -1,0 +1,29 @@
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.argv = ["model_step.py", "--model", "vrcnet", "--ops", "ours", "--patch-knn"]
+import torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+import model_step as ms
+module, args = ms.load_model("vrcnet", "ours")
+import mvp_benchmark_b200.model_patches as mp
+mp.apply(sys.modules["model_utils"], sys.modules["models.vrcnet"])
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+net = module.Model(args).to(dev).train()
+for mod in net.modules():
+    if isinstance(mod, torch.nn.ReLU):
+        mod.inplace = False
+x, gt = torch.rand(32, 3, 2048, device=dev), torch.rand(32, 2048, 3, device=dev)
+for _ in range(2):
+    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].backward()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
+    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].backward(); torch.cuda.synchronize()
+rows = []
+for e in prof.key_averages(group_by_input_shape=True):
+    if e.device_time_total > 300 and ("conv" in e.key or "mm" in e.key or "topk" in e.key or "index" in e.key or "repeat" in e.key or "cat" in e.key or "mul" == e.key[-3:] or "sum" in e.key or "max" in e.key):
+        rows.append((e.device_time_total / 1e3, e.count, e.key, str(e.input_shapes)[:150]))
+rows.sort(reverse=True)
+for r in rows[:40]:
+    print("%.3f ms x%d %s %s" % r)

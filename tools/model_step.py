@@ -79,6 +79,8 @@ def run_arm(a):
     torch.manual_seed(0)
     net = module.Model(args).to(dev)
     net.train()
+    if a.patch_knn and not a.no_pointwise:
+        mp.apply_pointwise_convs(net)
     # torch >= 1.x refuses the in-place ReLU the reference applies to a view returned by chunk()
     # (vrcnet.py:460 -> :105, "Output 0 of SplitBackward0 is a view and is being modified inplace"): switch the
     # flag on the instantiated modules — same arithmetic, both arms alike, model source untouched.
@@ -206,6 +208,7 @@ def main():
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--patch-knn", action="store_true",
                     help="opt-in: replace model_utils.knn_point / knn by the fused operators (SURVEY.md §8f row 1)")
+    ap.add_argument("--no-pointwise", action="store_true", help="with --patch-knn: keep cuDNN for the 1x1 convolutions")
     ap.add_argument("--ddp", action="store_true", help="N>1: torch DDP instead of mvp_benchmark_b200.dist.allreduce_gradients")
     ap.add_argument("--bucket-mb", type=int, default=32)
     ap.add_argument("--no-overlap", action="store_true", help="N>1: all-reduce after backward instead of overlapped with it")
