@@ -1,3 +1,6 @@
+"""Diagnostic: one patched VRCNet training step under torch.profiler with record_shapes — device time per aten op and input
+shape (how the thin 1x1 convolutions whose weight gradient cuDNN runs through wgrad2d_grouped_direct_kernel were found).
+Run under gpurun: python tools/model_ops_by_shape.py"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.argv = ["model_step.py", "--model", "vrcnet", "--ops", "ours", "--patch-knn"]
@@ -10,6 +13,7 @@ mp.apply(sys.modules["model_utils"], sys.modules["models.vrcnet"])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = module.Model(args).to(dev).train()
+mp.apply_pointwise_convs(net)
 for mod in net.modules():
     if isinstance(mod, torch.nn.ReLU):
         mod.inplace = False
@@ -22,8 +26,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_sh
     net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].backward(); torch.cuda.synchronize()
 rows = []
 for e in prof.key_averages(group_by_input_shape=True):
-    if e.device_time_total > 300 and ("conv" in e.key or "mm" in e.key or "topk" in e.key or "index" in e.key or "repeat" in e.key or "cat" in e.key or "mul" == e.key[-3:] or "sum" in e.key or "max" in e.key):
+    if e.device_time_total > 150 and e.key.startswith("aten::") and not e.key.startswith("aten::_") :
         rows.append((e.device_time_total / 1e3, e.count, e.key, str(e.input_shapes)[:150]))
 rows.sort(reverse=True)
-for r in rows[:40]:
+for r in rows[:70]:
     print("%.3f ms x%d %s %s" % r)
