@@ -206,6 +206,12 @@ int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight, mvp_st
 int mvp_three_nn_weights_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
                             float *weight, void *workspace, size_t workspace_bytes, mvp_stream_t stream);
 
+/* The k <= 32 largest entries of every row of a (rows, cols) fp32 score matrix, descending, equal scores in ascending
+ * column order — what completion/model_utils.py:242-247 asks torch.topk for on its (B, N, N) matrix of negative
+ * feature-space distances.  Any of values (rows,k) / idx64 (rows,k) int64 / idx32 (rows,k) int32 may be NULL. */
+int mvp_topk_rows(long long rows, int cols, int k, const float *scores, float *values, long long *idx64, int *idx32,
+                  mvp_stream_t stream);
+
 /* furthest_point_sample followed by gather_points on the transposed cloud (completion/model_utils.py:91-93,
  * completion/models/vrcnet.py:451) as ONE launch: idx (b,m) as mvp_furthest_point_sampling, and the sampled points
  * themselves, (b,m,3) or — channels_first != 0 — (b,3,m), the layout gather_points returns. */

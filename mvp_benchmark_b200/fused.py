@@ -167,3 +167,20 @@ class _BallQueryGroup(torch.autograd.Function):
         grad = torch.zeros(ctx.shape, device=g_grouped.device, dtype=g_grouped.dtype)
         grad.scatter_add_(1, idx.long().view(B, -1, 1).expand(-1, -1, 3), g_grouped.reshape(B, -1, 3))
         return None, None, None, grad, None
+
+
+def topk_rows(scores, k):
+    """The k largest entries along the last axis of `scores` (..., cols), descending, equal scores in ascending index:
+    (values, indices int64) like torch.topk(scores, k, dim=-1) — one warp per row, no multi-block radix select.  For
+    the feature-space kNN of the completion models (completion/model_utils.py:242-247).  k <= 32; not differentiable
+    through the values (the models only use the indices)."""
+    s_ = scores.detach().contiguous()
+    dev = _lib.require_cuda(s_, dtype=torch.float32, what="topk_rows")
+    cols = s_.size(-1)
+    rows = s_.numel() // cols
+    vals = torch.empty(*s_.shape[:-1], k, device=dev, dtype=torch.float32)
+    idx = torch.empty(*s_.shape[:-1], k, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.mvp_topk_rows(rows, cols, int(k), _lib.ptr(s_), _lib.ptr(vals), _lib.ptr(idx), None,
+                                          _lib.stream_of(s_)), "mvp_topk_rows")
+    return vals, idx

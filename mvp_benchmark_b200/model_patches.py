@@ -15,7 +15,8 @@ step); the replacements run one exact grid search (fused.knn_points).  Differenc
 neighbours are ranked by the directly evaluated squared distance, ties by index, where the original ranks by
 the matmul expansion (≈1e-7 apart; near-ties may swap) and leaves exact ties unspecified; returned distances
 (knn_point) are recomputed from the gathered points, differentiable like the original's.
-Point sets that are not 3-D (feature-space kNN) fall through to the original function."""
+Point sets that are not 3-D (feature-space kNN) keep the original's score matrix and replace only its torch.topk by
+fused.topk_rows (one warp per row)."""
 import torch
 
 from . import fused
@@ -32,6 +33,12 @@ def _neg_sqdist(queries, cloud, idx):
 
 def knn(x, k):
     """model_utils.py:242-247: x (B, C, N) -> idx (B, N, k) int64 of the k nearest points (self included)."""
+    if x.dim() == 3 and x.size(1) != 3 and x.is_cuda and x.dtype == torch.float32 and k <= min(x.size(2), 32):
+        # feature-space neighbours (ECG's / EF_expansion's dynamic graph): the original's score matrix, its top-k by
+        # one warp per row (fused.topk_rows) instead of torch.topk's multi-block radix select
+        inner = -2 * torch.matmul(x.transpose(2, 1).contiguous(), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        return fused.topk_rows(-xx - inner - xx.transpose(2, 1).contiguous(), k)[1]
     if x.dim() != 3 or x.size(1) != 3 or not x.is_cuda or x.dtype != torch.float32 or k > min(x.size(2), 64):
         return _ORIGINAL["knn"](x, k)
     _, idx = fused.knn_points(k, x.transpose(1, 2))

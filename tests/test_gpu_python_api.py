@@ -225,8 +225,13 @@ def test_model_patches_knn_and_knn_point(cuda, cpu):
     assert agree > 0.995, agree
     negd.sum().backward()
     assert sub.grad is not None and torch.isfinite(sub.grad).all()
-    feat = torch.randn(2, 64, 100, device=cuda)            # feature-space kNN: not ours
-    fake.knn(feat, 5)
+    feat = torch.randn(2, 64, 100, device=cuda)            # feature-space kNN: the original's matrix, our row-wise top-k
+    got = fake.knn(feat, 5)
+    inner = -2 * torch.matmul(feat.transpose(2, 1).contiguous(), feat)
+    xx = torch.sum(feat ** 2, dim=1, keepdim=True)
+    want = (-xx - inner - xx.transpose(2, 1).contiguous()).topk(k=5, dim=-1)[1]
+    assert not calls and got.dtype == torch.int64 and torch.equal(got, want)
+    fake.knn(feat, 40)                                      # k > 32: the original
     assert calls == ["knn"]
 
 
@@ -505,3 +510,25 @@ def test_model_patches_pointwise_convs(cuda):
     y0 = c1(torch.ones(2, 16, 9, device=cuda))
     assert mp.apply_pointwise_convs(c1) == 1
     torch.testing.assert_close(c1(torch.ones(2, 16, 9, device=cuda)), y0, rtol=1e-3, atol=1e-4)
+
+
+
+@pytest.mark.parametrize("shape,k", [((3, 700, 700), 16), ((2, 5, 33), 32), ((4096, 40), 1), ((2, 3, 2048, 2048), 20), ((1, 9, 31), 31)])
+def test_topk_rows_vs_torch(cuda, shape, k):
+    """fused.topk_rows (mvp_topk_rows) against torch.topk: identical values; indices identical where the values are
+    distinct, ascending index inside runs of equal values (lattice-like scores), NaN never selected."""
+    from mvp_benchmark_b200 import fused
+    g = torch.Generator(device=cuda).manual_seed(9)
+    x = torch.randn(*shape, device=cuda, generator=g)
+    v, i = fused.topk_rows(x, k)
+    wv, wi = x.topk(k, dim=-1)
+    assert i.dtype == torch.int64 and torch.equal(v, wv) and torch.equal(i, wi)
+    q = torch.round(x * 2) / 2                               # many exact ties
+    q[..., 0] = float("nan")
+    v, i = fused.topk_rows(q, min(k, shape[-1] - 1))
+    wv, _ = torch.nan_to_num(q, nan=float("-inf")).topk(min(k, shape[-1] - 1), dim=-1)
+    assert torch.equal(v, wv) and torch.equal(torch.gather(q, -1, i), v) and (i != 0).all()
+    same = v[..., 1:] == v[..., :-1]
+    assert (i[..., 1:][same] > i[..., :-1][same]).all()      # ties in ascending index
+    srt = i.sort(dim=-1)[0]
+    assert (srt[..., 1:] != srt[..., :-1]).all()             # no index twice
