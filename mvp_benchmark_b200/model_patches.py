@@ -168,6 +168,8 @@ def _pointwise_conv_forward(self, x):
     work: 8.8 ms of a 36 ms VRCNet training step (profiles/r2_model_step.json).  As batched matmuls the same gradients
     are two small GEMMs.  torch.matmul computes in full fp32 by default where cuDNN uses TF32: a little MORE accurate."""
     shp = x.shape
+    if 2.0 * x.numel() * self.out_channels > kPointwiseMaxFlops:
+        return self._conv_forward(x, self.weight, self.bias)   # a long tensor: cuDNN's TF32 kernels beat an fp32 GEMM
     xs = x.reshape(shp[0], shp[1], -1)
     w = self.weight.view(1, self.out_channels, self.in_channels).expand(shp[0], -1, -1)
     if self.bias is not None:
@@ -178,6 +180,7 @@ def _pointwise_conv_forward(self, x):
 
 
 kPointwiseMaxWeights = 16384  # in_channels * out_channels up to 64 x 256: above that cuDNN's TF32 kernels are the faster ones
+kPointwiseMaxFlops = 4e9      # ... and so they are for a thin convolution over a very long tensor (decided per call)
 
 
 def apply_pointwise_convs(model, max_weights=kPointwiseMaxWeights):

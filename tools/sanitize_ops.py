@@ -68,5 +68,31 @@ la, lc = R(3, 2048).requires_grad_(True), R(3, 1024).requires_grad_(True)
 cp, ct = fused.chamfer_loss(la, lc)
 (cp.sum() + ct.sum()).backward()
 fused.three_nn_weights(u, kn)
+# ---- round 2: the completion pass of the Chamfer grid path on the geometries that reach each of its branches
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import _data  # noqa: E402
+T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+cdf = metrics.cd()
+cdf(T(_data.uniform(2, 4096, 1)), T(_data.blob(2, 4096, 2)))          # far queries, a warp per query
+cdf(T(_data.uniform(2, 4096, 1)), T(_data.shifted(2, 4096, 2)))       # disjoint: lanes over queries, list regrouping
+cdf(T(_data.clustered(2, 4096, 1)), T(_data.clustered(2, 4096, 2)))   # dense cells: Z-order re-sort (bitonic), plan list B
+cdf(T(_data.outliers(2, 2048, 1)), T(_data.outliers(2, 3000, 2)))
+cdf(T(_data.constant(2, 2048, 1)), T(_data.uniform(2, 2048, 2)))      # one point n times
+if not small:
+    cdf(T(_data.uniform(1, 40000, 1)), T(_data.blob(1, 40000, 2)))    # two level-2 nodes
+# ---- round 2: fused chains, cluster FPS, warp-per-centre knn, row-wise top-k
+p = R(3, 2048, 3).requires_grad_(True)
+i_, o_ = fused.fps_gather(p, 512)
+o_.sum().backward()
+fused.fps_gather(R(2, 6000, 3), 200, channels_first=True)              # four-CTA cluster + epilogue
+mm.furthest_point_sample(R(2, 8192, 3), 300)
+q = R(2, 2048, 3).requires_grad_(True)
+_, gq = fused.ball_query_group(0, 0.1, 12, q, q[:, :102].detach().contiguous())
+gq.sum().backward()
+mm.knn(16, R(2, 2048, 3), R(2, 300, 3))
+mm.knn(100, R(1, 1500, 3), R(1, 77, 3))
+mm.knn(9, R(2, 5, 3), R(2, 7, 3))
+fused.topk_rows(torch.randn(3, 700, 700, device=dev, generator=g), 16)
+fused.topk_rows(torch.randn(5, 33, device=dev, generator=g), 32)
 torch.cuda.synchronize()
 print("sanitize_ops: all entry points ran,", _lib.launch_count(), "kernels launched")
