@@ -206,6 +206,15 @@ int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight, mvp_st
 int mvp_three_nn_weights_ws(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
                             float *weight, void *workspace, size_t workspace_bytes, mvp_stream_t stream);
 
+/* gather_points over the pk neighbours of every sampled point followed by torch.max over the neighbours
+ * (completion/model_utils.py:97-102: edge_preserve_sampling) as ONE launch: points (b,c,n), idx (b,npoints,k) ->
+ * out (b,c,npoints) and arg (b,c,npoints) int32, the neighbour index attaining each maximum (first among equals).
+ * n <= 16384.  mvp_gather_max_grad: grad_points (b,c,n) = grad_out scattered by arg, fully written. */
+int mvp_gather_max(int b, int c, int n, int npoints, int k, const float *points, const int *idx, float *out, int *arg,
+                   mvp_stream_t stream);
+int mvp_gather_max_grad(int b, int c, int n, int npoints, const float *grad_out, const int *arg, float *grad_points,
+                        mvp_stream_t stream);
+
 /* The k <= 32 largest entries of every row of a (rows, cols) fp32 score matrix, descending, equal scores in ascending
  * column order — what completion/model_utils.py:242-247 asks torch.topk for on its (B, N, N) matrix of negative
  * feature-space distances.  Any of values (rows,k) / idx64 (rows,k) int64 / idx32 (rows,k) int32 may be NULL. */

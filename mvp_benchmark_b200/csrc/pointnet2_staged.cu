@@ -354,6 +354,69 @@ int scatter_csr_launch(bool interp, int b, int c, int rows, int cols, const floa
   return launch_status();
 }
 
+// ---- gather + max over the neighbours (edge_preserve_sampling) ----------------------------------
+// completion/model_utils.py:97-102 gathers the pk nearest neighbours' features of every sampled point with gather_points
+// — a (B, C, M * pk) tensor, 250 MB at the first level — views it as (B, C, M, pk) and takes torch.max over pk.  Here
+// the CTA that has a group of channel rows in shared memory takes the maximum over a point's pk neighbours on the spot:
+// out[b,c,p] = max_j points[b,c,idx[b,p,j]], arg[b,c,p] = the neighbour index that attains it (the first j among equal
+// maxima: torch.max's rule), which is all the backward pass needs — grad_points[b,c,arg[b,c,p]] += grad_out[b,c,p],
+// accumulated in zeroed shared-memory rows and written once.  The (B, C, M, pk) tensor never exists.
+constexpr int kGmG = 8;  // channel rows per CTA (register arrays of the running maxima)
+
+__global__ void __launch_bounds__(kStThreads)
+gather_max_staged_kernel(int c, int n, int mpts, int k, int G, int chunk, const float *__restrict__ points,
+                         const int *__restrict__ idx, float *__restrict__ out, int *__restrict__ arg) {
+  extern __shared__ __align__(128) float rows[];
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
+  stage_rows(rows, points + ((size_t)b * c + c0) * n, gcount * n, &bar);
+  const int p0 = blockIdx.y * chunk, p1 = min(mpts, p0 + chunk);
+  float *oo = out + ((size_t)b * c + c0) * mpts;
+  int *oa = arg + ((size_t)b * c + c0) * mpts;
+  const float ninf = __int_as_float(0xff800000);
+  for (int p = p0 + threadIdx.x; p < p1; p += kStThreads) {
+    const int *id = idx + ((size_t)b * mpts + p) * k;
+    float best[kGmG];
+    int bi[kGmG];
+#pragma unroll
+    for (int g = 0; g < kGmG; g++) best[g] = ninf, bi[g] = 0;
+    for (int j = 0; j < k; j++) {
+      const int src = __ldg(id + j);
+#pragma unroll
+      for (int g = 0; g < kGmG; g++) {
+        if (g < gcount) {
+          const float v = rows[g * n + src];
+          if (v > best[g] || j == 0) best[g] = v, bi[g] = src;  // strict: the first of equal maxima stays
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kGmG; g++) {
+      if (g < gcount) {
+        oo[(size_t)g * mpts + p] = best[g];
+        oa[(size_t)g * mpts + p] = bi[g];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStThreads)
+gather_max_grad_staged_kernel(int c, int n, int mpts, int G, const float *__restrict__ grad_out,
+                              const int *__restrict__ arg, float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) float rows[];
+  const int b = blockIdx.z, c0 = blockIdx.x * G, gcount = min(G, c - c0);
+  for (int i = threadIdx.x; i < gcount * n; i += kStThreads) rows[i] = 0.f;
+  __syncthreads();
+  const float *go = grad_out + ((size_t)b * c + c0) * mpts;
+  const int *ga = arg + ((size_t)b * c + c0) * mpts;
+  for (int g = 0; g < gcount; g++)
+    for (int p = threadIdx.x; p < mpts; p += kStThreads)
+      atomicAdd(&rows[g * n + __ldg(ga + (size_t)g * mpts + p)], __ldg(go + (size_t)g * mpts + p));
+  __syncthreads();
+  float *gp = grad_points + ((size_t)b * c + c0) * n;
+  for (int i = threadIdx.x; i < gcount * n; i += kStThreads) gp[i] = rows[i];
+}
+
 // ---- launch plans --------------------------------------------------------------------------------------------------
 // rows: source columns per channel (n for gather, m for interpolate); cols: gathered columns per channel
 bool staged_applicable(int b, int c, int rows, int cols) {
@@ -433,4 +496,47 @@ int three_interpolate_grad_staged_launch(int b, int c, int n, int m, const float
   return launch_status();
 }
 
+
+int gather_max_launch(int b, int c, int n, int mpts, int k, const float *points, const int *idx, float *out, int *arg,
+                      cudaStream_t s) {
+  const int G = std::min(group_size(c, n), kGmG), groups = (c + G - 1) / G;
+  const int chunk = column_chunk(b, groups, n, mpts * std::max(k, 1));  // (k reads per output: more columns' worth of work)
+  const size_t smem = (size_t)G * n * 4;
+  if (int rc = set_smem<20>(gather_max_staged_kernel, smem)) return rc;
+  dim3 grid(groups, (mpts + chunk - 1) / chunk, b);
+  gather_max_staged_kernel<<<grid, kStThreads, smem, s>>>(c, n, mpts, k, G, chunk, points, idx, out, arg);
+  count_launch();
+  return launch_status();
+}
+
+int gather_max_grad_launch(int b, int c, int n, int mpts, const float *grad_out, const int *arg, float *grad_points,
+                           cudaStream_t s) {
+  const int G = std::min(group_size(c, n), kGmG), groups = (c + G - 1) / G;
+  const size_t smem = (size_t)G * n * 4;
+  if (int rc = set_smem<21>(gather_max_grad_staged_kernel, smem)) return rc;
+  gather_max_grad_staged_kernel<<<dim3(groups, 1, b), kStThreads, smem, s>>>(c, n, mpts, G, grad_out, arg, grad_points);
+  count_launch();
+  return launch_status();
+}
+
 }  // namespace mvp
+
+// gather_points over the pk neighbours of every sampled point followed by a maximum over the neighbours
+// (completion/model_utils.py:97-102) as ONE launch.  points (b,c,n), idx (b,npoints,k) -> out (b,c,npoints) and
+// arg (b,c,npoints), the neighbour index that attains each maximum (the first among equals).  n * 4 bytes <= 64 KB.
+MVP_API int mvp_gather_max(int b, int c, int n, int npoints, int k, const float *points, const int *idx, float *out,
+                           int *arg, mvp_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || k <= 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0 || npoints == 0) return MVP_OK;
+  if (!points || !idx || !out || !arg || b > 65535 || (size_t)n * 4 > mvp::kStRowBytes) return MVP_ERR_INVALID_ARGUMENT;
+  return mvp::gather_max_launch(b, c, n, npoints, k, points, idx, out, arg, (cudaStream_t)stream);
+}
+
+// its backward: grad_points (b,c,n), fully written, = grad_out (b,c,npoints) scattered by arg (b,c,npoints)
+MVP_API int mvp_gather_max_grad(int b, int c, int n, int npoints, const float *grad_out, const int *arg,
+                                float *grad_points, mvp_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0 || c == 0) return MVP_OK;
+  if (!grad_out || !arg || !grad_points || b > 65535 || (size_t)n * 4 > mvp::kStRowBytes) return MVP_ERR_INVALID_ARGUMENT;
+  return mvp::gather_max_grad_launch(b, c, n, npoints, grad_out, arg, grad_points, (cudaStream_t)stream);
+}

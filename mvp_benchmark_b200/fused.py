@@ -184,3 +184,41 @@ def topk_rows(scores, k):
         _lib.check(_lib.lib.mvp_topk_rows(rows, cols, int(k), _lib.ptr(s_), _lib.ptr(vals), _lib.ptr(idx), None,
                                           _lib.stream_of(s_)), "mvp_topk_rows")
     return vals, idx
+
+
+class _GatherMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        f, i = features.contiguous(), idx.contiguous()
+        dev = _lib.require_cuda(f, dtype=torch.float32, what="gather_max")
+        if i.dtype != torch.int32 or i.device != f.device:
+            raise _lib.MvpOpsError("gather_max: idx must be an int32 CUDA tensor on the features' device")
+        B, C, N = f.shape
+        M, K = i.shape[1], i.shape[2]
+        out = torch.empty(B, C, M, device=dev, dtype=torch.float32)
+        arg = torch.empty(B, C, M, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.mvp_gather_max(B, C, N, M, K, _lib.ptr(f), _lib.ptr(i), _lib.ptr(out), _lib.ptr(arg),
+                                               _lib.stream_of(f)), "mvp_gather_max")
+        ctx.save_for_backward(arg)
+        ctx.n = N
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        g = g.contiguous()
+        B, C, M = g.shape
+        grad = torch.empty(B, C, ctx.n, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib.mvp_gather_max_grad(B, C, ctx.n, M, _lib.ptr(g), _lib.ptr(arg), _lib.ptr(grad),
+                                                    _lib.stream_of(g)), "mvp_gather_max_grad")
+        return grad, None
+
+
+def gather_max(features, idx):
+    """max over the K neighbours of every point of their gathered features, without the gathered tensor:
+    features (B, C, N), idx (B, M, K) int32 -> (B, C, M) — `gather_points(features, idx.view(B, M * K)).view(B, C, M, K)`
+    followed by `torch.max(..., 3)[0]` (completion/model_utils.py:97-102) as ONE launch; the gradient goes to the
+    neighbour that attained each maximum (the first among equals, as torch.max routes it).  N <= 16384."""
+    return _GatherMax.apply(features, idx)

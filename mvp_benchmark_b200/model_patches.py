@@ -80,8 +80,8 @@ def three_nn_upsampling(target_points, source_points):
 
 def edge_preserve_sampling(feature_input, point_input, num_samples, k=10):
     """model_utils.py:86-108 with its first two statements (furthest_point_sample, then transpose + gather_points +
-    transpose back) as ONE launch (fused.fps_gather); everything after that is the original's
-    sequence of operator calls, through whatever knn_point / gather_points / grouping_operation the module has."""
+    transpose back) as ONE launch (fused.fps_gather) and the neighbour-feature gather + torch.max
+    as ONE launch (fused.gather_max: the (B, C, M, pk) tensor never exists); the rest is the original's sequence."""
     if not point_input.is_cuda or point_input.dtype != torch.float32 or point_input.dim() != 3 or point_input.size(2) != 3:
         return _ORIGINAL["edge_preserve_sampling"](feature_input, point_input, num_samples, k)
     import mm3d_pn2
@@ -90,9 +90,12 @@ def edge_preserve_sampling(feature_input, point_input, num_samples, k=10):
     pk = int(min(k, num_points))
     _, pn_idx = knn_point(pk, point_input, point_output)
     pn_idx = pn_idx.detach().int()
-    neighbor_feature = mm3d_pn2.gather_points(feature_input, pn_idx.view(batch_size, num_samples * pk)).view(
-        batch_size, feature_size, num_samples, pk)
-    neighbor_feature, _ = torch.max(neighbor_feature, 3)
+    if feature_input.is_cuda and feature_input.dtype == torch.float32 and num_points <= 16384:
+        neighbor_feature = fused.gather_max(feature_input, pn_idx)   # gather + max over the pk neighbours: ONE launch
+    else:
+        neighbor_feature = mm3d_pn2.gather_points(feature_input, pn_idx.view(batch_size, num_samples * pk)).view(
+            batch_size, feature_size, num_samples, pk)
+        neighbor_feature, _ = torch.max(neighbor_feature, 3)
     center_feature = mm3d_pn2.grouping_operation(feature_input, p_idx.unsqueeze(2)).view(batch_size, -1, num_samples)
     net = torch.cat((center_feature, neighbor_feature), 1)
     return net, p_idx, pn_idx, point_output

@@ -390,6 +390,19 @@ def test_fps_gather_and_ball_query_group_chains(ops, cuda):
         center_feature = mm.grouping_operation(feature_input, p_idx.unsqueeze(2)).view(batch_size, -1, num_samples)
         return torch.cat((center_feature, neighbor_feature), 1), p_idx, pn_idx, point_output
 
+    # gather + max over the neighbours (fused.gather_max) against gather_points + torch.max, ties included
+    for B_, C_, N_, M_, K_ in ((4, 64, 3072, 1536, 10), (2, 37, 700, 333, 16), (3, 5, 16384, 100, 3), (70, 3, 64, 64, 1)):
+        feat = torch.randn(B_, C_, N_, device=cuda)
+        feat = torch.round(feat * 4) / 4                    # exact ties: the first neighbour among equal maxima wins
+        nidx = torch.randint(0, N_, (B_, M_, K_), device=cuda, dtype=torch.int32)
+        a, c = feat.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+        got = fused.gather_max(a, nidx)
+        want, _ = torch.max(mm.gather_points(c, nidx.view(B_, M_ * K_)).view(B_, C_, M_, K_), 3)
+        assert torch.equal(got, want)
+        g = torch.randn_like(got)
+        got.backward(g), want.backward(g)
+        torch.testing.assert_close(a.grad, c.grad, rtol=1e-5, atol=1e-5)
+
     fake = types.SimpleNamespace(edge_preserve_sampling=orig_eps, knn_point=orig_knn_point)
     assert mp.apply(fake) == 2
     pts, feat = T(_data.uniform(4, 3072, 43), cuda), torch.randn(4, 64, 3072, device=cuda)
