@@ -215,6 +215,16 @@ int mvp_gather_max(int b, int c, int n, int npoints, int k, const float *points,
 int mvp_gather_max_grad(int b, int c, int n, int npoints, const float *grad_out, const int *arg, float *grad_points,
                         mvp_stream_t stream);
 
+/* SA_module's attention-weighted aggregation of the neighbours (completion/models/vrcnet.py:49-52: get_edge_features,
+ * repeat of the weights over share_planes, multiply, sum over k) as ONE launch without its (B, C, k, N) intermediates:
+ * out[b,ch,p] = sum_j w[b, ch mod cw, j, p] * y[b, ch, idx[b,p,j]].  y (b,c,n), idx (b,n,k) int32, w (b,cw,k,n),
+ * out (b,c,n); c = S * cw with S <= 8 channels sharing a weight row; n <= 6144.  _grad: grad_y (b,c,n) and
+ * grad_w (b,cw,k,n), fully written. */
+int mvp_neighbor_weighted_sum(int b, int c, int cw, int n, int k, const float *y, const int *idx, const float *w,
+                              float *out, mvp_stream_t stream);
+int mvp_neighbor_weighted_sum_grad(int b, int c, int cw, int n, int k, const float *y, const int *idx, const float *w,
+                                   const float *grad_out, float *grad_y, float *grad_w, mvp_stream_t stream);
+
 /* The k <= 32 largest entries of every row of a (rows, cols) fp32 score matrix, descending, equal scores in ascending
  * column order — what completion/model_utils.py:242-247 asks torch.topk for on its (B, N, N) matrix of negative
  * feature-space distances.  Any of values (rows,k) / idx64 (rows,k) int64 / idx32 (rows,k) int32 may be NULL. */

@@ -62,6 +62,8 @@ def _load():
         "mvp_three_nn_weights": (_c_int, [_c_int] * 2 + [_p] * 2 + [_p]),
         "mvp_gather_max": (_c_int, [_c_int] * 5 + [_p] * 4 + [_p]),
         "mvp_gather_max_grad": (_c_int, [_c_int] * 4 + [_p] * 3 + [_p]),
+        "mvp_neighbor_weighted_sum": (_c_int, [_c_int] * 5 + [_p] * 4 + [_p]),
+        "mvp_neighbor_weighted_sum_grad": (_c_int, [_c_int] * 5 + [_p] * 6 + [_p]),
         "mvp_topk_rows": (_c_int, [ctypes.c_longlong, _c_int, _c_int] + [_p] * 4 + [_p]),
         "mvp_three_nn_weights_ws": (_c_int, [_c_int] * 3 + [_p] * 6 + [_c_size_t, _p]),
         "mvp_furthest_point_sampling_gather": (_c_int, [_c_int] * 3 + [_p] * 4 + [_c_int, _p]),

@@ -417,6 +417,92 @@ gather_max_grad_staged_kernel(int c, int n, int mpts, int G, const float *__rest
   for (int i = threadIdx.x; i < gcount * n; i += kStThreads) gp[i] = rows[i];
 }
 
+// ---- attention-weighted sum over the neighbours (SA_module, vrcnet.py:49-52) ---------------
+// After the 1x1 convolutions have been moved in front of the gather (model_patches.sa_module_forward), SA_module still
+// materialises x3 = get_edge_features(y3, idx) (B, C, k, N), repeats the attention weights w (B, C/S, k, N) S times
+// along the channels, multiplies and sums over k: four (B, C, k, N) tensors forward, as many backward.  Here
+//     out[b,c,p] = sum_j w[b, c mod Cw, j, p] * y[b, c, idx[b,p,j]]
+// is one kernel: a CTA owns the S channels { cw, cw + Cw, ... } that SHARE a weight row, stages their S rows of y in
+// shared memory, and a thread walks the k neighbours of its point once — one index load, one weight load (coalesced
+// along p), S shared-memory reads and S fmas per neighbour.  Backward: grad_w[b,cw,j,p] = sum_s g[b,c_s,p] y[b,c_s,idx]
+// (same staging, summed in registers) and grad_y[b,c,m] = sum over { (p,j) : idx[b,p,j] = m } of g[b,c,p] w[b,cw,j,p]
+// (accumulated in zeroed shared-memory rows, written once: no global atomics).
+constexpr int kNwS = 8;  // channels sharing a weight row (share_planes)
+
+// MODE 0: forward (out).  MODE 1: grad_w (a = grad_out).  grid (Cw, column chunks, b)
+template <int MODE>
+__global__ void __launch_bounds__(kStThreads)
+nbr_wsum_kernel(int c, int cw, int n, int k, int S, int chunk, const float *__restrict__ y, const int *__restrict__ idx,
+                const float *__restrict__ w, const float *__restrict__ a, float *__restrict__ out) {
+  extern __shared__ __align__(128) float rows[];
+  const int b = blockIdx.z, w0 = blockIdx.x;
+  for (int s_ = 0; s_ < S; s_++) {
+    const float *src = y + ((size_t)b * c + w0 + (size_t)s_ * cw) * n;
+    for (int i = threadIdx.x; i < n; i += kStThreads) rows[s_ * n + i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int p0 = blockIdx.y * chunk, p1 = min(n, p0 + chunk);
+  for (int p = p0 + threadIdx.x; p < p1; p += kStThreads) {
+    const int *id = idx + ((size_t)b * n + p) * k;
+    const float *wp = w + ((size_t)b * cw + w0) * k * n + p;
+    float acc[kNwS];
+#pragma unroll
+    for (int s_ = 0; s_ < kNwS; s_++) {
+      acc[s_] = 0.f;
+      if (MODE == 1 && s_ < S) acc[s_] = __ldg(a + ((size_t)b * c + w0 + (size_t)s_ * cw) * n + p);  // upstream gradients
+    }
+    for (int j = 0; j < k; j++) {
+      const int src = __ldg(id + j);
+      if (MODE == 0) {
+        const float wv = __ldg(wp + (size_t)j * n);
+#pragma unroll
+        for (int s_ = 0; s_ < kNwS; s_++)
+          if (s_ < S) acc[s_] = __fmaf_rn(wv, rows[s_ * n + src], acc[s_]);
+      } else {
+        float d = 0.f;
+#pragma unroll
+        for (int s_ = 0; s_ < kNwS; s_++)
+          if (s_ < S) d = __fmaf_rn(acc[s_], rows[s_ * n + src], d);
+        out[(((size_t)b * cw + w0) * k + j) * n + p] = d;
+      }
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int s_ = 0; s_ < kNwS; s_++)
+        if (s_ < S) out[((size_t)b * c + w0 + (size_t)s_ * cw) * n + p] = acc[s_];
+    }
+  }
+}
+
+// grad_y: grid (Cw, 1, b): a CTA produces the S complete gradient rows of its channels
+__global__ void __launch_bounds__(kStThreads)
+nbr_wsum_grad_y_kernel(int c, int cw, int n, int k, int S, const int *__restrict__ idx, const float *__restrict__ w,
+                       const float *__restrict__ g, float *__restrict__ grad_y) {
+  extern __shared__ __align__(128) float rows[];
+  const int b = blockIdx.z, w0 = blockIdx.x;
+  for (int i = threadIdx.x; i < S * n; i += kStThreads) rows[i] = 0.f;
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += kStThreads) {
+    const int *id = idx + ((size_t)b * n + p) * k;
+    const float *wp = w + ((size_t)b * cw + w0) * k * n + p;
+    float gv[kNwS];
+#pragma unroll
+    for (int s_ = 0; s_ < kNwS; s_++) gv[s_] = s_ < S ? __ldg(g + ((size_t)b * c + w0 + (size_t)s_ * cw) * n + p) : 0.f;
+    for (int j = 0; j < k; j++) {
+      const int src = __ldg(id + j);
+      const float wv = __ldg(wp + (size_t)j * n);
+#pragma unroll
+      for (int s_ = 0; s_ < kNwS; s_++)
+        if (s_ < S) atomicAdd(&rows[s_ * n + src], gv[s_] * wv);
+    }
+  }
+  __syncthreads();
+  for (int s_ = 0; s_ < S; s_++) {
+    float *dst = grad_y + ((size_t)b * c + w0 + (size_t)s_ * cw) * n;
+    for (int i = threadIdx.x; i < n; i += kStThreads) dst[i] = rows[s_ * n + i];
+  }
+}
+
 // ---- launch plans --------------------------------------------------------------------------------------------------
 // rows: source columns per channel (n for gather, m for interpolate); cols: gathered columns per channel
 bool staged_applicable(int b, int c, int rows, int cols) {
@@ -519,6 +605,31 @@ int gather_max_grad_launch(int b, int c, int n, int mpts, const float *grad_out,
   return launch_status();
 }
 
+
+int nbr_wsum_launch(int mode, int b, int c, int cw, int n, int k, const float *y, const int *idx, const float *w,
+                    const float *a, float *out, cudaStream_t s) {
+  const int S = c / cw;
+  const size_t smem = (size_t)S * n * 4;
+  if (mode == 2) {
+    if (int rc = set_smem<32>(nbr_wsum_grad_y_kernel, smem)) return rc;
+    nbr_wsum_grad_y_kernel<<<dim3(cw, 1, b), kStThreads, smem, s>>>(c, cw, n, k, S, idx, w, a, out);
+  } else {
+    int split = 1;
+    while ((long long)b * cw * split < 2LL * kNumSMs && n / (split * 2) >= kStThreads) split *= 2;
+    const int chunk = ((n + split - 1) / split + kStThreads - 1) / kStThreads * kStThreads;
+    dim3 grid(cw, (n + chunk - 1) / chunk, b);
+    if (mode == 0) {
+      if (int rc = set_smem<30>(nbr_wsum_kernel<0>, smem)) return rc;
+      nbr_wsum_kernel<0><<<grid, kStThreads, smem, s>>>(c, cw, n, k, S, chunk, y, idx, w, nullptr, out);
+    } else {
+      if (int rc = set_smem<31>(nbr_wsum_kernel<1>, smem)) return rc;
+      nbr_wsum_kernel<1><<<grid, kStThreads, smem, s>>>(c, cw, n, k, S, chunk, y, idx, w, a, out);
+    }
+  }
+  count_launch();
+  return launch_status();
+}
+
 }  // namespace mvp
 
 // gather_points over the pk neighbours of every sampled point followed by a maximum over the neighbours
@@ -539,4 +650,28 @@ MVP_API int mvp_gather_max_grad(int b, int c, int n, int npoints, const float *g
   if (b == 0 || c == 0) return MVP_OK;
   if (!grad_out || !arg || !grad_points || b > 65535 || (size_t)n * 4 > mvp::kStRowBytes) return MVP_ERR_INVALID_ARGUMENT;
   return mvp::gather_max_grad_launch(b, c, n, npoints, grad_out, arg, grad_points, (cudaStream_t)stream);
+}
+
+// out[b,ch,p] = sum_j w[b, ch mod cw, j, p] * y[b, ch, idx[b,p,j]]  (SA_module's weighted neighbour aggregation,
+// completion/models/vrcnet.py:49-52, without its (B, C, k, N) intermediates).  y (b,c,n), idx (b,n,k) int32,
+// w (b,cw,k,n), c = S * cw with S <= 8, n <= 6144.
+static bool nbr_wsum_ok(int b, int c, int cw, int n, int k) {
+  return b > 0 && b <= 65535 && c > 0 && cw > 0 && c % cw == 0 && c / cw <= mvp::kNwS && n > 0 && k > 0 &&
+         (size_t)(c / cw) * n * 4 <= 200 * 1024;
+}
+MVP_API int mvp_neighbor_weighted_sum(int b, int c, int cw, int n, int k, const float *y, const int *idx, const float *w,
+                                      float *out, mvp_stream_t stream) {
+  if (b == 0) return MVP_OK;
+  if (!nbr_wsum_ok(b, c, cw, n, k) || !y || !idx || !w || !out) return MVP_ERR_INVALID_ARGUMENT;
+  return mvp::nbr_wsum_launch(0, b, c, cw, n, k, y, idx, w, nullptr, out, (cudaStream_t)stream);
+}
+// its backward: grad_w (b,cw,k,n) and grad_y (b,c,n), both fully written, from grad_out (b,c,n)
+MVP_API int mvp_neighbor_weighted_sum_grad(int b, int c, int cw, int n, int k, const float *y, const int *idx,
+                                           const float *w, const float *grad_out, float *grad_y, float *grad_w,
+                                           mvp_stream_t stream) {
+  if (b == 0) return MVP_OK;
+  if (!nbr_wsum_ok(b, c, cw, n, k) || !y || !idx || !w || !grad_out || !grad_y || !grad_w) return MVP_ERR_INVALID_ARGUMENT;
+  int rc = mvp::nbr_wsum_launch(1, b, c, cw, n, k, y, idx, w, grad_out, grad_w, (cudaStream_t)stream);
+  if (rc) return rc;
+  return mvp::nbr_wsum_launch(2, b, c, cw, n, k, y, idx, w, grad_out, grad_y, (cudaStream_t)stream);
 }

@@ -222,3 +222,43 @@ def gather_max(features, idx):
     followed by `torch.max(..., 3)[0]` (completion/model_utils.py:97-102) as ONE launch; the gradient goes to the
     neighbour that attained each maximum (the first among equals, as torch.max routes it).  N <= 16384."""
     return _GatherMax.apply(features, idx)
+
+
+class _NeighborWeightedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, idx, w):
+        y_, i_, w_ = y.contiguous(), idx.contiguous(), w.contiguous()
+        dev = _lib.require_cuda(y_, w_, dtype=torch.float32, what="neighbor_weighted_sum")
+        if i_.dtype != torch.int32 or i_.device != y_.device:
+            raise _lib.MvpOpsError("neighbor_weighted_sum: idx must be an int32 CUDA tensor on the features' device")
+        B, C, N = y_.shape
+        Cw, K = w_.shape[1], w_.shape[2]
+        if i_.shape != (B, N, K) or w_.shape != (B, Cw, K, N) or C % Cw or C // Cw > 8:
+            raise _lib.MvpOpsError("neighbor_weighted_sum: y (B,C,N), idx (B,N,K), w (B,Cw,K,N) with C = S*Cw, S <= 8")
+        out = torch.empty(B, C, N, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.mvp_neighbor_weighted_sum(B, C, Cw, N, K, _lib.ptr(y_), _lib.ptr(i_), _lib.ptr(w_),
+                                                          _lib.ptr(out), _lib.stream_of(y_)), "mvp_neighbor_weighted_sum")
+        ctx.save_for_backward(y_, i_, w_)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y_, i_, w_ = ctx.saved_tensors
+        g = g.contiguous()
+        B, C, N = y_.shape
+        Cw, K = w_.shape[1], w_.shape[2]
+        gy, gw = torch.empty_like(y_), torch.empty_like(w_)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib.mvp_neighbor_weighted_sum_grad(B, C, Cw, N, K, _lib.ptr(y_), _lib.ptr(i_), _lib.ptr(w_),
+                                                               _lib.ptr(g), _lib.ptr(gy), _lib.ptr(gw), _lib.stream_of(g)),
+                       "mvp_neighbor_weighted_sum_grad")
+        return gy, None, gw
+
+
+def neighbor_weighted_sum(y, idx, w):
+    """out[b,c,p] = sum_j w[b, c mod Cw, j, p] * y[b, c, idx[b,p,j]] — SA_module's aggregation of the k neighbours'
+    features with attention weights shared by groups of channels (completion/models/vrcnet.py:49-52:
+    `w.repeat(1, share_planes, 1, 1) * get_edge_features(y, idx)` summed over k) as ONE launch, without the (B, C, k, N)
+    intermediates.  y (B, C, N), idx (B, N, K) int32, w (B, Cw, K, N) with C = S * Cw, S <= 8; differentiable in y and w."""
+    return _NeighborWeightedSum.apply(y, idx, w)

@@ -151,12 +151,16 @@ def sa_module_forward(self, input):
     x = self.activation_fn(x)
     x1, y2, y3 = self.conv1(x), self.conv2(x), self.conv3(x)     # all three on (B, C, 1, N)
     x2 = gef(y2, idx)                                              # B C/16 K N
-    x3 = gef(y3, idx)                                              # B C/4 K N
     x2 = x2.contiguous().view(batch_size, -1, 1, num_points)       # B kC 1 N
     w = self.conv_w(torch.cat([x1, x2], 1)).view(batch_size, -1, self.k, num_points)
-    w = w.repeat(1, self.share_planes, 1, 1)
-    out = w * x3
-    out = torch.sum(out, dim=2, keepdim=True)
+    if self.share_planes <= 8 and num_points <= 6144 and idx.dim() == 3 and idx.size(2) == self.k:
+        # sum_j w[c mod Cw, j] * y3[c, idx_j]: one launch instead of gather, repeat, multiply and sum over (B, C, K, N)
+        out = fused.neighbor_weighted_sum(y3.squeeze(2), idx.int(), w).unsqueeze(2)
+    else:
+        x3 = gef(y3, idx)                                          # B C/4 K N
+        w = w.repeat(1, self.share_planes, 1, 1)
+        out = w * x3
+        out = torch.sum(out, dim=2, keepdim=True)
     out = self.activation_fn(out)
     out = self.conv_out(out)  # B C 1 N
     out += identity

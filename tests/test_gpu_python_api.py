@@ -545,3 +545,27 @@ def test_topk_rows_vs_torch(cuda, shape, k):
     assert (i[..., 1:][same] > i[..., :-1][same]).all()      # ties in ascending index
     srt = i.sort(dim=-1)[0]
     assert (srt[..., 1:] != srt[..., :-1]).all()             # no index twice
+
+
+
+@pytest.mark.parametrize("B,C,Cw,N,K", [(3, 16, 2, 3072, 20), (2, 128, 16, 384, 10), (2, 24, 3, 777, 5), (1, 8, 8, 100, 1)])
+def test_neighbor_weighted_sum_vs_torch(ops, cuda, B, C, Cw, N, K):
+    """fused.neighbor_weighted_sum (SA_module's aggregation, vrcnet.py:49-52) against the torch sequence it replaces —
+    gather of the neighbours' features, repeat of the weights over share_planes, multiply, sum over k — forward and
+    both gradients."""
+    from mvp_benchmark_b200 import fused
+    _, mm = ops
+    g_ = torch.Generator(device=cuda).manual_seed(13)
+    y0 = torch.randn(B, C, N, device=cuda, generator=g_)
+    w0 = torch.randn(B, Cw, K, N, device=cuda, generator=g_)
+    idx = torch.randint(0, N, (B, N, K), device=cuda, generator=g_, dtype=torch.int32)
+    ya, wa = y0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    yb, wb = y0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    got = fused.neighbor_weighted_sum(ya, idx, wa)
+    x3 = mm.grouping_operation(yb, idx.transpose(1, 2).contiguous())          # (B, C, K, N), as get_edge_features
+    want = torch.sum(wb.repeat(1, C // Cw, 1, 1) * x3, dim=2)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    go = torch.randn_like(got)
+    got.backward(go), want.backward(go)
+    torch.testing.assert_close(wa.grad, wb.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ya.grad, yb.grad, rtol=1e-4, atol=1e-4)
