@@ -482,15 +482,15 @@ def run_ours(args):
                 out_host[key].copy_(t, non_blocking=True)
 
     torch.cuda.synchronize()
-    for k in range(warm):
+    for k in range(max(warm, 20)):
         e2e_pipelined(k)
     torch.cuda.synchronize()
     mdist.barrier()
-    # K steps, three times over: host->device throughput of a virtualised host varies between runs by 2x and more
+    # K steps, five times over: host->device throughput of a virtualised host varies between runs by 2x and more
     # (tools/pcie_probe.py: 11-43 GB/s for the same pinned buffer), device->host does not; the median run is reported,
-    # all three are listed.
+    # all five are listed.
     e2e_runs = []
-    for rep in range(3):
+    for rep in range(5):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(s_in)
         for k in range(steps):
@@ -499,7 +499,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         mdist.barrier()
         e2e_runs.append(mdist.max_over_ranks(p0.elapsed_time(p1), dev) / steps)
-    e2e_ms = sorted(e2e_runs)[1]
+    e2e_ms = sorted(e2e_runs)[len(e2e_runs) // 2]
     e2e_value = world * pairs / (e2e_ms * 1e-3)
 
     # The ceiling of that leg on this host: the same bytes per step (inputs in, six outputs out) as bare copies on the
