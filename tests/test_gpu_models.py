@@ -36,9 +36,11 @@ def test_first_training_step_matches_the_reference_kernels(cuda, model):
 
 
 @pytest.mark.skipif(not os.path.isfile(STAGED), reason="reference models not staged")
-def test_vrcnet_step_with_the_opt_in_knn(cuda):
-    """model_patches rebinding knn / knn_point inside the reference's modules: the step runs and the loss stays that
-    of the unpatched model up to the near-tie differences of the neighbour ranking."""
-    plain, patched = _step("vrcnet", "--ops", "ours"), _step("vrcnet", "--ops", "ours", "--patch-knn")
+@pytest.mark.parametrize("model", ["vrcnet", "ecg"])
+def test_step_with_the_opt_in_patches(cuda, model):
+    """Every opt-in patch of model_patches applied (tools/model_step.py --patch-knn): the step runs and the loss of the
+    first training step stays that of the unpatched model to 1e-3 (near-tie differences of the neighbour ranking, fp32
+    instead of TF32 in the thin convolutions)."""
+    plain, patched = _step(model, "--ops", "ours"), _step(model, "--ops", "ours", "--patch-knn")
     assert patched["patch_knn"] is True
     assert patched["loss"] == pytest.approx(plain["loss"], rel=1e-3), (patched["loss"], plain["loss"])
