@@ -574,7 +574,13 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float 
 #ifndef MVP_GRID_QMINBK
 #define MVP_GRID_QMINBK 6            // ... and for the k-nearest-neighbour lists of 12 and 16 entries (356 -> 319 us at 64 x 3072, k = 16; 8: 339)
 #endif
-template <int K, bool kRT = false>
+// kDyn (Chamfer only): the nine rows of the 3x3x3 cube are not walked in lockstep.  Unrolled, every row's set-up and
+// candidate loop is executed by the whole warp as soon as ONE lane needs the row: ncu (round 2) shows the four face
+// rows running with 7-14 of 32 lanes and the four diagonal rows with 3-6, 70 % of the kernel's instructions.  Here
+// every lane advances to ITS next row that its current bound does not prune (same fixed order, same progressive
+// pruning, hence the same candidates and results), so a warp runs for the largest NUMBER of rows a lane needs —
+// about five or six — instead of nine.
+template <int K, bool kRT = false, bool kDyn = false>
 __global__ void __launch_bounds__(kGridQThreads, (kRT ? (K == 16 || K == 12 ? MVP_GRID_QMINBK : 0) : K == 1 ? MVP_GRID_QMINB : MVP_GRID_QMINB3))  // (an explicit 1 lets ptxas take 100+ registers)
 chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
                           int *__restrict__ idx1, int *__restrict__ idx2, int kk) {
@@ -688,6 +694,48 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
         { const float g = gap(uz, cz - 1, slz); gzs[0] = cz > 0 ? g * g : inf; }
         { const float g = gap(uz, cz + 1, slz); gzs[2] = cz + 1 < gz ? g * g : inf; }
         const int xlo = cx > 0 ? cx - 1 : cx, xhi = cx + 1 < gx ? cx + 1 : cx;
+        if constexpr (kDyn) {
+          // rows in the order centre, four faces, four diagonals: offsets + 1, two bits per row
+          constexpr unsigned kOY = 1u | 0u << 2 | 2u << 4 | 1u << 6 | 1u << 8 | 0u << 10 | 2u << 12 | 0u << 14 | 2u << 16;
+          constexpr unsigned kOZ = 1u | 1u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 0u << 10 | 0u << 12 | 2u << 14 | 2u << 16;
+          auto sel3 = [](const float (&a)[3], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); };
+          // The loop is kept WARP-UNIFORM (one ballot per round): lanes that have run out of rows idle inside it, so
+          // that the warp reconverges at the top of every round — left to themselves, diverged lanes never do
+          // (measured: 15 rounds per warp and 8.7 lanes per instruction with per-lane `break`s).
+          const unsigned wmask = __activemask();
+          // centre row: every lane, in lockstep
+          {
+            const int base = (cz * gy + cy) * gx;
+            scan(__ldg(start + base + xlo), __ldg(start + base + xhi + 1));
+          }
+          // the other eight rows: those the centre row's bound leaves, as a bit mask (all lanes, no divergence) ...
+          unsigned todo = 0;
+#pragma unroll
+          for (int t = 1; t < 9; t++) {
+            constexpr int oyt[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+            constexpr int ozt[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+            const float lb = gys[oyt[t] + 1] + gzs[ozt[t] + 1];
+            if (!(lb * s2 > best) && lb < inf) todo |= 1u << t;  // (lb = inf: outside the grid)
+          }
+          if (budget < 0) todo = 0;
+          // ... then every lane takes ITS next such row per round and re-tests it against its current bound
+          while (__any_sync(wmask, todo != 0)) {
+            if (todo) {
+              const int t = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const int oy1 = (int)(kOY >> (2 * t)) & 3, oz1 = (int)(kOZ >> (2 * t)) & 3;
+              const float lbyz = sel3(gys, oy1) + sel3(gzs, oz1);
+              if (!(lbyz * s2 > best)) {
+                const int yy = cy + oy1 - 1, zz = cz + oz1 - 1;
+                const int x0 = (gxs[0] + lbyz) * s2 > best ? cx : xlo;
+                const int x1 = (gxs[2] + lbyz) * s2 > best ? cx : xhi;
+                const int base = (zz * gy + yy) * gx;
+                scan(__ldg(start + base + x0), __ldg(start + base + x1 + 1));
+                if (budget < 0) todo = 0;
+              }
+            }
+          }
+        } else
 #pragma unroll
         for (int t = 0; t < 9; t++) {
           // visiting order: centre, the four face neighbours, the four diagonal rows
@@ -793,8 +841,16 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
     if (rc) return rc;
   }
   const long long total = (long long)b * ((long long)n + m);
-  chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
-      b, n, m, W, dist1, dist2, idx1, idx2, 1);
+  static const int dyn = [] {  // measuring aid: MVP_GRID_DYNROWS=0 selects the rows-in-lockstep kernel
+    const char *e = getenv("MVP_GRID_DYNROWS");
+    return e ? atoi(e) : 1;
+  }();
+  if (dyn)
+    chamfer_grid_query_kernel<1, false, true><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+        b, n, m, W, dist1, dist2, idx1, idx2, 1);
+  else
+    chamfer_grid_query_kernel<1><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
+        b, n, m, W, dist1, dist2, idx1, idx2, 1);
   count_launch(2);
   const int rc = launch_status();
   if (rc) return rc;
