@@ -162,7 +162,10 @@ chamfer_grad_kernel(int b, int n, int m, const float *__restrict__ xyz1, const f
 // coordinates, indices and upstream gradients arrive as 128-bit loads, the own halves leave as three 128-bit
 // stores, and the scattered halves as ONE 64-bit + one 32-bit reduction per point instead of three 32-bit ones
 // (red.global.add.v2.f32 on whichever pair of the 12-byte row is 8-byte aligned).
-template <bool kScatter>
+// MODE 0: own halves, plain stores.  MODE 1: scattered halves, reductions.  MODE 2: both in ONE pass onto gradients the
+// launcher has zeroed — the own halves as coalesced 128-bit reductions — so that coordinates, indices and upstream
+// gradients are read once instead of twice.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                      const float *__restrict__ gd1, const float *__restrict__ gd2,
@@ -195,12 +198,19 @@ chamfer_grad4_kernel(int b, int n, int m, const float *__restrict__ xyz1, const 
       vy[e] = g * (ay[e] - __ldg(t + 1));
       vz[e] = g * (az[e] - __ldg(t + 2));
     }
-    if (!kScatter) {
+    if (MODE == 0) {
       float4 *o = reinterpret_cast<float4 *>(GA + p * 3);
       o[0] = make_float4(vx[0], vy[0], vz[0], vx[1]);
       o[1] = make_float4(vy[1], vz[1], vx[2], vy[2]);
       o[2] = make_float4(vz[2], vx[3], vy[3], vz[3]);
-    } else {
+    }
+    if (MODE == 2) {
+      float *o = GA + p * 3;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(vx[0]), "f"(vy[0]), "f"(vz[0]), "f"(vx[1]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(vy[1]), "f"(vz[1]), "f"(vx[2]), "f"(vy[2]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 8), "f"(vz[2]), "f"(vx[3]), "f"(vy[3]), "f"(vz[3]) : "memory");
+    }
+    if (MODE != 0) {
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         float *t = GB + (long long)jj[e] * 3;
@@ -510,10 +520,31 @@ MVP_API int mvp_chamfer_backward_algo(int algo, int b, int n, int m, const float
   if (total >= (1 << 19) && n % 4 == 0 && m % 4 == 0 && al16(xyz1) && al16(xyz2) && al16(graddist1) && al16(graddist2) && al16(idx1) &&
       al16(idx2) && al16(gradxyz1) && al16(gradxyz2)) {
     const int grid4 = (int)std::min<long long>((total / 4 + 255) / 256, (long long)kNumSMs * 16);
-    chamfer_grad4_kernel<false><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
-                                                      gradxyz2);
-    chamfer_grad4_kernel<true><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
-                                                     gradxyz2);
+    // One pass over zeroed gradients (31.7 us at the headline size) against two passes without a memset (33.8 us):
+    // the second random gather of the neighbours' coordinates costs more than the memset and the extra coalesced
+    // reductions.  MVP_CHAMFER_BWD_ONEPASS=0 selects the two-pass kernels.
+    static const int one_pass = [] {
+      const char *e = getenv("MVP_CHAMFER_BWD_ONEPASS");
+      return e ? atoi(e) : 1;
+    }();
+    if (one_pass) {
+      const size_t bytes1 = sizeof(float) * 3 * (size_t)b * n, bytes2 = sizeof(float) * 3 * (size_t)b * m;
+      cudaError_t e1, e2 = cudaSuccess;
+      if (reinterpret_cast<char *>(gradxyz1) + bytes1 == reinterpret_cast<char *>(gradxyz2)) {
+        e1 = cudaMemsetAsync(gradxyz1, 0, bytes1 + bytes2, s);  // (the Python layer allocates both in one buffer)
+      } else {
+        e1 = cudaMemsetAsync(gradxyz1, 0, bytes1, s);
+        e2 = cudaMemsetAsync(gradxyz2, 0, bytes2, s);
+      }
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
+      chamfer_grad4_kernel<2><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                    gradxyz2);
+    } else {
+      chamfer_grad4_kernel<0><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                    gradxyz2);
+      chamfer_grad4_kernel<1><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
+                                                    gradxyz2);
+    }
   } else {
     chamfer_grad_kernel<false><<<grid, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
                                                     gradxyz2);
