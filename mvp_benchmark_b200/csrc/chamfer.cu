@@ -539,6 +539,8 @@ MVP_API int mvp_chamfer_backward_algo(int algo, int b, int n, int m, const float
       if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
       chamfer_grad4_kernel<2><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
                                                     gradxyz2);
+      count_launch();
+      return launch_status();
     } else {
       chamfer_grad4_kernel<0><<<grid4, 256, 0, s>>>(b, n, m, xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1,
                                                     gradxyz2);
