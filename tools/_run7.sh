@@ -1,2 +1,3 @@
-for v in 0 1; do echo "--- ONEPASS=$v"; MVP_CHAMFER_BWD_ONEPASS=$v python tools/chamfer_step.py --steps 10 2>&1 | tail -3; done
-MVP_CHAMFER_BWD_ONEPASS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "chamfer_backward or full_size" 2>&1 | tail -2
+ncu --set full --clock-control none --import-source on -k regex:"chamfer_grid_query|chamfer_rest_kernel" -s 2 -c 2 -o gpurun_out/r2_blob_qr -f python tools/chamfer_step.py --steps 2 --no-backward --kind uniform --kind2 blob > /dev/null 2>&1
+python tools/ncu_summary.py full gpurun_out/r2_blob_qr.ncu-rep | grep -E "^### |time_duration|thread_inst|inst_executed.sum|issue_active.avg.pct_of_peak_sustained_active|long_scoreboard|lg_throttle|l1tex__throughput|lts__throughput|warps_active"
+python tools/ncu_regions.py gpurun_out/r2_blob_qr.ncu-rep | head -30
