@@ -116,6 +116,7 @@ chamfer_grid_build_kernel(int b, int n, int m, const float *__restrict__ xyz1, c
   __shared__ int s_fin[32];
   __shared__ int s_warp[32];
   __shared__ GridHdr s_hdr;
+  pdl_trigger();
   const int cloud = blockIdx.x, side = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = side ? m : n;
@@ -301,6 +302,7 @@ chamfer_grid_build2_kernel(int b, int n, int m, const float *__restrict__ xyz1, 
   __shared__ int s_warp[32];
   __shared__ float s_part[8];    // this CTA's box (lo xyz, hi xyz) and finiteness flag, read by the peer
   __shared__ GridHdr s_hdr;
+  pdl_trigger();
   const int cloud = blockIdx.x, side = blockIdx.y;
   const int rank = (int)cluster.block_rank(), peer = rank ^ 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -586,6 +588,8 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
                           int *__restrict__ idx1, int *__restrict__ idx2, int kk) {
   constexpr int kBudget = kRT ? MVP_GRID_BUDGET + 64 * K : MVP_GRID_BUDGET;
   constexpr int kMaxRing = kRT ? MVP_GRID_MAXRING + 1 : MVP_GRID_MAXRING;
+  pdl_wait();     // (the grid build's output; a no-op unless launched with launch_pdl)
+  pdl_trigger();
   const int ko = kRT ? kk : K;  // neighbours per query in the outputs
   const long long total1 = (long long)b * n, total = K == 1 ? total1 + (long long)b * m : total1;
   const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
@@ -845,7 +849,16 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
     const char *e = getenv("MVP_GRID_DYNROWS");
     return e ? atoi(e) : 1;
   }();
-  if (dyn)
+  static const int pdl = [] {  // measuring aid: MVP_PDL=0 launches the chain the ordinary way
+    const char *e = getenv("MVP_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  if (dyn && pdl) {
+    const cudaError_t e = launch_pdl(chamfer_grid_query_kernel<1, false, true>,
+                                     dim3((unsigned)((total + kGridQThreads - 1) / kGridQThreads)), dim3(kGridQThreads), 0, s, b, n,
+                                     m, W, dist1, dist2, idx1, idx2, 1);
+    if (e != cudaSuccess) return (int)e;
+  } else if (dyn)
     chamfer_grid_query_kernel<1, false, true><<<(unsigned)((total + kGridQThreads - 1) / kGridQThreads), kGridQThreads, 0, s>>>(
         b, n, m, W, dist1, dist2, idx1, idx2, 1);
   else

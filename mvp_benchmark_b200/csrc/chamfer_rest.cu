@@ -80,6 +80,8 @@ chamfer_rest_prep_kernel(int b, int n, int m, const float *__restrict__ xyz1, co
                          int plan_cap) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_base, s_warp[32];
+  pdl_wait();     // the query kernel's lists
+  pdl_trigger();
   const int cloud = blockIdx.x, ts = blockIdx.y, qs = 1 - ts;
   const int li = qs * b + cloud;
   const int cnt = W.count[li];
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(kRestThreads, 10)
 chamfer_rest_kernel(int b, int n, int m, GridWs W, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                     float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1, int *__restrict__ idx2,
                     int plan_cap) {
+  pdl_wait();     // the plan written by chamfer_rest_prep_kernel
   const int total_a = W.plan[kPlanTotal], total = total_a + W.plan[kPlanTotalB];
   if (total == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -532,8 +535,21 @@ int chamfer_rest_launch(int b, int n, int m, const GridWs &W, const float *xyz1,
   const int rc = grant_dyn_smem(chamfer_rest_prep_kernel, kPrepSmem, granted, 0);
   if (rc) return rc;
   const int plan_cap = rest_plan_cap(b, n, m);
-  chamfer_rest_prep_kernel<<<dim3(b, 2), kPrepThreads, kPrepSmem, s>>>(b, n, m, xyz1, xyz2, W, plan_cap);
-  chamfer_rest_kernel<<<kRestCtas, kRestThreads, 0, s>>>(b, n, m, W, xyz1, xyz2, dist1, dist2, idx1, idx2, plan_cap);
+  static const int pdl = [] {
+    const char *e = getenv("MVP_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  if (pdl) {
+    cudaError_t e = launch_pdl(chamfer_rest_prep_kernel, dim3(b, 2), dim3(kPrepThreads), kPrepSmem, s, b, n, m, xyz1, xyz2, W,
+                               plan_cap);
+    if (e == cudaSuccess)
+      e = launch_pdl(chamfer_rest_kernel, dim3(kRestCtas), dim3(kRestThreads), 0, s, b, n, m, W, xyz1, xyz2, dist1, dist2, idx1,
+                     idx2, plan_cap);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    chamfer_rest_prep_kernel<<<dim3(b, 2), kPrepThreads, kPrepSmem, s>>>(b, n, m, xyz1, xyz2, W, plan_cap);
+    chamfer_rest_kernel<<<kRestCtas, kRestThreads, 0, s>>>(b, n, m, W, xyz1, xyz2, dist1, dist2, idx1, idx2, plan_cap);
+  }
   count_launch(2);
   return launch_status();
 }

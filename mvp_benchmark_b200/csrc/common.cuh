@@ -78,4 +78,28 @@ constexpr int kPlanTicket = 0, kPlanNFlag = 1, kPlanNRest = 2, kPlanMap = 4;
 
 __device__ __forceinline__ float ld_nc(const float *p) { return __ldg(p); }
 
+// Programmatic dependent launch (the chain of small dependent kernels of the Chamfer forward): a kernel launched with
+// launch_pdl() may be scheduled while its predecessor in the stream is still running; it must call pdl_wait() before it
+// touches anything the predecessor wrote (returns once the predecessor's grid has completed and its writes are
+// visible).  pdl_trigger() in the predecessor says "my dependents may be scheduled from here on" — placed at the top,
+// so that the dependent's CTAs fill the slots the predecessor's last wave leaves free and its launch latency
+// disappears behind the predecessor's tail.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace mvp
