@@ -582,10 +582,20 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float 
 // every lane advances to ITS next row that its current bound does not prune (same fixed order, same progressive
 // pruning, hence the same candidates and results), so a warp runs for the largest NUMBER of rows a lane needs —
 // about five or six — instead of nine.
-template <int K, bool kRT = false, bool kDyn = false>
+// kPool (with kDyn): the (lane, row) pairs a warp has left after the centre row are POOLED and dealt out 32 at a time —
+// see the ring-1 block.
+struct QueryPool {  // per warp
+  float f[10][32];               // self x y z | gys[0] gys[2] gzs[0] gzs[2] gxs[0] gxs[2] | best after the centre row
+  int c[3][32];                  // cx cy cz
+  unsigned long long key[32];    // (bits(best) << 32) | index: the queries' running results, merged with atomicMin
+  int over[32];                  // a row of this query exceeded the candidate budget
+  unsigned char item[256];       // ((row - 1) << 5) | lane, in row-major order
+};
+template <int K, bool kRT = false, bool kDyn = false, bool kPool = false>
 __global__ void __launch_bounds__(kGridQThreads, (kRT ? (K == 16 || K == 12 ? MVP_GRID_QMINBK : 0) : K == 1 ? MVP_GRID_QMINB : MVP_GRID_QMINB3))  // (an explicit 1 lets ptxas take 100+ registers)
 chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dist1, float *__restrict__ dist2,
                           int *__restrict__ idx1, int *__restrict__ idx2, int kk) {
+  __shared__ QueryPool s_pool[kPool ? kGridQThreads / 32 : 1];
   constexpr int kBudget = kRT ? MVP_GRID_BUDGET + 64 * K : MVP_GRID_BUDGET;
   constexpr int kMaxRing = kRT ? MVP_GRID_MAXRING + 1 : MVP_GRID_MAXRING;
   pdl_wait();     // (the grid build's output; a no-op unless launched with launch_pdl)
@@ -722,6 +732,78 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
             if (!(lb * s2 > best) && lb < inf) todo |= 1u << t;  // (lb = inf: outside the grid)
           }
           if (budget < 0) todo = 0;
+          // Pooled: a round of the loop below runs with ~13 of 32 lanes (a lane needs 2.7 rows on average, the
+          // unluckiest of a warp six).  When the whole warp looks at ONE target grid, the (lane, row) pairs are
+          // instead written to a list and dealt out 32 at a time: the lane that gets a pair fetches that query's state
+          // from shared memory, clips and scans the row, and merges its result into the query's 64-bit
+          // (distance, index) key with a shared-memory atomicMin — lexicographic, hence the same winner as any order
+          // of evaluation.  Rows are tested against the centre row's bound only (no progressive tightening between
+          // the rows of a query): a few more candidates, evaluated by full warps.
+          bool pooled = false;
+          if constexpr (kPool) {
+            const int lane = threadIdx.x & 31;
+            const int cloud0 = __shfl_sync(wmask, cloud, 0), dir0 = __shfl_sync(wmask, dir, 0);
+            // one target grid for the whole warp, and a grid with rows on both sides of most cells (a planar cloud's queries
+            // have two neighbour rows, not eight: not worth the hand-over)
+            pooled = wmask == 0xffffffffu && gy >= 3 && gz >= 3 && __all_sync(wmask, cloud == cloud0 && dir == dir0);
+            if (pooled) {
+              QueryPool &P = s_pool[threadIdx.x >> 5];
+              P.f[0][lane] = self.x, P.f[1][lane] = self.y, P.f[2][lane] = self.z;
+              P.f[3][lane] = gys[0], P.f[4][lane] = gys[2], P.f[5][lane] = gzs[0], P.f[6][lane] = gzs[2];
+              P.f[7][lane] = gxs[0], P.f[8][lane] = gxs[2], P.f[9][lane] = best;
+              P.c[0][lane] = cx, P.c[1][lane] = cy, P.c[2][lane] = cz;
+              P.key[lane] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bestk;
+              P.over[lane] = 0;
+              int total_items = 0;
+#pragma unroll
+              for (int t = 1; t < 9; t++) {
+                const bool mine = (todo >> t) & 1u;
+                const unsigned mt = __ballot_sync(0xffffffffu, mine);
+                if (mine) P.item[total_items + __popc(mt & ((1u << lane) - 1u))] = (unsigned char)(((t - 1) << 5) | lane);
+                total_items += __popc(mt);
+              }
+              __syncwarp();
+              for (int k0 = 0; k0 < total_items; k0 += 32) {
+                const int k = k0 + lane;
+                if (k < total_items) {
+                  const int it = P.item[k], q = it & 31, t = (it >> 5) + 1;
+                  const int oy1 = (int)(kOY >> (2 * t)) & 3, oz1 = (int)(kOZ >> (2 * t)) & 3;
+                  const float lby = oy1 == 1 ? 0.f : (oy1 == 0 ? P.f[3][q] : P.f[4][q]);
+                  const float lbz = oz1 == 1 ? 0.f : (oz1 == 0 ? P.f[5][q] : P.f[6][q]);
+                  const float lbyz = lby + lbz, bq = P.f[9][q];
+                  const int qcx = P.c[0][q], yy = P.c[1][q] + oy1 - 1, zz = P.c[2][q] + oz1 - 1;
+                  const int qxlo = qcx > 0 ? qcx - 1 : qcx, qxhi = qcx + 1 < gx ? qcx + 1 : qcx;
+                  const int x0 = (P.f[7][q] + lbyz) * s2 > bq ? qcx : qxlo;
+                  const int x1 = (P.f[8][q] + lbyz) * s2 > bq ? qcx : qxhi;
+                  const int base = (zz * gy + yy) * gx;
+                  const int a = __ldg(start + base + x0), e = __ldg(start + base + x1 + 1);
+                  if (e - a > kBudget) {
+                    P.over[q] = 1;
+                  } else {
+                    const float sx = P.f[0][q], sy = P.f[1][q], sz = P.f[2][q];
+                    float bb = bq;
+                    int bi = 0x7fffffff;
+#pragma unroll 2
+                    for (int i = a; i < e; i++) {
+                      const float4 c4 = __ldg(T + i);
+                      const float d = sqdist(c4.x - sx, c4.y - sy, c4.z - sz);
+                      const int ci = __float_as_int(c4.w);
+                      if (d < bb || (d == bb && ci < bi)) bb = d, bi = ci;
+                    }
+                    if (bi != 0x7fffffff)
+                      atomicMin(&P.key[q], ((unsigned long long)__float_as_uint(bb) << 32) | (unsigned)bi);
+                  }
+                }
+              }
+              __syncwarp();
+              const unsigned long long kq = P.key[lane];
+              best = __uint_as_float((unsigned)(kq >> 32));
+              bestk = (int)(unsigned)kq;
+              if (P.over[lane]) budget = -1;
+              todo = 0;
+              __syncwarp();
+            }
+          }
           // ... then every lane takes ITS next such row per round and re-tests it against its current bound
           while (__any_sync(wmask, todo != 0)) {
             if (todo) {
@@ -853,7 +935,16 @@ int chamfer_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz
     const char *e = getenv("MVP_PDL");
     return e ? atoi(e) : 1;
   }();
-  if (dyn && pdl) {
+  static const int pool = [] {  // measuring aid: MVP_GRID_POOL=0 keeps every query's rows on its own lane
+    const char *e = getenv("MVP_GRID_POOL");
+    return e ? atoi(e) : 1;
+  }();
+  if (dyn && pool) {
+    const cudaError_t e = launch_pdl(chamfer_grid_query_kernel<1, false, true, true>,
+                                     dim3((unsigned)((total + kGridQThreads - 1) / kGridQThreads)), dim3(kGridQThreads), 0, s, b, n,
+                                     m, W, dist1, dist2, idx1, idx2, 1);
+    if (e != cudaSuccess) return (int)e;
+  } else if (dyn && pdl) {
     const cudaError_t e = launch_pdl(chamfer_grid_query_kernel<1, false, true>,
                                      dim3((unsigned)((total + kGridQThreads - 1) / kGridQThreads)), dim3(kGridQThreads), 0, s, b, n,
                                      m, W, dist1, dist2, idx1, idx2, 1);
