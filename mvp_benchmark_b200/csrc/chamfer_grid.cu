@@ -568,7 +568,7 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float 
   }
 }
 #ifndef MVP_GRID_QMINB
-#define MVP_GRID_QMINB 12            // resident CTAs per SM the query kernel is compiled for: 42 registers, a few spills, more warps in flight (forward 0.137 -> 0.133 ms; 10: 0.136, 16: 0.139)
+#define MVP_GRID_QMINB 8             // resident CTAs per SM the Chamfer query kernel is compiled for.  The per-lane kernels of round 1 wanted 12 (40 registers, a few spills, more warps in flight: 0.137 -> 0.133 ms); the pooled kernel keeps more state live and measures best at 8 (64 registers, no spills): forward 0.1055 -> 0.1029 ms at the headline size, 0.0416 -> 0.0385 ms at 64 x 2048 x 2048
 #endif
 #ifndef MVP_GRID_QMINB3
 #define MVP_GRID_QMINB3 12           // the same for three_nn (K = 3): 68 -> 63 us at 64 x 3072 from 1536; 0 = no occupancy target
