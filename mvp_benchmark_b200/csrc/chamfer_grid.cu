@@ -585,8 +585,10 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bk)[K], float 
 // kPool (with kDyn): the (lane, row) pairs a warp has left after the centre row are POOLED and dealt out 32 at a time —
 // see the ring-1 block.
 struct QueryPool {  // per warp
-  float f[10][32];               // self x y z | gys[0] gys[2] gzs[0] gzs[2] gxs[0] gxs[2] | best after the centre row
-  int c[3][32];                  // cx cy cz
+  float4 s0[32];                 // self x y z, best after the centre row
+  float4 s1[32];                 // gys[0] gys[2] gzs[0] gzs[2]
+  float4 s2[32];                 // gxs[0] gxs[2], cx cy (as int bits)
+  int cz[32];
   unsigned long long key[32];    // (bits(best) << 32) | index: the queries' running results, merged with atomicMin
   int over[32];                  // a row of this query exceeded the candidate budget
   unsigned char item[256];       // ((row - 1) << 5) | lane, in row-major order
@@ -601,13 +603,14 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
   pdl_wait();     // (the grid build's output; a no-op unless launched with launch_pdl)
   pdl_trigger();
   const int ko = kRT ? kk : K;  // neighbours per query in the outputs
-  const long long total1 = (long long)b * n, total = K == 1 ? total1 + (long long)b * m : total1;
-  const long long t = blockIdx.x * (long long)kGridQThreads + threadIdx.x;
+  // (b * (n + m) < 2^31 is a precondition of every grid path: 32-bit index arithmetic, one unsigned division)
+  const unsigned total1 = (unsigned)b * (unsigned)n, total = K == 1 ? total1 + (unsigned)b * (unsigned)m : total1;
+  const unsigned t = blockIdx.x * (unsigned)kGridQThreads + threadIdx.x;
   if (t < total) {
   const int dir = t >= total1 ? 1 : 0;       // 0: points of xyz1 against xyz2's grid; 1: the other way round
-  const long long pi = dir ? t - total1 : t;
+  const unsigned pi = dir ? t - total1 : t;
   const int nq = dir ? m : n, nt = dir ? n : m;
-  const int cloud = (int)(pi / nq);
+  const int cloud = (int)(pi / (unsigned)nq);
   const float4 self = __ldg((dir ? W.sorted[1] : W.sorted[0]) + pi);
   const int orig = __float_as_int(self.w);
   const int ts = 1 - dir;  // target side
@@ -667,7 +670,7 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
       }
       budget -= e - a;
 #pragma unroll(K == 1 ? kScanUnroll : 1)  // longer ordered lists: the duplicated insertion code costs more than it saves
-      for (int i = a; i < e; i++) {
+      for (unsigned i = (unsigned)a; i < (unsigned)e; i++) {  // (unsigned: the address is one IMAD.WIDE.U32)
         const float4 q = __ldg(T + i);
         const float d = sqdist(q.x - self.x, q.y - self.y, q.z - self.z);
         if (d <= best) {  // rare after the first few candidates
@@ -748,10 +751,10 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
             pooled = wmask == 0xffffffffu && gy >= 3 && gz >= 3 && __all_sync(wmask, cloud == cloud0 && dir == dir0);
             if (pooled) {
               QueryPool &P = s_pool[threadIdx.x >> 5];
-              P.f[0][lane] = self.x, P.f[1][lane] = self.y, P.f[2][lane] = self.z;
-              P.f[3][lane] = gys[0], P.f[4][lane] = gys[2], P.f[5][lane] = gzs[0], P.f[6][lane] = gzs[2];
-              P.f[7][lane] = gxs[0], P.f[8][lane] = gxs[2], P.f[9][lane] = best;
-              P.c[0][lane] = cx, P.c[1][lane] = cy, P.c[2][lane] = cz;
+              P.s0[lane] = make_float4(self.x, self.y, self.z, best);
+              P.s1[lane] = make_float4(gys[0], gys[2], gzs[0], gzs[2]);
+              P.s2[lane] = make_float4(gxs[0], gxs[2], __int_as_float(cx), __int_as_float(cy));
+              P.cz[lane] = cz;
               P.key[lane] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bestk;
               P.over[lane] = 0;
               int total_items = 0;
@@ -768,23 +771,24 @@ chamfer_grid_query_kernel(int b, int n, int m, GridWs W, float *__restrict__ dis
                 if (k < total_items) {
                   const int it = P.item[k], q = it & 31, t = (it >> 5) + 1;
                   const int oy1 = (int)(kOY >> (2 * t)) & 3, oz1 = (int)(kOZ >> (2 * t)) & 3;
-                  const float lby = oy1 == 1 ? 0.f : (oy1 == 0 ? P.f[3][q] : P.f[4][q]);
-                  const float lbz = oz1 == 1 ? 0.f : (oz1 == 0 ? P.f[5][q] : P.f[6][q]);
-                  const float lbyz = lby + lbz, bq = P.f[9][q];
-                  const int qcx = P.c[0][q], yy = P.c[1][q] + oy1 - 1, zz = P.c[2][q] + oz1 - 1;
+                  const float4 q0 = P.s0[q], q1 = P.s1[q], q2 = P.s2[q];
+                  const float lby = oy1 == 1 ? 0.f : (oy1 == 0 ? q1.x : q1.y);
+                  const float lbz = oz1 == 1 ? 0.f : (oz1 == 0 ? q1.z : q1.w);
+                  const float lbyz = lby + lbz, bq = q0.w;
+                  const int qcx = __float_as_int(q2.z), yy = __float_as_int(q2.w) + oy1 - 1, zz = P.cz[q] + oz1 - 1;
                   const int qxlo = qcx > 0 ? qcx - 1 : qcx, qxhi = qcx + 1 < gx ? qcx + 1 : qcx;
-                  const int x0 = (P.f[7][q] + lbyz) * s2 > bq ? qcx : qxlo;
-                  const int x1 = (P.f[8][q] + lbyz) * s2 > bq ? qcx : qxhi;
+                  const int x0 = (q2.x + lbyz) * s2 > bq ? qcx : qxlo;
+                  const int x1 = (q2.y + lbyz) * s2 > bq ? qcx : qxhi;
                   const int base = (zz * gy + yy) * gx;
                   const int a = __ldg(start + base + x0), e = __ldg(start + base + x1 + 1);
                   if (e - a > kBudget) {
                     P.over[q] = 1;
                   } else {
-                    const float sx = P.f[0][q], sy = P.f[1][q], sz = P.f[2][q];
+                    const float sx = q0.x, sy = q0.y, sz = q0.z;
                     float bb = bq;
                     int bi = 0x7fffffff;
 #pragma unroll 2
-                    for (int i = a; i < e; i++) {
+                    for (unsigned i = (unsigned)a; i < (unsigned)e; i++) {
                       const float4 c4 = __ldg(T + i);
                       const float d = sqdist(c4.x - sx, c4.y - sy, c4.z - sz);
                       const int ci = __float_as_int(c4.w);
