@@ -94,5 +94,10 @@ mm.knn(100, R(1, 1500, 3), R(1, 77, 3))
 mm.knn(9, R(2, 5, 3), R(2, 7, 3))
 fused.topk_rows(torch.randn(3, 700, 700, device=dev, generator=g), 16)
 fused.topk_rows(torch.randn(5, 33, device=dev, generator=g), 32)
+ff = torch.randn(2, 19, 1536, device=dev, generator=g).requires_grad_(True)
+fused.gather_max(ff, torch.randint(0, 1536, (2, 700, 10), device=dev, generator=g, dtype=torch.int32)).sum().backward()
+yy = torch.randn(2, 16, 768, device=dev, generator=g).requires_grad_(True)
+ww = torch.randn(2, 2, 10, 768, device=dev, generator=g).requires_grad_(True)
+fused.neighbor_weighted_sum(yy, torch.randint(0, 768, (2, 768, 10), device=dev, generator=g, dtype=torch.int32), ww).sum().backward()
 torch.cuda.synchronize()
 print("sanitize_ops: all entry points ran,", _lib.launch_count(), "kernels launched")
