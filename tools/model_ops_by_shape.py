@@ -1,15 +1,16 @@
-"""Diagnostic: one patched VRCNet training step under torch.profiler with record_shapes — device time per aten op and input
+"""Diagnostic: one patched training step (python tools/model_ops_by_shape.py [vrcnet|ecg|pcn]) under torch.profiler with record_shapes — device time per aten op and input
 shape (how the thin 1x1 convolutions whose weight gradient cuDNN runs through wgrad2d_grouped_direct_kernel were found).
 Run under gpurun: python tools/model_ops_by_shape.py"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.argv = ["model_step.py", "--model", "vrcnet", "--ops", "ours", "--patch-knn"]
+MODEL = sys.argv[1] if len(sys.argv) > 1 else "vrcnet"
+sys.argv = ["model_step.py", "--model", MODEL, "--ops", "ours", "--patch-knn"]
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
 import model_step as ms
-module, args = ms.load_model("vrcnet", "ours")
+module, args = ms.load_model(MODEL, "ours")
 import mvp_benchmark_b200.model_patches as mp
-mp.apply(sys.modules["model_utils"], sys.modules["models.vrcnet"])
+mp.apply(sys.modules["model_utils"], sys.modules["models." + MODEL])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = module.Model(args).to(dev).train()
@@ -19,11 +20,11 @@ for mod in net.modules():
         mod.inplace = False
 x, gt = torch.rand(32, 3, 2048, device=dev), torch.rand(32, 2048, 3, device=dev)
 for _ in range(2):
-    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].backward()
+    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].mean().backward()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
-    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].backward(); torch.cuda.synchronize()
+    net.zero_grad(); out = net(x, gt, alpha=0.01); out[2].mean().backward(); torch.cuda.synchronize()
 rows = []
 for e in prof.key_averages(group_by_input_shape=True):
     if e.device_time_total > 150 and e.key.startswith("aten::") and not e.key.startswith("aten::_") :
