@@ -474,17 +474,20 @@ nbr_wsum_kernel(int c, int cw, int n, int k, int S, int chunk, const float *__re
   }
 }
 
-// grad_y: grid (Cw, 1, b): a CTA produces the S complete gradient rows of its channels
+// grad_y: grid (Cw, channel sub-groups, b): a CTA produces the complete gradient rows of `per` of the S channels that
+// share weight row w0 (all S when there are enough CTAs without splitting)
 __global__ void __launch_bounds__(kStThreads)
-nbr_wsum_grad_y_kernel(int c, int cw, int n, int k, int S, const int *__restrict__ idx, const float *__restrict__ w,
-                       const float *__restrict__ g, float *__restrict__ grad_y) {
+nbr_wsum_grad_y_kernel(int c, int cw, int n, int k, int S_all, int per, const int *__restrict__ idx,
+                       const float *__restrict__ w, const float *__restrict__ g, float *__restrict__ grad_y) {
   extern __shared__ __align__(128) float rows[];
-  const int b = blockIdx.z, w0 = blockIdx.x;
+  const int b = blockIdx.z, s_lo = blockIdx.y * per, S = min(per, S_all - s_lo);
+  const int w0 = blockIdx.x + s_lo * cw;  // first channel of this CTA; the others follow at a stride of cw
+  if (S <= 0) return;
   for (int i = threadIdx.x; i < S * n; i += kStThreads) rows[i] = 0.f;
   __syncthreads();
   for (int p = threadIdx.x; p < n; p += kStThreads) {
     const int *id = idx + ((size_t)b * n + p) * k;
-    const float *wp = w + ((size_t)b * cw + w0) * k * n + p;
+    const float *wp = w + ((size_t)b * cw + blockIdx.x) * k * n + p;
     float gv[kNwS];
 #pragma unroll
     for (int s_ = 0; s_ < kNwS; s_++) gv[s_] = s_ < S ? __ldg(g + ((size_t)b * c + w0 + (size_t)s_ * cw) * n + p) : 0.f;
@@ -611,8 +614,11 @@ int nbr_wsum_launch(int mode, int b, int c, int cw, int n, int k, const float *y
   const int S = c / cw;
   const size_t smem = (size_t)S * n * 4;
   if (mode == 2) {
+    int per = S;  // channels per CTA: halved until the grid fills the machine about twice
+    while (per > 1 && (long long)b * cw * ((S + per - 1) / per) < 2LL * kNumSMs) per = (per + 1) / 2;
     if (int rc = set_smem<32>(nbr_wsum_grad_y_kernel, smem)) return rc;
-    nbr_wsum_grad_y_kernel<<<dim3(cw, 1, b), kStThreads, smem, s>>>(c, cw, n, k, S, idx, w, a, out);
+    nbr_wsum_grad_y_kernel<<<dim3(cw, (S + per - 1) / per, b), kStThreads, (size_t)per * n * 4, s>>>(c, cw, n, k, S, per, idx, w,
+                                                                                                a, out);
   } else {
     int split = 1;
     while ((long long)b * cw * split < 2LL * kNumSMs && n / (split * 2) >= kStThreads) split *= 2;

@@ -2,7 +2,7 @@
 """One call of every operator family at the sizes the completion models use — the subject of the per-kernel ncu
 captures summarised under profiles/ (run it under `ncu --set full -k regex:mvp`; keep it short: ncu replays every
 kernel ~40 times).   python tools/profile_ops.py [family ...]   families: fps gather group interp three_nn knn_points
-ball_query knn chamfer_brute chamfer_bwd emd"""
+ball_query knn fused chamfer_brute chamfer_bwd emd"""
 import os
 import sys
 
@@ -51,6 +51,14 @@ if on("ball_query"):
 if on("knn"):
     mm.knn(16, R(64, 2048, 3), R(64, 512, 3), False)
     mm.knn(64, R(16, 8192, 3), R(16, 2048, 3), False)
+if on("fused"):
+    f = N(64, 64, 3072).requires_grad_(True)
+    i = torch.randint(0, 3072, (64, 1536, 10), device=dev, generator=g, dtype=torch.int32)
+    fused.gather_max(f, i).sum().backward()
+    y = N(64, 16, 3072).requires_grad_(True)
+    w = N(64, 2, 20, 3072).requires_grad_(True)
+    fused.neighbor_weighted_sum(y, torch.randint(0, 3072, (64, 3072, 20), device=dev, generator=g, dtype=torch.int32), w).sum().backward()
+    fused.topk_rows(N(32, 2048, 2048), 16)
 if on("chamfer_brute"):
     b, n = 32, 16384
     a, c = R(b, n, 3), R(b, n, 3)
