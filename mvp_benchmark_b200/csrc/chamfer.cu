@@ -18,19 +18,15 @@ namespace mvp {
 constexpr int kChThreads = 256;
 constexpr int kChTile = 1024;  // targets per shared-memory tile (AoS, 12 KB)
 
-// kRest: the queries are the `count[b]` entries of `list + b*n` (the grid path's left-over points, chamfer_grid.cu)
-// instead of all n points of the cloud; CTAs beyond the list length exit at once.
-template <int R, bool kRest>
+template <int R>
 __device__ __forceinline__ void chamfer_dir_body(int chunk, int b, int n, int m, const float *__restrict__ xyz,
                                                  const float *__restrict__ xyz2, float *__restrict__ dist,
-                                                 int *__restrict__ idx, const int *__restrict__ list,
-                                                 const int *__restrict__ count) {
+                                                 int *__restrict__ idx) {
   __shared__ __align__(16) float tile[kChTile * 3];
   const int tid = threadIdx.x;
   const int qbase = chunk * (kChThreads * R);
-  const int nq = kRest ? __ldg(count + b) : n;
+  const int nq = n;
   if (qbase >= nq) return;
-  if (kRest) list += (size_t)b * n;
   const float *q = xyz + (size_t)b * n * 3;
   const float *t = xyz2 + (size_t)b * m * 3;
 
@@ -39,8 +35,7 @@ __device__ __forceinline__ void chamfer_dir_body(int chunk, int b, int n, int m,
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int j = qbase + r * kChThreads + tid;
-    int jj = j < nq ? j : nq - 1;
-    if (kRest) jj = __ldg(list + jj);
+    const int jj = j < nq ? j : nq - 1;
     qi[r] = jj;
     qx[r] = __ldg(q + jj * 3 + 0);
     qy[r] = __ldg(q + jj * 3 + 1);
@@ -90,7 +85,7 @@ template <int R>
 __global__ void __launch_bounds__(kChThreads)
 chamfer_dir_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ xyz2,
                    float *__restrict__ dist, int *__restrict__ idx) {
-  chamfer_dir_body<R, false>(blockIdx.x, blockIdx.y, n, m, xyz, xyz2, dist, idx, nullptr, nullptr);
+  chamfer_dir_body<R>(blockIdx.x, blockIdx.y, n, m, xyz, xyz2, dist, idx);
 }
 
 int chamfer_dir_launch(int b, int n, int m, const float *xyz, const float *xyz2, float *dist, int *idx,

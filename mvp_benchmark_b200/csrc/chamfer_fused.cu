@@ -68,33 +68,19 @@ struct PairSmem {
   uint64_t bar[2];
 };
 
-// A work item is (row tile, column split, cloud): WARPS warps, TM = kBlk * WARPS rows per tile.
-//   plan == nullptr: grid (row tiles, column splits, b), one item per CTA.
-//   plan != nullptr: the fall-back of the grid path (chamfer_grid.cu).  plan[kPlanNFlag] clouds, listed in
-//     plan + kPlanMap, were handed over to brute force; a 1-D grid of resident CTAs strides over their items and
-//     leaves at once when there are none (the normal case).
-template <int WARPS, bool kPlan>
+// A CTA's work item is (row tile, column split, cloud) = blockIdx: WARPS warps, TM = kBlk * WARPS rows per tile.
+template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4))
 chamfer_pair_kernel(int n, int m, int tiles_x, int split, int tiles_per_cta, int use_tma,
                     const float *__restrict__ xyz1, const float *__restrict__ xyz2, u64 *__restrict__ rowkey,
-                    u64 *__restrict__ colkey, const int *__restrict__ plan) {
+                    u64 *__restrict__ colkey) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PairSmem<WARPS> &S = *reinterpret_cast<PairSmem<WARPS> *>(smem_raw);
   constexpr int T = WARPS * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float inf = __int_as_float(0x7f800000);
   const int per_cloud = tiles_x * split;
-  long long nwork, work, stride;
-  if (kPlan) {
-    nwork = (long long)__ldg(plan + kPlanNFlag) * per_cloud;
-    work = blockIdx.x;
-    stride = gridDim.x;
-    if (work >= nwork) return;
-  } else {
-    work = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    nwork = work + 1;
-    stride = 1;
-  }
+  const long long work = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (use_tma && tid == 0) {
     mbar_init(&S.bar[0], 1);
     mbar_init(&S.bar[1], 1);
@@ -103,9 +89,9 @@ chamfer_pair_kernel(int n, int m, int tiles_x, int split, int tiles_per_cta, int
   __syncthreads();
   uint32_t tt = 0;  // tiles fetched by TMA so far in this CTA: buffer = tt & 1, mbarrier parity = (tt >> 1) & 1
 
-  for (; work < nwork; work += stride) {
+  {
   const int slot = (int)(work / per_cloud), rem = (int)(work % per_cloud);
-  const int b = kPlan ? __ldg(plan + kPlanMap + slot) : slot;
+  const int b = slot;
   const int bx = rem % tiles_x, by = rem / tiles_x;
   const float *A = xyz1 + (size_t)b * n * 3;
   const float *Bc = xyz2 + (size_t)b * m * 3;
@@ -248,8 +234,7 @@ chamfer_pair_kernel(int n, int m, int tiles_x, int split, int tiles_per_cta, int
     if (i < n && ntiles > 0)
       atomicMin(rowkey + (size_t)b * n + i, ((u64)__float_as_uint(best[r]) << 32) | (unsigned)bchunk[r]);
   }
-  if (kPlan) __syncthreads();  // the next work item re-stages S.x/y/z and rewrites S.wmin
-  }  // work items
+  }
 }
 
 // One warp per point p (both directions in one launch: the b*n points of xyz1 against xyz2, then the b*m points of
@@ -257,17 +242,15 @@ chamfer_pair_kernel(int n, int m, int tiles_x, int split, int tiles_per_cta, int
 // re-evaluated, kBlk/32 consecutive candidates per lane (128-bit loads when the block is whole and 16-byte
 // aligned), and the first one whose distance to p has exactly those bits is the answer.
 //   grid: x strides over the n + m points of a cloud pair (8 per CTA), y over the clouds.
-//   plan == nullptr: all b clouds.   plan != nullptr: only the clouds listed in the plan (see chamfer_pair_kernel).
 __global__ void __launch_bounds__(256)
 chamfer_resolve_kernel(int b, int n, int m, int vec1, int vec2, const float *__restrict__ xyz1,
                        const float *__restrict__ xyz2, const u64 *__restrict__ rowkey, const u64 *__restrict__ colkey,
                        float *__restrict__ dist1, float *__restrict__ dist2, int *__restrict__ idx1,
-                       int *__restrict__ idx2, const int *__restrict__ plan) {
+                       int *__restrict__ idx2) {
   constexpr int PER = kBlk / 32;  // candidates per lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int clouds = plan ? __ldg(plan + kPlanNFlag) : b;
-  for (int slot = blockIdx.y; slot < clouds; slot += gridDim.y) {
-  const long long cloud = plan ? __ldg(plan + kPlanMap + slot) : slot;
+  for (int slot = blockIdx.y; slot < b; slot += gridDim.y) {
+  const long long cloud = slot;
   for (int i = blockIdx.x * 8 + warp; i < n + m; i += gridDim.x * 8) {
     const bool first_dir = i < n;
     const int np = first_dir ? n : m, nq = first_dir ? m : n;
@@ -345,35 +328,25 @@ static PairShape pair_shape(int b, int n, int m) {
 
 template <int WARPS>
 static int pair_launch(int b, int n, int m, const PairShape &sh, int use_tma, const float *xyz1, const float *xyz2,
-                       u64 *rowkey, u64 *colkey, const int *plan, cudaStream_t s) {
+                       u64 *rowkey, u64 *colkey, cudaStream_t s) {
   const size_t smem = sizeof(PairSmem<WARPS>);
   {
-    static size_t granted[2][kMaxDevices];
-    int rc0 = grant_dyn_smem(chamfer_pair_kernel<WARPS, false>, smem, granted[0], 0);
-    if (!rc0) rc0 = grant_dyn_smem(chamfer_pair_kernel<WARPS, true>, smem, granted[1], 0);
+    static size_t granted[kMaxDevices];
+    const int rc0 = grant_dyn_smem(chamfer_pair_kernel<WARPS>, smem, granted, 0);
     if (rc0) return rc0;
   }
-  // plan-driven: one wave of resident CTAs striding over the handed-over clouds' tiles
-  const int resident = kNumSMs * (WARPS >= 8 ? MVP_PAIR_MINB : (WARPS == 4 ? 2 * MVP_PAIR_MINB : 4));
-  const long long items = (long long)b * sh.tiles_x * sh.split;
-  if (plan)
-    chamfer_pair_kernel<WARPS, true><<<(unsigned)std::min<long long>(items, resident), WARPS * 32, smem, s>>>(
-        n, m, sh.tiles_x, sh.split, sh.tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, plan);
-  else
-    chamfer_pair_kernel<WARPS, false><<<dim3(sh.tiles_x, sh.split, b), WARPS * 32, smem, s>>>(
-        n, m, sh.tiles_x, sh.split, sh.tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey, plan);
+  chamfer_pair_kernel<WARPS><<<dim3(sh.tiles_x, sh.split, b), WARPS * 32, smem, s>>>(
+      n, m, sh.tiles_x, sh.split, sh.tiles_per_cta, use_tma, xyz1, xyz2, rowkey, colkey);
   count_launch();
   return launch_status();
 }
 
-// plan == nullptr: every cloud.  plan != nullptr (device memory, written by chamfer_grid_query_kernel's last CTA):
-// only the clouds it lists; every kernel leaves at once when it lists none.
-int chamfer_fused_launch_plan(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                              int *idx1, int *idx2, void *ws, size_t ws_bytes, const int *plan, cudaStream_t s) {
+int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                         int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < chamfer_fused_workspace_bytes(b, n, m)) return MVP_ERR_WORKSPACE;
   u64 *rowkey = reinterpret_cast<u64 *>(ws);
   u64 *colkey = rowkey + (size_t)b * n;
-  if (!plan) {  // (plan-driven: chamfer_grid_build_kernel has set the keys)
+  {
     cudaError_t e = cudaMemsetAsync(ws, 0xff, chamfer_fused_workspace_bytes(b, n, m), s);
     if (e != cudaSuccess) return (int)e;
   }
@@ -382,28 +355,18 @@ int chamfer_fused_launch_plan(int b, int n, int m, const float *xyz1, const floa
   // multiples of m*12 bytes
   const int use_tma = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
   int rc;
-  if (sh.warps == 8) rc = pair_launch<8>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
-  else if (sh.warps == 4) rc = pair_launch<4>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
-  else rc = pair_launch<2>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, plan, s);
+  if (sh.warps == 8) rc = pair_launch<8>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, s);
+  else if (sh.warps == 4) rc = pair_launch<4>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, s);
+  else rc = pair_launch<2>(b, n, m, sh, use_tma, xyz1, xyz2, rowkey, colkey, s);
   if (rc) return rc;
 
   const int vec2 = ((reinterpret_cast<uintptr_t>(xyz2) & 15) == 0 && (m % 4) == 0) ? 1 : 0;
   const int vec1 = ((reinterpret_cast<uintptr_t>(xyz1) & 15) == 0 && (n % 4) == 0) ? 1 : 0;
   const long long chunks = ((long long)n + m + 7) / 8;
   dim3 rgrid((unsigned)std::min<long long>(chunks, 1 << 20), b);
-  if (plan) {  // about one wave of CTAs, leaving at once when nothing was handed over
-    const int gy = std::min(b, 16);
-    rgrid = dim3((unsigned)std::min<long long>(chunks, (kNumSMs * 8 + gy - 1) / gy), gy);
-  }
-  chamfer_resolve_kernel<<<rgrid, 256, 0, s>>>(b, n, m, vec1, vec2, xyz1, xyz2, rowkey, colkey, dist1, dist2, idx1, idx2,
-                                               plan);
+  chamfer_resolve_kernel<<<rgrid, 256, 0, s>>>(b, n, m, vec1, vec2, xyz1, xyz2, rowkey, colkey, dist1, dist2, idx1, idx2);
   count_launch();
   return launch_status();
-}
-
-int chamfer_fused_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                         int *idx1, int *idx2, void *ws, size_t ws_bytes, cudaStream_t s) {
-  return chamfer_fused_launch_plan(b, n, m, xyz1, xyz2, dist1, dist2, idx1, idx2, ws, ws_bytes, nullptr, s);
 }
 
 }  // namespace mvp

@@ -71,11 +71,6 @@ __device__ __forceinline__ uint32_t redux_max_u32(uint32_t v) {
   return r;
 }
 
-// Hand-over plan of the grid-pruned Chamfer path (chamfer_grid.cu), int words in the workspace:
-//   [kPlanTicket] (unused)                                        [kPlanNFlag] clouds handed to the fused brute force
-//   [kPlanNRest]  (direction, cloud) lists for the left-over pass [kPlanMap ...] b cloud ids, then 2b list ids
-constexpr int kPlanTicket = 0, kPlanNFlag = 1, kPlanNRest = 2, kPlanMap = 4;
-
 __device__ __forceinline__ float ld_nc(const float *p) { return __ldg(p); }
 
 // Programmatic dependent launch (the chain of small dependent kernels of the Chamfer forward): a kernel launched with
