@@ -367,6 +367,30 @@ def run(dev, hbm_gbs=None):
         e["ours_per_s"] = 64.0 * n_ * m_ / (e["ours_ms"] * 1e-3)
         e["speedup_vs_torch_formula"] = e["torch_matmul_topk_ms"] / e["ours_ms"]
         out["knn_points_" + tag] = e
+    # ---- the fused caller-side operators of round 2 against the torch / operator sequences they replace
+    def fused_entry(name, ours_fn, torch_fn, note):
+        out[name] = {"ours_ms": _time(ours_fn, 5, 2), "torch_sequence_ms": _time(torch_fn, 3, 1), "replaces": note}
+        out[name]["speedup"] = out[name]["torch_sequence_ms"] / out[name]["ours_ms"]
+
+    ff = torch.randn(64, 64, 3072, device=dev, generator=g)
+    fi = torch.randint(0, 3072, (64, 1536, 10), device=dev, generator=g, dtype=torch.int32)
+    fused_entry("gather_max_64x64x3072_to_1536x10", lambda: fused.gather_max(ff, fi),
+                lambda: torch.max(mm.gather_points(ff, fi.view(64, -1)).view(64, 64, 1536, 10), 3),
+                "gather_points + view + torch.max (model_utils.py:97-102)")
+    yy = torch.randn(64, 16, 3072, device=dev, generator=g)
+    ww = torch.randn(64, 2, 20, 3072, device=dev, generator=g)
+    wi = torch.randint(0, 3072, (64, 3072, 20), device=dev, generator=g, dtype=torch.int32)
+    wit = wi.transpose(1, 2).contiguous()
+    fused_entry("neighbor_weighted_sum_64x16x3072_k20", lambda: fused.neighbor_weighted_sum(yy, wi, ww),
+                lambda: torch.sum(ww.repeat(1, 8, 1, 1) * mm.grouping_operation(yy, wit), dim=2),
+                "grouping_operation + repeat + mul + sum (vrcnet.py:49-52)")
+    sc = torch.randn(32, 2048, 2048, device=dev, generator=g)
+    fused_entry("topk_rows_32x2048x2048_k16", lambda: fused.topk_rows(sc, 16), lambda: sc.topk(16, dim=-1),
+                "torch.topk on the feature-space score matrix (model_utils.py:246)")
+    fp = R(64, 3072, 3)
+    fused_entry("fps_gather_64x3072_to_1536", lambda: fused.fps_gather(fp, 1536),
+                lambda: mm.gather_points(fp.transpose(1, 2).contiguous(), mm.furthest_point_sample(fp, 1536)).transpose(1, 2).contiguous(),
+                "furthest_point_sample + transpose + gather_points + transpose (model_utils.py:91-93)")
     out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
     steps = model_steps()
     if steps is not None:

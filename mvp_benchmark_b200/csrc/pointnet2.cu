@@ -254,28 +254,35 @@ topk_rows_kernel(long long rows, int cols, int k, const float *__restrict__ scor
   const float ninf = __int_as_float(0xff800000);
   float lv = ninf, thr_v = ninf;  // this lane's entry; the k-th entry
   int li = 0x7fffffff, thr_i = 0x7fffffff;
-  for (int t0 = 0; t0 < cols; t0 += 32) {
-    const int j = t0 + lane;
-    float v = ninf;
-    bool pass = false;
-    if (j < cols) {
-      v = __ldg(r + j);
-      pass = v > thr_v || (v == thr_v && j < thr_i);
+  // four steps of 32 scores in flight together (the row streams from HBM: a dependent 4-byte load per step would leave
+  // the memory system idle); each step's 32 scores are then filtered and inserted in column order
+  for (int t0 = 0; t0 < cols; t0 += 128) {
+    float v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = t0 + 32 * u + lane;
+      v4[u] = j < cols ? __ldg(r + j) : ninf;
     }
-    unsigned mask = __ballot_sync(full, pass);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float cv = __shfl_sync(full, v, src);
-      const int cj = t0 + src;
-      if (!(cv > thr_v || (cv == thr_v && cj < thr_i))) continue;  // the k-th entry has moved since the filter
-      const int pos = __popc(__ballot_sync(full, lv > cv || (lv == cv && li < cj)));
-      const float uv = __shfl_up_sync(full, lv, 1);
-      const int ui = __shfl_up_sync(full, li, 1);
-      if (lane > pos) lv = uv, li = ui;
-      else if (lane == pos) lv = cv, li = cj;
-      thr_v = __shfl_sync(full, lv, k - 1);
-      thr_i = __shfl_sync(full, li, k - 1);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = t0 + 32 * u + lane;
+      const float v = v4[u];
+      const bool pass = j < cols && (v > thr_v || (v == thr_v && j < thr_i));
+      unsigned mask = __ballot_sync(full, pass);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cv = __shfl_sync(full, v, src);
+        const int cj = t0 + 32 * u + src;
+        if (!(cv > thr_v || (cv == thr_v && cj < thr_i))) continue;  // the k-th entry has moved since the filter
+        const int pos = __popc(__ballot_sync(full, lv > cv || (lv == cv && li < cj)));
+        const float uv = __shfl_up_sync(full, lv, 1);
+        const int ui = __shfl_up_sync(full, li, 1);
+        if (lane > pos) lv = uv, li = ui;
+        else if (lane == pos) lv = cv, li = cj;
+        thr_v = __shfl_sync(full, lv, k - 1);
+        thr_i = __shfl_sync(full, li, k - 1);
+      }
     }
   }
   if (lane < k) {
