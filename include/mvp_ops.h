@@ -225,6 +225,27 @@ int mvp_neighbor_weighted_sum(int b, int c, int cw, int n, int k, const float *y
 int mvp_neighbor_weighted_sum_grad(int b, int c, int cw, int n, int k, const float *y, const int *idx, const float *w,
                                    const float *grad_out, float *grad_y, float *grad_w, mvp_stream_t stream);
 
+/* A shared 1x1 convolution over a cloud's feature map on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate in
+ * tensor memory): y[b,co,p] = sum_ci w[co,ci] * x[b,ci,p] (+ bias[co]) (then max(., 0) if relu != 0) — what the
+ * nn.Conv1d / nn.Conv2d(kernel_size=1) layers of completion/models/{pcn,ecg,vrcnet}.py and of
+ * completion/model_utils.py compute (cuDNN runs them in TF32 too: torch.backends.cudnn.allow_tf32 defaults to True).
+ * x (b,cin,n), w (cout,cin), bias (cout) or NULL, y (b,cout,n), all fp32; operands are rounded to TF32 (round to
+ * nearest) as they are staged.  b <= 65535.
+ * mvp_pointwise_conv_masked: the same contraction of x * (mask > 0), mask (b,cin,n), no bias — the input gradient of a
+ * layer followed by ReLU: x = the gradient of the ReLU's output, mask = that output, w = the layer's weight transposed. */
+int mvp_pointwise_conv(int b, int cin, int cout, int n, const float *x, const float *w, const float *bias, int relu,
+                       float *y, mvp_stream_t stream);
+int mvp_pointwise_conv_masked(int b, int cin, int cout, int n, const float *x, const float *mask, const float *w, float *y,
+                              mvp_stream_t stream);
+
+/* The bias of a wide 1x1 layer that stays on a library GEMM: y[b,c,:] += bias[c] in place (then max(., 0) if relu),
+ * y (b,c,n); and its gradient: out[c] = sum over clouds and points of g[b,c,p], g (b,c,n), in a fixed order
+ * (deterministic).  workspace: mvp_channel_sum_workspace_bytes(b, c) bytes of device memory. */
+int mvp_bias_add(int b, int c, int n, float *y, const float *bias, int relu, mvp_stream_t stream);
+size_t mvp_channel_sum_workspace_bytes(int b, int c);
+int mvp_channel_sum(int b, int c, int n, const float *g, float *out, void *workspace, size_t workspace_bytes,
+                    mvp_stream_t stream);
+
 /* The k <= 32 largest entries of every row of a (rows, cols) fp32 score matrix, descending, equal scores in ascending
  * column order — what completion/model_utils.py:242-247 asks torch.topk for on its (B, N, N) matrix of negative
  * feature-space distances.  Any of values (rows,k) / idx64 (rows,k) int64 / idx32 (rows,k) int32 may be NULL. */

@@ -64,6 +64,11 @@ def _load():
         "mvp_gather_max_grad": (_c_int, [_c_int] * 4 + [_p] * 3 + [_p]),
         "mvp_neighbor_weighted_sum": (_c_int, [_c_int] * 5 + [_p] * 4 + [_p]),
         "mvp_neighbor_weighted_sum_grad": (_c_int, [_c_int] * 5 + [_p] * 6 + [_p]),
+        "mvp_pointwise_conv": (_c_int, [_c_int] * 4 + [_p] * 3 + [_c_int, _p] + [_p]),
+        "mvp_pointwise_conv_masked": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
+        "mvp_bias_add": (_c_int, [_c_int] * 3 + [_p] * 2 + [_c_int, _p]),
+        "mvp_channel_sum_workspace_bytes": (_c_size_t, [_c_int] * 2),
+        "mvp_channel_sum": (_c_int, [_c_int] * 3 + [_p] * 3 + [_c_size_t, _p]),
         "mvp_topk_rows": (_c_int, [ctypes.c_longlong, _c_int, _c_int] + [_p] * 4 + [_p]),
         "mvp_three_nn_weights_ws": (_c_int, [_c_int] * 3 + [_p] * 6 + [_c_size_t, _p]),
         "mvp_furthest_point_sampling_gather": (_c_int, [_c_int] * 3 + [_p] * 4 + [_c_int, _p]),

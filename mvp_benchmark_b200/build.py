@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmvp_ops.so")
-SOURCES = ["capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu", "chamfer_rest.cu", "emd.cu", "fps.cu", "loss.cu", "pointnet2.cu", "pointnet2_staged.cu"]
+SOURCES = ["capi.cu", "chamfer.cu", "chamfer_fused.cu", "chamfer_grid.cu", "chamfer_rest.cu", "emd.cu", "fps.cu", "loss.cu", "pointnet2.cu", "pointwise.cu", "pointnet2_staged.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

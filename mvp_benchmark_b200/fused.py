@@ -169,6 +169,148 @@ class _BallQueryGroup(torch.autograd.Function):
         return None, None, None, grad, None
 
 
+def _pointwise_conv_raw(x3, w2, bias, relu=False, mask=None, out_shape=None):
+    """x3 (B, C, N), w2 (O, C), bias (O) or None -> (B, O, N) (or out_shape, same elements) through
+    mvp_pointwise_conv(_masked); all contiguous fp32."""
+    dev = _lib.require_cuda(x3, w2, dtype=torch.float32, what="pointwise_conv")
+    B, C, N = x3.shape
+    O = w2.shape[0]
+    y = torch.empty(out_shape if out_shape is not None else (B, O, N), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        if mask is None:
+            _lib.check(_lib.lib.mvp_pointwise_conv(B, C, O, N, _lib.ptr(x3), _lib.ptr(w2),
+                                                   _lib.ptr(bias) if bias is not None else None, 1 if relu else 0,
+                                                   _lib.ptr(y), _lib.stream_of(x3)), "mvp_pointwise_conv")
+        else:
+            _lib.check(_lib.lib.mvp_pointwise_conv_masked(B, C, O, N, _lib.ptr(x3), _lib.ptr(mask), _lib.ptr(w2),
+                                                          _lib.ptr(y), _lib.stream_of(x3)), "mvp_pointwise_conv_masked")
+    return y
+
+
+kPointwiseBmmWgrad = 8192  # in x out channels up to which the weight gradient is a batched fp32 matmul (see model_patches)
+
+
+class _PointwiseConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        shp = x.shape
+        B, C = shp[0], shp[1]
+        N = x.numel() // max(1, B * C) if B * C else 0
+        x3 = x.reshape(B, C, N).contiguous()
+        w2 = weight.reshape(weight.shape[0], -1).contiguous()
+        if w2.shape[1] != C:
+            raise _lib.MvpOpsError("pointwise_conv: weight must be (out_channels, in_channels[, 1[, 1]])")
+        b1 = bias.contiguous() if bias is not None else None
+        y = _pointwise_conv_raw(x3, w2, b1, relu, out_shape=(B, w2.shape[0], *shp[2:]))
+        ctx.save_for_backward(x3, w2, y if relu else None)
+        ctx.meta = (shp, weight.shape, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x3, w2, y = ctx.saved_tensors
+        shp, wshape, has_bias = ctx.meta
+        B, C, N = x3.shape
+        O = w2.shape[0]
+        g3 = g.reshape(B, O, N).contiguous()
+        y3 = y.view(B, O, N) if y is not None else None
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # the input gradient is the same contraction with the weight transposed (and, behind a fused ReLU, with the
+            # gradient masked by the sign of the output as it is staged)
+            gx = _pointwise_conv_raw(g3, w2.t().contiguous(), None, False, mask=y3, out_shape=shp)
+        if y3 is not None and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
+            g3 = g3 * (y3 > 0)
+        if ctx.needs_input_grad[1]:
+            if O * C <= kPointwiseBmmWgrad:
+                gw = torch.bmm(g3, x3.transpose(1, 2)).sum(0)
+            else:  # a library TF32 weight gradient (cuDNN), as the layer's own backward would run
+                gw = torch.ops.aten.convolution_backward(g3.unsqueeze(-1), x3.unsqueeze(-1), w2.view(O, C, 1, 1), None,
+                                                         [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+                                                         [False, True, False])[1]
+            gw = gw.reshape(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = channel_sum(g3)
+        return gx, gw, gb, None
+
+
+def bias_add_(y, bias, relu=False):
+    """y (B, C, ...) += bias (C) over the channel axis IN PLACE (then ReLU if asked), through mvp_bias_add.  No autograd:
+    a building block of conv_bias / of a caller's own Function."""
+    dev = _lib.require_cuda(y, bias, dtype=torch.float32, what="bias_add_")
+    if not y.is_contiguous() or not bias.is_contiguous():
+        raise _lib.MvpOpsError("bias_add_: contiguous tensors expected")
+    B, C = y.shape[0], y.shape[1]
+    if bias.numel() != C:
+        raise _lib.MvpOpsError("bias_add_: bias must have one entry per channel")
+    N = y.numel() // max(1, B * C)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.mvp_bias_add(B, C, N, _lib.ptr(y), _lib.ptr(bias), 1 if relu else 0, _lib.stream_of(y)),
+                   "mvp_bias_add")
+    return y
+
+
+def channel_sum(g):
+    """g (B, C, ...) -> (C,): the sum over clouds and points of every channel (a bias gradient), deterministic, through
+    mvp_channel_sum.  No autograd."""
+    g = g.contiguous()
+    dev = _lib.require_cuda(g, dtype=torch.float32, what="channel_sum")
+    B, C = g.shape[0], g.shape[1]
+    N = g.numel() // max(1, B * C)
+    out = torch.zeros(C, device=dev, dtype=torch.float32)
+    if B == 0 or N == 0:
+        return out
+    nbytes = int(_lib.lib.mvp_channel_sum_workspace_bytes(B, C))
+    ws = torch.empty(nbytes // 4, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.mvp_channel_sum(B, C, N, _lib.ptr(g), _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream_of(g)),
+                   "mvp_channel_sum")
+    return out
+
+
+class _ConvBias(torch.autograd.Function):
+    """A wide 1x1 layer: the contraction on the library's TF32 GEMM (cuDNN, as nn.Conv would run it) WITHOUT its bias,
+    the bias added in place by mvp_bias_add and its gradient summed by mvp_channel_sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nd = x.dim() - 2
+        if weight.dim() != x.dim() or any(k != 1 for k in weight.shape[2:]):
+            raise _lib.MvpOpsError("conv_bias: weight must be (out_channels, in_channels, 1[, 1]) for a (B, C, N[, M]) input")
+        y = torch.ops.aten.convolution(x, weight, None, [1] * nd, [0] * nd, [1] * nd, False, [0] * nd, 1)
+        if y.numel() and y.is_contiguous():
+            bias_add_(y, bias.contiguous())
+        elif y.numel():  # a channels-last result: torch's own add
+            y.add_(bias.view(1, -1, *([1] * nd)))
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        nd = x.dim() - 2
+        g = g.contiguous()
+        gx, gw, _ = torch.ops.aten.convolution_backward(g, x, weight, None, [1] * nd, [0] * nd, [1] * nd, False, [0] * nd, 1,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        gb = channel_sum(g) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+def conv_bias(x, weight, bias):
+    """A 1x1 convolution WITH bias whose contraction stays on the library (see _ConvBias): x (B, C, N[, M]),
+    weight (O, C, 1[, 1]) (an nn.Conv1d's / nn.Conv2d's), bias (O) -> (B, O, N[, M])."""
+    return _ConvBias.apply(x, weight, bias)
+
+
+def pointwise_conv(x, weight, bias=None, relu=False):
+    """A 1x1 convolution (nn.Conv1d / nn.Conv2d with kernel_size 1: completion/models/*.py, model_utils.py) as what it
+    is over a point cloud — one (out, in) matrix applied to every point's feature vector — on the tensor cores through
+    this repository's tcgen05 kernel (csrc/pointwise.cu): TF32 operands, fp32 accumulation, bias (and optionally ReLU)
+    in the epilogue.  x (B, C, ...), weight (O, C[, 1[, 1]]), bias (O) or None -> (B, O, ...).  The input gradient runs
+    through the same kernel (weight transposed); the weight gradient is a library matmul / cuDNN call."""
+    return _PointwiseConv.apply(x, weight, bias, relu)
+
+
 def topk_rows(scores, k):
     """The k largest entries along the last axis of `scores` (..., cols), descending, equal scores in ascending index:
     (values, indices int64) like torch.topk(scores, k, dim=-1) — one warp per row, no multi-block radix select.  For

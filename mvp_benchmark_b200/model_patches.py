@@ -168,39 +168,57 @@ def sa_module_forward(self, input):
 
 
 def _pointwise_conv_forward(self, x):
-    """A THIN nn.Conv1d / nn.Conv2d with a 1x1 kernel as what it is — a matrix product over the channel axis — through
-    torch.baddbmm (a library GEMM: cuBLAS / CUTLASS; NOT a kernel of this repository).  Why: for the thin 1x1
-    convolutions of the completion models ((64, 64, 1, 3072) -> 4, 16 or 64 channels; 68 -> 2; 3 -> 128) cuDNN's
-    heuristics pick `wgrad2d_grouped_direct_kernel` for the weight gradient, 0.5-1.6 ms per call for 0.1-1.6 GFLOP of
-    work: 8.8 ms of a 36 ms VRCNet training step (profiles/r2_model_step.json).  As batched matmuls the same gradients
-    are two small GEMMs.  torch.matmul computes in full fp32 by default where cuDNN uses TF32: a little MORE accurate."""
+    """An nn.Conv1d / nn.Conv2d with a 1x1 kernel as what it is over a point cloud — one (out, in) matrix applied to every
+    point's feature vector — routed by shape (measured on B200, tools/pointwise_probe.py, profiles/r2_pointwise.md):
+      * up to 128 input and at least 64 output channels (HBM-bound: 64 -> 256 over 64 x 3072 points moves 252 MB for
+        6.4 GFLOP): this repository's tcgen05 kernel, bias in its epilogue (fused.pointwise_conv; 0.086 ms against
+        cuDNN + torch's bias add 0.187 ms), input gradient through the same kernel;
+      * THIN layers ((64, 64, 1, 3072) -> 4, 16 or 64 channels; 68 -> 2): torch.baddbmm, a library fp32 GEMM — cuDNN's
+        heuristics pick `wgrad2d_grouped_direct_kernel` for their weight gradient, 0.5-1.6 ms per call for 0.1-1.6 GFLOP:
+        8.8 ms of a 36 ms VRCNet training step;
+      * the wide, compute-bound layers with a bias (512 -> 1024 over 64 x 2048 points: 137 GFLOP): the library's TF32
+        GEMM without the bias, the bias added in place and its gradient summed by this repository's kernels
+        (fused.conv_bias: torch's broadcasting add and its sum run at 2.7 and 2.1 TB/s, these at 6.7 and 5.6);
+      * anything else: the module's own forward."""
     shp = x.shape
-    if 2.0 * x.numel() * self.out_channels > kPointwiseMaxFlops:
-        return self._conv_forward(x, self.weight, self.bias)   # a long tensor: cuDNN's TF32 kernels beat an fp32 GEMM
-    xs = x.reshape(shp[0], shp[1], -1)
-    w = self.weight.view(1, self.out_channels, self.in_channels).expand(shp[0], -1, -1)
-    if self.bias is not None:
-        y = torch.baddbmm(self.bias.view(1, -1, 1), w, xs)
-    else:
-        y = torch.bmm(w, xs)
-    return y.view(shp[0], self.out_channels, *shp[2:])
+    cin, cout = self.in_channels, self.out_channels
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
+        return self._conv_forward(x, self.weight, self.bias)
+    if cin <= kTensorCoreMaxIn and cout >= kTensorCoreMinOut and x.numel() >= kTensorCoreMinElems:
+        return fused.pointwise_conv(x, self.weight, self.bias)
+    if cin * cout <= kPointwiseMaxWeights and 2.0 * x.numel() * cout <= kPointwiseMaxFlops:
+        xs = x.reshape(shp[0], shp[1], -1)
+        w = self.weight.view(1, cout, cin).expand(shp[0], -1, -1)
+        if self.bias is not None:
+            y = torch.baddbmm(self.bias.view(1, -1, 1), w, xs)
+        else:
+            y = torch.bmm(w, xs)
+        return y.view(shp[0], cout, *shp[2:])
+    if self.bias is not None and x.numel() // cin * cout >= kConvBiasMinElems:
+        return fused.conv_bias(x, self.weight, self.bias)
+    return self._conv_forward(x, self.weight, self.bias)   # cuDNN's TF32 kernels
 
 
 kPointwiseMaxWeights = 16384  # in_channels * out_channels up to 64 x 256: above that cuDNN's TF32 kernels are the faster ones
 kPointwiseMaxFlops = 4e9      # ... and so they are for a thin convolution over a very long tensor (decided per call)
+kTensorCoreMaxIn = 128        # the tcgen05 kernel: weight tile resident, HBM-bound shapes
+kTensorCoreMinOut = 64
+kTensorCoreMinElems = 1 << 20  # input elements below which a launch is all there is to save
+kConvBiasMinElems = 1 << 22    # output elements from which the separate bias kernels pay
 
 
-def apply_pointwise_convs(model, max_weights=kPointwiseMaxWeights):
-    """Route the THIN 1x1, stride-1, ungrouped nn.Conv1d / nn.Conv2d modules of an instantiated model (in_channels x
-    out_channels <= max_weights) through _pointwise_conv_forward (same parameters, same state_dict; opt-in like
-    everything in this file).  Returns the number of modules switched."""
+def apply_pointwise_convs(model, max_weights=None):
+    """Route the 1x1, stride-1, ungrouped nn.Conv1d / nn.Conv2d modules of an instantiated model through
+    _pointwise_conv_forward (same parameters, same state_dict; opt-in like everything in this file; the route is chosen
+    per call from the shapes).  max_weights: only modules with in_channels x out_channels up to it (None: all).
+    Returns the number of modules switched."""
     import types
     count = 0
     for mod in model.modules():
         if (isinstance(mod, (torch.nn.Conv1d, torch.nn.Conv2d)) and all(k == 1 for k in mod.kernel_size)
                 and all(s_ == 1 for s_ in mod.stride) and not isinstance(mod.padding, str)
                 and all(p_ == 0 for p_ in mod.padding) and all(d == 1 for d in mod.dilation) and mod.groups == 1
-                and mod.in_channels * mod.out_channels <= max_weights):
+                and (max_weights is None or mod.in_channels * mod.out_channels <= max_weights)):
             mod.forward = types.MethodType(_pointwise_conv_forward, mod)
             count += 1
     return count

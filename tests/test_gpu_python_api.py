@@ -518,12 +518,129 @@ def test_model_patches_pointwise_convs(cuda):
     for n_, p in net.named_parameters():
         assert (p.grad - ref[n_]).abs().max().item() <= 1e-3 * ref[n_].abs().max().item(), n_
     big = nn.Conv1d(512, 1024, 1).to(cuda)
-    assert mp.apply_pointwise_convs(big) == 0               # wide ones stay on cuDNN
+    assert mp.apply_pointwise_convs(big, max_weights=16384) == 0   # the caller may leave the wide ones alone
     c1 = nn.Conv1d(16, 3, 1).to(cuda)
     y0 = c1(torch.ones(2, 16, 9, device=cuda))
     assert mp.apply_pointwise_convs(c1) == 1
     torch.testing.assert_close(c1(torch.ones(2, 16, 9, device=cuda)), y0, rtol=1e-3, atol=1e-4)
 
+
+
+def _tf32(t):
+    """round to nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32 does"""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("B,C,O,N,relu,bias", [(2, 32, 16, 128, False, False), (2, 64, 256, 384, False, True), (3, 3, 5, 77, True, True),
+                                               (2, 67, 300, 130, False, True), (2, 512, 1024, 256, True, True),
+                                               (1, 130, 16, 1000, False, False), (2, 8, 4, 2048, False, True),
+                                               (5, 128, 256, 700, True, True), (2, 256, 256, 130, False, True), (0, 8, 8, 16, False, True)])
+def test_pointwise_conv_tensor_core(cuda, B, C, O, N, relu, bias):
+    """mvp_pointwise_conv (tcgen05.mma kind::tf32, csrc/pointwise.cu; resident-weight and streaming variants by shape)
+    against the same contraction in fp64 of the TF32-rounded operands: what is left is fp32 accumulation order, so the
+    tolerance is 1e-4 of the output scale (against the unrounded operands: TF32's 2^-11 per operand)."""
+    from mvp_benchmark_b200 import fused
+    g = torch.Generator(device=cuda).manual_seed(B * 1000 + C + O + N)
+    x = torch.randn(B, C, N, device=cuda, generator=g)
+    w = torch.randn(O, C, device=cuda, generator=g) / C ** 0.5
+    bs = torch.randn(O, device=cuda, generator=g) if bias else None
+    y = fused.pointwise_conv(x, w, bs, relu)
+    assert y.shape == (B, O, N)
+    if B == 0:
+        return
+    ref = torch.matmul(_tf32(w).double(), _tf32(x).double())
+    full = torch.matmul(w.double(), x.double())
+    if bias:
+        ref, full = ref + bs.double().view(1, -1, 1), full + bs.double().view(1, -1, 1)
+    if relu:
+        ref, full = ref.clamp_min(0), full.clamp_min(0)
+    scale = full.abs().max().item()
+    assert (y.double() - ref).abs().max().item() <= 1e-4 * scale
+    assert (y.double() - full).abs().max().item() <= 2e-3 * scale
+
+
+def test_pointwise_conv_exact_cases_and_gradients(cuda):
+    """One-hot operands land where they should (the shared-memory operand layout: every (point, channel) pair of a tile
+    boundary case), values representable in TF32 come out exact, and the autograd Function's gradients agree with
+    nn.Conv1d's; the masked entry (input gradient behind a ReLU) equals the unmasked one on the masked gradient."""
+    import torch.nn.functional as F
+    from mvp_benchmark_b200 import fused
+    for (C, O, N, k, co, p) in [(32, 16, 128, 0, 0, 0), (32, 16, 128, 5, 3, 77), (64, 256, 256, 37, 200, 130),
+                                (8, 16, 128, 7, 15, 127), (40, 48, 300, 33, 47, 299), (300, 70, 129, 299, 69, 128)]:
+        x = torch.zeros(1, C, N, device=cuda); x[0, k, p] = 1.0
+        w = torch.zeros(O, C, device=cuda); w[co, k] = 2.0
+        y = fused.pointwise_conv(x, w)
+        nz = torch.nonzero(y)
+        assert nz.shape[0] == 1 and nz[0].tolist() == [0, co, p] and float(y[0, co, p]) == 2.0
+    g = torch.Generator(device=cuda).manual_seed(3)
+    xi = torch.randint(-8, 9, (3, 96, 515), device=cuda, generator=g).float()
+    wi = torch.randint(-4, 5, (80, 96), device=cuda, generator=g).float()
+    assert torch.equal(fused.pointwise_conv(xi, wi), torch.matmul(wi, xi))        # small integers: exact in TF32 and fp32
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for (B, C, O, N) in [(4, 64, 256, 512), (2, 130, 48, 300), (2, 512, 640, 256)]:
+            x = torch.randn(B, C, N, device=cuda, generator=g).requires_grad_(True)
+            w = (torch.randn(O, C, 1, device=cuda, generator=g) / C ** 0.5).requires_grad_(True)
+            bs = torch.randn(O, device=cuda, generator=g).requires_grad_(True)
+            go = torch.randn(B, O, N, device=cuda, generator=g)
+            for relu in (False, True):
+                y = fused.pointwise_conv(x, w, bs, relu); y.backward(go)
+                got = [y.detach(), x.grad.clone(), w.grad.clone(), bs.grad.clone()]
+                x.grad = w.grad = bs.grad = None
+                y2 = F.conv1d(x, w, bs)
+                if relu:  # the sign pattern of THIS output: a pre-activation within TF32 rounding of zero may fall either way
+                    y2 = y2 * (got[0] > 0)
+                y2.backward(go)
+                for a, r in zip(got, [y2.detach(), x.grad, w.grad, bs.grad]):
+                    assert (a - r).abs().max().item() <= 3e-3 * r.abs().max().item()
+                x.grad = w.grad = bs.grad = None
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    go = torch.randn(2, 48, 300, device=cuda, generator=g); yy = torch.randn(2, 48, 300, device=cuda, generator=g)
+    wt = torch.randn(130, 48, device=cuda, generator=g)
+    m1, m2 = fused._pointwise_conv_raw(go, wt, None, False, mask=yy), fused._pointwise_conv_raw(go * (yy > 0), wt, None)
+    assert (m1 - m2).abs().max().item() <= 1e-5 * m2.abs().max().item()   # two kernels (streaming / resident), same products
+
+
+@pytest.mark.parametrize("B,C,N", [(8, 1024, 2048), (3, 5, 77), (64, 4, 3072), (2, 1000, 6), (7, 33, 1)])
+def test_bias_add_and_channel_sum(cuda, B, C, N):
+    """mvp_bias_add: bit-identical to torch's broadcasting add (one IEEE add per element); mvp_channel_sum: the
+    per-channel sum over clouds and points within fp32 accumulation error of the fp64 sum, and deterministic."""
+    from mvp_benchmark_b200 import fused
+    g = torch.Generator(device=cuda).manual_seed(C)
+    y = torch.randn(B, C, N, device=cuda, generator=g); bs = torch.randn(C, device=cuda, generator=g)
+    assert torch.equal(fused.bias_add_(y.clone(), bs), y + bs.view(1, -1, 1))
+    assert torch.equal(fused.bias_add_(y.clone(), bs, relu=True), (y + bs.view(1, -1, 1)).clamp_min(0))
+    s1, s2 = fused.channel_sum(y), fused.channel_sum(y)
+    assert torch.equal(s1, s2)
+    want = y.double().sum((0, 2))
+    assert (s1.double() - want).abs().max().item() <= 2e-6 * y.abs().double().sum((0, 2)).max().item()
+    y4 = y.view(B, C, N, 1)
+    assert torch.equal(fused.channel_sum(y4), s1)
+
+
+def test_model_patches_conv_routes(cuda):
+    """_pointwise_conv_forward's three routes give what nn.Conv gives (TF32 tolerance) with gradients: the tcgen05 kernel
+    (64 -> 256 over a long tensor), the library GEMM with this repository's bias kernels (512 -> 640), cuDNN for the rest."""
+    from torch import nn
+    from mvp_benchmark_b200 import model_patches as mp
+    torch.manual_seed(5)
+    for conv, x in ((nn.Conv2d(64, 256, 1), torch.randn(16, 64, 1, 1100, device=cuda)),
+                    (nn.Conv1d(512, 640, 1), torch.randn(16, 512, 600, device=cuda)),
+                    (nn.Conv1d(300, 20, 1), torch.randn(4, 300, 50, device=cuda))):
+        conv = conv.to(cuda)
+        a = x.clone().requires_grad_(True)
+        want = conv(a); want.square().sum().backward()
+        ref = [a.grad.clone()] + [p.grad.clone() for p in conv.parameters()]
+        conv.zero_grad()
+        assert mp.apply_pointwise_convs(conv) == 1
+        b = x.clone().requires_grad_(True)
+        got = conv(b); got.square().sum().backward()
+        assert (got - want).abs().max().item() <= 3e-3 * want.abs().max().item()
+        for u, v in zip([b.grad] + [p.grad for p in conv.parameters()], ref):
+            assert (u - v).abs().max().item() <= 5e-3 * v.abs().max().item()
 
 
 @pytest.mark.parametrize("shape,k", [((3, 700, 700), 16), ((2, 5, 33), 32), ((4096, 40), 1), ((2, 3, 2048, 2048), 20), ((1, 9, 31), 31)])

@@ -32,3 +32,16 @@ for e in prof.key_averages(group_by_input_shape=True):
 rows.sort(reverse=True)
 for r in rows[:70]:
     print("%.3f ms x%d %s %s" % r)
+
+# the same step by operator name only (no shape split, no threshold): where the long tail goes
+tot = {}
+nk = 0
+for e in prof.key_averages():
+    if e.device_time_total > 0 and not e.key.startswith("aten::") and not e.key.startswith("autograd::") and "Backward" not in e.key:
+        nk += e.count
+for e in prof.key_averages():
+    if e.key.startswith("aten::") and e.self_device_time_total > 0:
+        tot[e.key] = (e.self_device_time_total / 1e3, e.count)
+print("-- self device time by aten op (ms, calls); %d device kernels/memsets in the step" % nk)
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
+    print("%.3f ms x%d %s" % (v[0], v[1], k))
