@@ -218,37 +218,31 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_conv_kernel(int cin, int
 
 // ---- the thin layers: weight resident, persistent CTAs -------------------------------------------------------------------
 // When the (nt x cin) weight tile fits in shared memory next to the staging ring it is staged ONCE per CTA, and the CTA
-// walks over (cloud, 128-point tile) pairs: per step of 32 input channels the points' features arrive by cp.async
-// (4-byte copies into the K-major core-matrix layout: the transposition happens in the copy, no registers, kPwStages - 1
-// steps in flight), one thread issues the step's MMAs into one of TWO accumulators in tensor memory, and while the
-// tensor core works on tile T all 16 warps run the epilogue of tile T - 1 from the other accumulator.
-// Each thread then rounds the 32 bytes it copied to TF32 in place (cvt.rna, like the weights): the tensor core would
-// otherwise truncate them.  The MMAs of step q - 2 must be done before their stage is refilled (not those of q - 1: the
-// tensor core always has the next step queued).
-// kPwStages stages (template: 6 when they fit next to the weight tile, else 4); 4 resp. 3 steps of copies in flight.
+// walks over (cloud, 128-point tile) pairs in steps of 32 input channels.  A step's features travel HBM -> registers
+// (eight coalesced 4-byte loads per thread: one point, eight channels) -> TF32 rounding -> two 16-byte stores into the
+// K-major core-matrix layout; the loads of the next kPwAhead steps are already in flight in registers when a step is
+// stored (48 KB per SM).  One thread issues the step's MMAs into one of TWO accumulators in tensor memory, and while
+// the tensor core works on tile T all 16 warps run the epilogue of tile T - 1 from the other accumulator.
+// (Tried and dropped: cp.async 4-byte copies straight into the layout — LDGSTS.32 moves about one element per clock per
+// SM, 1.7 us per 16 KB step; 16-byte copies need the MN-major operand form, which in its no-swizzle variant gave zeros.)
+constexpr int kPwStages = 3;   // shared-memory stages (the tensor core reads one while the next is written)
+constexpr int kPwAhead = 3;    // steps of loads in flight in registers
 constexpr int kPwRThreads = 512;
-
-__device__ __forceinline__ void cp_async4(uint32_t dst, const float *src, bool valid) {
-  const uint32_t sz = valid ? 4u : 0u;  // src-size 0: the four bytes are zero-filled, nothing is read
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
+static_assert(kPwStages == kPwAhead, "stage u and register set u belong to the same step");
 
 // grid (G, channel tiles): CTA (g, ct) owns output channels [ct * nt, ct * nt + nt) and the point tiles g, g + G, ...
 // of the b * ceil(n / 128) tiles.  acc_cols: columns between the two accumulators (power of two >= max(32, nt)).
-template <int kPwStages>
 __global__ void __launch_bounds__(kPwRThreads, 1) pointwise_resident_kernel(int b, int cin, int cout, int n,
                                                                             const float *__restrict__ x,
                                                                             const float *__restrict__ w,
                                                                             const float *__restrict__ bias,
                                                                             float *__restrict__ y, int relu, int nt,
                                                                             int acc_cols) {
-  constexpr int kPwAhead = kPwStages == 4 ? 3 : kPwStages - 2;  // steps of copies in flight
-  constexpr int kPwLag = kPwStages - kPwAhead;                  // the stage refilled at step q held step q - kPwLag
   extern __shared__ __align__(128) unsigned char pw_smem[];
   __shared__ __align__(8) uint64_t abar[kPwStages];  // a stage's MMAs are done: it may be overwritten
   __shared__ __align__(8) uint64_t tbar[2];          // an accumulator is complete
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[kPwMaxN];
+  __shared__ __align__(16) float s_bias[kPwMaxN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int co0 = blockIdx.y * nt;
   const int cin8 = (cin + 7) & ~7;
@@ -274,27 +268,40 @@ __global__ void __launch_bounds__(kPwRThreads, 1) pointwise_resident_kernel(int 
   }
   for (int i = tid; i < nt; i += kPwRThreads) s_bias[i] = (bias && co0 + i < cout) ? __ldg(bias + co0 + i) : 0.f;
 
-  // the features of step q (tile q / nk of this CTA, channels (q % nk) * 32 ...) into stage q % kPwStages
-  const int pm = tid & (kPwM - 1), kgrp = tid >> 7;  // this thread copies point pm, channels kgrp * 8 ... + 7 of the step
-  auto prefetch = [&](int q) {
-    if (q < steps) {
-      const int tl = q / nk, c = q - tl * nk;
-      const int tile = blockIdx.x + tl * gridDim.x;
-      const int bb = tile / tiles_p, p0 = (tile - bb * tiles_p) * kPwM;
-      const bool p_ok = p0 + pm < n;
-      const float *src = x + ((size_t)bb * cin + c * kPwKC + kgrp * 8) * n + (p_ok ? p0 + pm : 0);
-      const uint32_t dst = smem0 + (q % kPwStages) * a_bytes + (kgrp * 2) * (kPwM * 16) + pm * 16;
-      const int kleft = cin - (c * kPwKC + kgrp * 8);  // channels of this thread's eight that exist
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const bool ok = p_ok && i < kleft;
-        cp_async4(dst + (i >> 2) * (kPwM * 16) + (i & 3) * 4, ok ? src + (size_t)i * n : x, ok);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  // the features of a step (32 input channels of one 128-point tile): this thread's are point pm, channels kgrp * 8 ... + 7.
+  // The load side runs kPwAhead steps ahead of the compute side; both keep their (tile, chunk) position incrementally
+  // (the kernel is bound by instruction issue: no divisions or 64-bit multiplies per step).
+  const int pm = tid & (kPwM - 1), kgrp = tid >> 7;
+  const size_t chunk_stride = (size_t)kPwKC * n;
+  int ld_c = 0, ld_tile = blockIdx.x;
+  bool ld_pok = false;
+  const float *ld_ptr = x;
+  auto ld_setup = [&]() {  // at the start of a tile
+    const int bb = ld_tile / tiles_p, p0 = (ld_tile - bb * tiles_p) * kPwM;
+    ld_pok = p0 + pm < n;
+    ld_ptr = x + ((size_t)bb * cin + kgrp * 8) * n + (ld_pok ? p0 + pm : 0);
   };
-#pragma unroll 1
-  for (int q = 0; q < kPwAhead; q++) prefetch(q);
+  ld_setup();
+  auto gload = [&](float (&r)[8]) {
+    const int kleft = cin - (ld_c * kPwKC + kgrp * 8);  // channels of this thread's eight that exist
+    if (ld_pok && kleft >= 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = __ldg(ld_ptr + (size_t)i * n);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = (ld_pok && i < kleft) ? __ldg(ld_ptr + (size_t)i * n) : 0.f;
+    }
+    ld_ptr += chunk_stride;
+    if (++ld_c == nk) {
+      ld_c = 0;
+      ld_tile += gridDim.x;
+      ld_setup();
+    }
+  };
+  float rg[kPwAhead][8];
+#pragma unroll
+  for (int u = 0; u < kPwAhead; u++)
+    if (u < steps) gload(rg[u]);
 
   // the weight tile, once: rows co0 ... co0 + nt - 1, all (padded) input channels
   {
@@ -327,60 +334,79 @@ __global__ void __launch_bounds__(kPwRThreads, 1) pointwise_resident_kernel(int 
     mbar_wait(&tbar[tl & 1], (tl >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int tile = blockIdx.x + tl * gridDim.x;
-    const int bb = tile / tiles_p, p = (tile - bb * tiles_p) * kPwM + (warp & 3) * 32 + lane;
+    const int bb = tile / tiles_p, p0 = (tile - bb * tiles_p) * kPwM, p = p0 + (warp & 3) * 32 + lane;
     float *yb = y + ((size_t)bb * cout + co0) * n + p;
+    const bool full = p0 + kPwM <= n && co0 + nt <= cout;  // no guards needed anywhere in the tile
     for (int cb = warp >> 2; cb * 32 < nt; cb += kPwRThreads / 128) {
       uint32_t r[32];
       tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (tl & 1) * acc_cols + cb * 32, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float *yp = yb + (size_t)(cb * 32) * n;
+      if (full && cb * 32 + 32 <= nt) {
+        const float4 *sb = reinterpret_cast<const float4 *>(s_bias + cb * 32);
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int col = cb * 32 + j;
-        if (col < nt && co0 + col < cout && p < n) {
-          float v = __uint_as_float(r[j]) + s_bias[col];
-          if (relu) v = fmaxf(v, 0.f);
-          yb[(size_t)col * n] = v;
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 bv = sb[j4];
+          float v0 = __uint_as_float(r[4 * j4 + 0]) + bv.x, v1 = __uint_as_float(r[4 * j4 + 1]) + bv.y;
+          float v2 = __uint_as_float(r[4 * j4 + 2]) + bv.z, v3 = __uint_as_float(r[4 * j4 + 3]) + bv.w;
+          if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+          yp[(size_t)(4 * j4 + 0) * n] = v0;
+          yp[(size_t)(4 * j4 + 1) * n] = v1;
+          yp[(size_t)(4 * j4 + 2) * n] = v2;
+          yp[(size_t)(4 * j4 + 3) * n] = v3;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int col = cb * 32 + j;
+          if (col < nt && co0 + col < cout && p < n) {
+            float v = __uint_as_float(r[j]) + s_bias[col];
+            if (relu) v = fmaxf(v, 0.f);
+            yp[(size_t)j * n] = v;
+          }
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
 
+  int tl = 0, c = 0;  // the compute side's tile (of this CTA) and chunk
 #pragma unroll 1
-  for (int q = 0; q < steps; q++) {
-    const int tl = q / nk, c = q - tl * nk;
-    // stage (q - kPwLag) % S is free once step q - kPwLag's MMAs are done: refill it with step q + kPwAhead
-    if (q >= kPwLag) mbar_wait(&abar[(q - kPwLag) % kPwStages], ((q - kPwLag) / kPwStages) & 1);
-    prefetch(q + kPwAhead);
-    asm volatile("cp.async.wait_group %0;" ::"n"(kPwAhead) : "memory");  // this thread's part of step q has landed
-    {
-      const uint32_t mine = smem0 + (q % kPwStages) * a_bytes + (kgrp * 2) * (kPwM * 16) + pm * 16;
+  for (int q0 = 0; q0 < steps; q0 += kPwAhead) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        uint32_t v0, v1, v2, v3;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(mine + h * (kPwM * 16)));
-        sts128(mine + h * (kPwM * 16), to_tf32(__uint_as_float(v0)), to_tf32(__uint_as_float(v1)), to_tf32(__uint_as_float(v2)),
-               to_tf32(__uint_as_float(v3)));
+    for (int u = 0; u < kPwAhead; u++) {  // kPwAhead == kPwStages: stage u, registers u
+      const int q = q0 + u;
+      if (q >= steps) break;  // uniform over the CTA
+      // the stage's previous contents (step q - kPwStages) have been consumed by the tensor core
+      if (q0 > 0) mbar_wait(&abar[u], ((q0 / kPwStages) - 1) & 1);
+      const uint32_t a_s = smem0 + u * a_bytes;
+      {
+        const uint32_t mine = a_s + (kgrp * 2) * (kPwM * 16) + pm * 16;
+        sts128(mine, to_tf32(rg[u][0]), to_tf32(rg[u][1]), to_tf32(rg[u][2]), to_tf32(rg[u][3]));
+        sts128(mine + kPwM * 16, to_tf32(rg[u][4]), to_tf32(rg[u][5]), to_tf32(rg[u][6]), to_tf32(rg[u][7]));
+      }
+      if (q + kPwAhead < steps) gload(rg[u]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int kq_n = min(kPwKC, cin8 - c * kPwKC) >> 3;
+        for (int j = 0; j < kq_n; j++) {
+          const uint64_t ad = umma_desc(a_s + j * 2 * (kPwM * 16), kPwM * 16, 128);
+          const uint64_t bd = umma_desc(w_s + (c * (kPwKC / 4) + j * 2) * (nt * 16), nt * 16, 128);
+          umma_tf32(tmem + (tl & 1) * acc_cols, ad, bd, idesc, (c > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&abar[u]);
+        if (c == nk - 1) umma_commit(&tbar[tl & 1]);
+      }
+      if (++c == nk) {
+        c = 0;
+        if (tl > 0) epilogue(tl - 1);  // overlaps the tensor core's work on tile tl
+        tl++;
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_s = smem0 + (q % kPwStages) * a_bytes;
-      const int kq_n = min(kPwKC, cin8 - c * kPwKC) >> 3;
-      for (int j = 0; j < kq_n; j++) {
-        const uint64_t ad = umma_desc(a_s + j * 2 * (kPwM * 16), kPwM * 16, 128);
-        const uint64_t bd = umma_desc(w_s + (c * (kPwKC / 4) + j * 2) * (nt * 16), nt * 16, 128);
-        umma_tf32(tmem + (tl & 1) * acc_cols, ad, bd, idesc, (c > 0 || j > 0) ? 1u : 0u);
-      }
-      umma_commit(&abar[q % kPwStages]);
-      if (c == nk - 1) umma_commit(&tbar[tl & 1]);
-    }
-    if (c == nk - 1 && tl > 0) epilogue(tl - 1);  // overlaps the tensor core's work on tile tl
   }
   if (my_tiles > 0) epilogue(my_tiles - 1);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * acc_cols) : "memory");
@@ -398,26 +424,24 @@ static int pointwise_launch(int b, int cin, int cout, int n, const float *x, con
   while (cols < nt) cols <<= 1;
   // the weight tile resident next to the staging ring (thin layers): persistent CTAs, two accumulators
   static const int mode = [] { const char *e = getenv("MVP_POINTWISE"); return e ? atoi(e) : 0; }();  // 1: streaming kernel only
-  const size_t stage = (size_t)kPwM * kPwKC * 4, cin8 = (size_t)((cin + 7) & ~7), budget = 200 * 1024;
-  auto fits = [&](int stages, int ntx) { return stages * stage + cin8 * ntx * 4 + 128 <= budget; };
-  const int stages = fits(6, nt) ? 6 : 4;
+  const size_t ring = (size_t)kPwStages * kPwM * kPwKC * 4, cin8 = (size_t)((cin + 7) & ~7), budget = 200 * 1024;
+  auto fits = [&](int ntx) { return ring + cin8 * ntx * 4 + 128 <= budget; };
   int ct = tiles_n, ntr = nt;  // more, narrower channel tiles until the weight tile fits (x is then re-read from L2)
-  while (!fits(stages, ntr) && ntr > 32) {
+  while (!fits(ntr) && ntr > 32) {
     ct++;
     ntr = (((cout + ct - 1) / ct) + 15) & ~15;
   }
-  if (!mask && mode != 1 && fits(stages, ntr) && ct <= 8) {
-    const size_t smem_r = stages * stage + cin8 * ntr * 4 + 128;
+  if (!mask && mode != 1 && fits(ntr) && ct <= 8) {
+    const size_t smem_r = ring + cin8 * ntr * 4 + 128;
     int colsr = 32;
     while (colsr < ntr) colsr <<= 1;
-    static size_t granted_r[2][kMaxDevices];
-    auto kernel = stages == 6 ? pointwise_resident_kernel<6> : pointwise_resident_kernel<4>;
-    const int st = grant_dyn_smem(kernel, smem_r, granted_r[stages == 6]);
+    static size_t granted_r[kMaxDevices];
+    const int st = grant_dyn_smem(pointwise_resident_kernel, smem_r, granted_r);
     if (st != MVP_OK) return st;
     ct = (cout + ntr - 1) / ntr;
     const long long tiles = (long long)b * ((n + kPwM - 1) / kPwM);
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(tiles, kNumSMs / ct)), ct, 1);
-    kernel<<<grid, kPwRThreads, smem_r, s>>>(b, cin, cout, n, x, w, bias, y, relu, ntr, colsr);
+    pointwise_resident_kernel<<<grid, kPwRThreads, smem_r, s>>>(b, cin, cout, n, x, w, bias, y, relu, ntr, colsr);
     count_launch();
     return launch_status();
   }

@@ -27,6 +27,8 @@ KEY_METRICS = [
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_tf32_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",

@@ -2,7 +2,7 @@
 """One call of every operator family at the sizes the completion models use — the subject of the per-kernel ncu
 captures summarised under profiles/ (run it under `ncu --set full -k regex:mvp`; keep it short: ncu replays every
 kernel ~40 times).   python tools/profile_ops.py [family ...]   families: fps gather group interp three_nn knn_points
-ball_query knn fused chamfer_brute chamfer_bwd emd"""
+ball_query knn fused pointwise chamfer_brute chamfer_bwd emd"""
 import os
 import sys
 
@@ -51,6 +51,14 @@ if on("ball_query"):
 if on("knn"):
     mm.knn(16, R(64, 2048, 3), R(64, 512, 3), False)
     mm.knn(64, R(16, 8192, 3), R(16, 2048, 3), False)
+if on("pointwise"):
+    # the tcgen05 1x1 layer: resident-weight kernel (64 -> 256 and 128 -> 256: forward, input gradient), streaming kernel
+    # (512 -> 512), and the bias kernels of the wide layers
+    for (b, c, o, n) in ((64, 64, 256, 3072), (64, 256, 64, 3072), (64, 128, 256, 2048), (64, 512, 512, 384)):
+        fused._pointwise_conv_raw(N(b, c, n), N(o, c), N(o))
+    y = N(64, 1024, 2048)
+    fused.bias_add_(y, N(1024))
+    fused.channel_sum(y)
 if on("fused"):
     f = N(64, 64, 3072).requires_grad_(True)
     i = torch.randint(0, 3072, (64, 1536, 10), device=dev, generator=g, dtype=torch.int32)
