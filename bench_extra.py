@@ -391,6 +391,34 @@ def run(dev, hbm_gbs=None):
     fused_entry("fps_gather_64x3072_to_1536", lambda: fused.fps_gather(fp, 1536),
                 lambda: mm.gather_points(fp.transpose(1, 2).contiguous(), mm.furthest_point_sample(fp, 1536)).transpose(1, 2).contiguous(),
                 "furthest_point_sample + transpose + gather_points + transpose (model_utils.py:91-93)")
+    # ---- the 1x1 layers (csrc/pointwise.cu): tcgen05 contraction with the bias in its epilogue, against cuDNN's TF32
+    # convolution + torch's bias add; the bias kernels of the wide layers against torch's add / sum
+    import torch.nn.functional as F
+    for (pb, pc, po, pn) in ((64, 64, 256, 3072), (64, 128, 256, 2048)):
+        px = torch.randn(pb, pc, pn, device=dev, generator=g)
+        pw = torch.randn(po, pc, device=dev, generator=g) / pc ** 0.5
+        pbias = torch.randn(po, device=dev, generator=g)
+        pg = torch.randn(pb, po, pn, device=dev, generator=g)
+        pwt, pw3 = pw.t().contiguous(), pw.view(po, pc, 1)
+        tag = "%dx%dto%dx%d" % (pb, pc, po, pn)
+        fused_entry("pointwise_conv_forward_" + tag, lambda: fused._pointwise_conv_raw(px, pw, pbias),
+                    lambda: F.conv1d(px, pw3, pbias), "nn.Conv1d / nn.Conv2d(kernel 1) forward: cuDNN TF32 + bias add")
+        out["pointwise_conv_forward_" + tag]["algorithmic_GBps"] = 4.0 * pb * (pc + po) * pn / out["pointwise_conv_forward_" + tag]["ours_ms"] / 1e6
+        fused_entry("pointwise_conv_input_grad_" + tag, lambda: fused._pointwise_conv_raw(pg, pwt, None),
+                    lambda: torch.ops.aten.convolution_backward(pg, px, pw3, None, [1], [0], [1], False, [0], 1, [True, False, False]),
+                    "the layer's input gradient: cuDNN dgrad")
+        fused_entry("pointwise_wgrad_bias_" + tag, lambda: fused._pointwise_wgrad_raw(pg, px, True),
+                    lambda: (torch.ops.aten.convolution_backward(pg, px, pw3, None, [1], [0], [1], False, [0], 1, [False, True, False]), pg.sum((0, 2))),
+                    "the layer's weight + bias gradients: cuDNN wgrad + torch.sum")
+    by = torch.randn(64, 1024, 2048, device=dev, generator=g)
+    bb = torch.randn(1024, device=dev, generator=g)
+    fused_entry("bias_add_64x1024x2048", lambda: fused.bias_add_(by, bb), lambda: by.add_(bb.view(1, -1, 1)),
+                "the bias add of a wide 1x1 layer (torch's broadcasting add_)")
+    out["bias_add_64x1024x2048"]["algorithmic_GBps"] = 2 * 4.0 * by.numel() / out["bias_add_64x1024x2048"]["ours_ms"] / 1e6
+    fused_entry("channel_sum_64x1024x2048", lambda: fused.channel_sum(by), lambda: by.sum((0, 2)),
+                "the bias gradient of a wide 1x1 layer (torch.sum over clouds and points)")
+    out["channel_sum_64x1024x2048"]["algorithmic_GBps"] = 4.0 * by.numel() / out["channel_sum_64x1024x2048"]["ours_ms"] / 1e6
+    del by
     out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
     steps = model_steps()
     if steps is not None:

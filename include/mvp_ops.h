@@ -238,6 +238,15 @@ int mvp_pointwise_conv(int b, int cin, int cout, int n, const float *x, const fl
 int mvp_pointwise_conv_masked(int b, int cin, int cout, int n, const float *x, const float *mask, const float *w, float *y,
                               mvp_stream_t stream);
 
+/* The weight and bias gradients of the same layer, again on the tensor cores (UMMA M = output channels, N = input
+ * channels, K = points: both operands K-major as they lie): grad_w[o,c] = sum_b sum_p g[b,o,p] * x[b,c,p], (cout,cin);
+ * grad_bias[o] = sum_b sum_p g[b,o,p] (a row of ones appended to x in shared memory) or NULL.  g (b,cout,n), x (b,cin,n).
+ * cin + (grad_bias != NULL) <= 256.  Deterministic: persistent CTAs write partial products, added in a fixed order.
+ * workspace: mvp_pointwise_wgrad_workspace_bytes(cin, cout, with_bias) bytes of device memory. */
+size_t mvp_pointwise_wgrad_workspace_bytes(int cin, int cout, int with_bias);
+int mvp_pointwise_wgrad(int b, int cin, int cout, int n, const float *g, const float *x, float *grad_w, float *grad_bias,
+                        void *workspace, size_t workspace_bytes, mvp_stream_t stream);
+
 /* The bias of a wide 1x1 layer that stays on a library GEMM: y[b,c,:] += bias[c] in place (then max(., 0) if relu),
  * y (b,c,n); and its gradient: out[c] = sum over clouds and points of g[b,c,p], g (b,c,n), in a fixed order
  * (deterministic).  workspace: mvp_channel_sum_workspace_bytes(b, c) bytes of device memory. */

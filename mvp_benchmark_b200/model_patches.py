@@ -184,9 +184,10 @@ def _pointwise_conv_forward(self, x):
     cin, cout = self.in_channels, self.out_channels
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
         return self._conv_forward(x, self.weight, self.bias)
-    if cin <= kTensorCoreMaxIn and cout >= kTensorCoreMinOut and x.numel() >= kTensorCoreMinElems:
+    thin = cin * cout <= kPointwiseMaxWeights and 2.0 * x.numel() * cout <= kPointwiseMaxFlops
+    if x.numel() >= kTensorCoreMinElems and (thin or (cin <= kTensorCoreMaxIn and cout >= kTensorCoreMinOut)):
         return fused.pointwise_conv(x, self.weight, self.bias)
-    if cin * cout <= kPointwiseMaxWeights and 2.0 * x.numel() * cout <= kPointwiseMaxFlops:
+    if thin:
         xs = x.reshape(shp[0], shp[1], -1)
         w = self.weight.view(1, cout, cin).expand(shp[0], -1, -1)
         if self.bias is not None:

@@ -580,7 +580,7 @@ def test_pointwise_conv_exact_cases_and_gradients(cuda):
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        for (B, C, O, N) in [(4, 64, 256, 512), (2, 130, 48, 300), (2, 512, 640, 256)]:
+        for (B, C, O, N) in [(4, 64, 256, 512), (2, 130, 48, 300), (2, 512, 640, 256), (3, 128, 256, 700)]:
             x = torch.randn(B, C, N, device=cuda, generator=g).requires_grad_(True)
             w = (torch.randn(O, C, 1, device=cuda, generator=g) / C ** 0.5).requires_grad_(True)
             bs = torch.randn(O, device=cuda, generator=g).requires_grad_(True)
@@ -602,6 +602,32 @@ def test_pointwise_conv_exact_cases_and_gradients(cuda):
     wt = torch.randn(130, 48, device=cuda, generator=g)
     m1, m2 = fused._pointwise_conv_raw(go, wt, None, False, mask=yy), fused._pointwise_conv_raw(go * (yy > 0), wt, None)
     assert (m1 - m2).abs().max().item() <= 1e-5 * m2.abs().max().item()   # two kernels (streaming / resident), same products
+
+
+@pytest.mark.parametrize("B,C,O,N,bias", [(2, 32, 16, 128, True), (3, 64, 256, 384, True), (3, 3, 5, 77, True), (2, 67, 300, 130, False),
+                                          (4, 255, 40, 515, True), (2, 256, 128, 1000, False), (16, 64, 4, 3072, True), (1, 8, 8, 4, True),
+                                          (5, 128, 256, 700, True)])
+def test_pointwise_wgrad_tensor_core(cuda, B, C, O, N, bias):
+    """mvp_pointwise_wgrad (tcgen05, K = points, a row of ones for the bias gradient) against fp64 sums of the
+    TF32-rounded operands (1e-4 of the scale: accumulation order) and of the raw operands (TF32's rounding);
+    deterministic: two runs are bit-identical."""
+    from mvp_benchmark_b200 import fused
+    g_ = torch.Generator(device=cuda).manual_seed(C * 7 + O)
+    x = torch.randn(B, C, N, device=cuda, generator=g_)
+    g = torch.randn(B, O, N, device=cuda, generator=g_)
+    gw, gb = fused._pointwise_wgrad_raw(g, x, bias)
+    gw2, gb2 = fused._pointwise_wgrad_raw(g, x, bias)
+    assert torch.equal(gw, gw2) and (not bias or torch.equal(gb, gb2))
+    ref = torch.einsum("bon,bcn->oc", _tf32(g).double(), _tf32(x).double())
+    full = torch.einsum("bon,bcn->oc", g.double(), x.double())
+    scale = full.abs().max().item()
+    assert (gw.double() - ref).abs().max().item() <= 1e-4 * scale
+    assert (gw.double() - full).abs().max().item() <= 3e-3 * scale
+    if bias:
+        sref = _tf32(g).double().sum((0, 2))
+        assert (gb.double() - sref).abs().max().item() <= 1e-4 * g.abs().double().sum((0, 2)).max().item()
+    else:
+        assert gb is None
 
 
 @pytest.mark.parametrize("B,C,N", [(8, 1024, 2048), (3, 5, 77), (64, 4, 3072), (2, 1000, 6), (7, 33, 1)])

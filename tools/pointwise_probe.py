@@ -70,11 +70,28 @@ def timings():
                "baddbmm_fp32": timeit(lambda: torch.baddbmm(bs.view(1, -1, 1), w.view(1, O, C).expand(B, -1, -1), x)),
                "ours_dgrad": timeit(lambda: fused._pointwise_conv_raw(g, wt, None)),
                "cudnn_dgrad": timeit(lambda: torch.ops.aten.convolution_backward(g.unsqueeze(-1), x.unsqueeze(-1), w.view(O, C, 1, 1), None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False])),
+               "ours_wgrad_bias": timeit(lambda: fused._pointwise_wgrad_raw(g, x, True)) if C < 256 else None,
+               "bmm_wgrad": timeit(lambda: torch.bmm(g, x.transpose(1, 2)).sum(0)),
                "cudnn_wgrad": timeit(lambda: torch.ops.aten.convolution_backward(g.unsqueeze(-1), x.unsqueeze(-1), w.view(O, C, 1, 1), None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [False, True, False])),
                "bytes_MB": (B * (C + O) * N * 4) / 1e6, "gflop": 2.0 * B * C * O * N / 1e9}
         out["%dx%d->%dx%d" % (B, C, O, N)] = row
-        print("%dx%d->%dx%d" % (B, C, O, N), json.dumps({k: round(v, 4) for k, v in row.items()}), flush=True)
+        print("%dx%d->%dx%d" % (B, C, O, N), json.dumps({k: round(v, 4) for k, v in row.items() if v is not None}), flush=True)
     return out
+
+
+def wgrad_cases():
+    bad = 0
+    for (B, C, O, N, bias) in [(2, 32, 16, 128, True), (3, 64, 256, 384, True), (3, 3, 5, 77, True), (2, 67, 300, 130, False),
+                               (4, 255, 40, 515, True), (2, 256, 128, 1000, False), (64, 64, 4, 3072, True), (1, 8, 8, 4, True)]:
+        x = torch.randn(B, C, N, device=dev); g = torch.randn(B, O, N, device=dev)
+        gw, gb = fused._pointwise_wgrad_raw(g, x, bias)
+        ref = torch.einsum("bon,bcn->oc", g.double(), x.double())
+        e1 = float((gw.double() - ref).abs().max() / ref.abs().max())
+        e2 = float((gb.double() - g.double().sum((0, 2))).abs().max() / g.double().sum((0, 2)).abs().max()) if bias else 0.0
+        ok = e1 < 3e-3 and e2 < 3e-3
+        bad += not ok
+        print("wgrad", (B, C, O, N, bias), "gw err %.2e gb err %.2e" % (e1, e2), "OK" if ok else "BAD", flush=True)
+    return bad
 
 
 def bias_pieces():
@@ -119,7 +136,7 @@ def autograd_cases():
 if __name__ == "__main__":
     b1 = onehot()
     b2 = rand_cases()
-    b3 = bias_pieces()
+    b3 = bias_pieces() + wgrad_cases()
     b4 = autograd_cases()
     print("BAD one-hot %d, random %d, bias %d, autograd %d" % (b1, b2, b3, b4))
     if "--time" in sys.argv and b1 + b2 == 0:

@@ -56,6 +56,8 @@ if on("pointwise"):
     # (512 -> 512), and the bias kernels of the wide layers
     for (b, c, o, n) in ((64, 64, 256, 3072), (64, 256, 64, 3072), (64, 128, 256, 2048), (64, 512, 512, 384)):
         fused._pointwise_conv_raw(N(b, c, n), N(o, c), N(o))
+    fused._pointwise_wgrad_raw(N(64, 256, 3072), N(64, 64, 3072), True)
+    fused._pointwise_wgrad_raw(N(64, 16, 3072), N(64, 64, 3072), True)
     y = N(64, 1024, 2048)
     fused.bias_add_(y, N(1024))
     fused.channel_sum(y)
