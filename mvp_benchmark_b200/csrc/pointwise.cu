@@ -658,7 +658,16 @@ __global__ void pointwise_wgrad_reduce_kernel(int cin, int cout, int nb, int G, 
   if (c >= cin + ones) return;
   const float *p = partial + ((size_t)(o >> 7) * G * 128 + (o & 127)) * nb + c;
   float t = 0.f;
-  for (int i = 0; i < G; i++) t += p[(size_t)i * 128 * nb];
+  const size_t stride = (size_t)128 * nb;
+  int i = 0;
+  for (; i + 8 <= G; i += 8) {  // eight loads in flight, added in order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = __ldg(p + (size_t)(i + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; u++) t += v[u];
+  }
+  for (; i < G; i++) t += __ldg(p + (size_t)i * stride);
   if (c < cin) gw[(size_t)o * cin + c] = t;
   else if (gb) gb[o] = t;
 }
