@@ -99,5 +99,17 @@ fused.gather_max(ff, torch.randint(0, 1536, (2, 700, 10), device=dev, generator=
 yy = torch.randn(2, 16, 768, device=dev, generator=g).requires_grad_(True)
 ww = torch.randn(2, 2, 10, 768, device=dev, generator=g).requires_grad_(True)
 fused.neighbor_weighted_sum(yy, torch.randint(0, 768, (2, 768, 10), device=dev, generator=g, dtype=torch.int32), ww).sum().backward()
+# the 1x1 layers (csrc/pointwise.cu): resident-weight and streaming tcgen05 kernels, masked input gradient, weight + bias
+# gradient, bias kernels; sizes off every multiple
+for (b_, c_, o_, n_) in ((2, 64, 256, 300), (2, 67, 20, 130), (1, 600, 300, 77), (2, 3, 5, 129)):
+    px = torch.randn(b_, c_, n_, device=dev, generator=g).requires_grad_(True)
+    pw = torch.randn(o_, c_, 1, device=dev, generator=g).requires_grad_(True)
+    pb = torch.randn(o_, device=dev, generator=g).requires_grad_(True)
+    fused.pointwise_conv(px, pw, pb, relu=True).sum().backward()
+    fused._pointwise_wgrad_raw(torch.randn(b_, o_, n_, device=dev, generator=g), px.detach(), c_ < 256) if c_ <= 256 else None
+cx = torch.randn(2, 40, 515, device=dev, generator=g).requires_grad_(True)
+cw = torch.randn(24, 40, 1, device=dev, generator=g).requires_grad_(True)
+cb = torch.randn(24, device=dev, generator=g).requires_grad_(True)
+fused.conv_bias(cx, cw, cb).sum().backward()
 torch.cuda.synchronize()
 print("sanitize_ops: all entry points ran,", _lib.launch_count(), "kernels launched")
