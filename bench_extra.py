@@ -419,6 +419,11 @@ def run(dev, hbm_gbs=None):
                 "the bias gradient of a wide 1x1 layer (torch.sum over clouds and points)")
     out["channel_sum_64x1024x2048"]["algorithmic_GBps"] = 4.0 * by.numel() / out["channel_sum_64x1024x2048"]["ours_ms"] / 1e6
     del by
+    mx = torch.randn(32, 96, 3072, 16, device=dev, generator=g)
+    fused_entry("max_last_32x96x3072x16", lambda: fused.max_last(mx), lambda: torch.max(mx, 3),
+                "torch.max over the k neighbours (ecg.py:64)")
+    out["max_last_32x96x3072x16"]["algorithmic_GBps"] = 4.0 * mx.numel() / out["max_last_32x96x3072x16"]["ours_ms"] / 1e6
+    del mx
     out["vrcnet_step_operator_census"] = vrcnet_census(dev, g, have_ref)
     steps = model_steps()
     if steps is not None:

@@ -255,6 +255,14 @@ size_t mvp_channel_sum_workspace_bytes(int b, int c);
 int mvp_channel_sum(int b, int c, int n, const float *g, float *out, void *workspace, size_t workspace_bytes,
                     mvp_stream_t stream);
 
+/* The maximum over a point's k neighbours — the last axis of a contiguous (rows, k) fp32 view, k <= 255: what
+ * `y, _ = torch.max(y, 3)` computes on the (B, C, N, k) neighbour tensors of completion/models/ecg.py:64 and
+ * completion/model_utils.py:53,104.  out (rows), arg (rows) uint8 = the first position of the maximum (a NaN wins, the
+ * first one, as in torch).  mvp_max_last_grad: grad_x (rows, k) = grad_out at arg, zero elsewhere, fully written. */
+int mvp_max_last(long long rows, int k, const float *x, float *out, unsigned char *arg, mvp_stream_t stream);
+int mvp_max_last_grad(long long rows, int k, const float *grad_out, const unsigned char *arg, float *grad_x,
+                      mvp_stream_t stream);
+
 /* The k <= 32 largest entries of every row of a (rows, cols) fp32 score matrix, descending, equal scores in ascending
  * column order — what completion/model_utils.py:242-247 asks torch.topk for on its (B, N, N) matrix of negative
  * feature-space distances.  Any of values (rows,k) / idx64 (rows,k) int64 / idx32 (rows,k) int32 may be NULL. */

@@ -203,7 +203,8 @@ def _pointwise_wgrad_raw(g3, x3, with_bias):
     return gw, gb
 
 
-kWgradMinIn, kWgradMinOut = 96, 128  # layers whose weight gradient goes through mvp_pointwise_wgrad
+kWgradMinIn, kWgradMinOut = 96, 128  # layers whose weight gradient goes through mvp_pointwise_wgrad ...
+kWgradMinPositions = 400000          # ... or any layer over at least this many positions (B x N)
 kPointwiseBmmWgrad = 8192  # in x out channels up to which the weight gradient is a batched fp32 matmul (see model_patches)
 
 
@@ -239,9 +240,11 @@ class _PointwiseConv(torch.autograd.Function):
         if y3 is not None and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
             g3 = g3 * (y3 > 0)
         want_w, want_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
-        if want_w and kWgradMinIn <= C and C + (1 if want_b else 0) <= 256 and O >= kWgradMinOut and B * N > 0:
+        if want_w and C + (1 if want_b else 0) <= 256 and B * N > 0 and (
+                (kWgradMinIn <= C and O >= kWgradMinOut) or B * N >= kWgradMinPositions):
             # both gradients from one pass over g and x (tcgen05); measured to pay for 128 -> 256 channels (0.098 ms against
-            # cuDNN's 0.144 + the bias sum), not for 64 -> 256 (0.116 against 0.053 + 0.044) nor for the thin layers
+            # cuDNN's 0.144 + the bias sum) and for layers over very many positions (ECG's 48 -> 24 over 32 x 49 152: the
+            # batched fp32 matmul takes 1.2 ms), not for 64 -> 256 over 64 x 3072 (0.116 against 0.053 + 0.044)
             gw, gb = _pointwise_wgrad_raw(g3, x3, want_b)
             gw = gw.reshape(wshape) if want_w else None
             return gx, gw, gb, None
@@ -333,6 +336,44 @@ def pointwise_conv(x, weight, bias=None, relu=False):
     in the epilogue.  x (B, C, ...), weight (O, C[, 1[, 1]]), bias (O) or None -> (B, O, ...).  The input gradient runs
     through the same kernel (weight transposed); the weight gradient is a library matmul / cuDNN call."""
     return _PointwiseConv.apply(x, weight, bias, relu)
+
+
+class _MaxLast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x_ = x.contiguous()
+        dev = _lib.require_cuda(x_, dtype=torch.float32, what="max_last")
+        k = x_.shape[-1]
+        rows = x_.numel() // max(1, k)
+        out = torch.empty(x_.shape[:-1], device=dev, dtype=torch.float32)
+        arg = torch.empty(x_.shape[:-1], device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.mvp_max_last(rows, k, _lib.ptr(x_), _lib.ptr(out), _lib.ptr(arg), _lib.stream_of(x_)),
+                       "mvp_max_last")
+        ctx.save_for_backward(arg)
+        ctx.k = k
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (arg,) = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty(*arg.shape, ctx.k, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib.mvp_max_last_grad(arg.numel(), ctx.k, _lib.ptr(g), _lib.ptr(arg), _lib.ptr(gx),
+                                                  _lib.stream_of(g)), "mvp_max_last_grad")
+        return gx
+
+
+def max_last(x):
+    """(values, arg) of the maximum over the LAST axis of x (..., k), k <= 255 — `torch.max(x, -1)` on the (B, C, N, k)
+    neighbour tensors of the completion models (ecg.py:64, model_utils.py:53,104) as one bandwidth-bound launch; arg is
+    uint8, the first position of the maximum; the gradient goes there."""
+    if x.shape[-1] > 255 or x.shape[-1] == 0:
+        v, i = torch.max(x, -1)
+        return v, i
+    return _MaxLast.apply(x)
 
 
 def topk_rows(scores, k):

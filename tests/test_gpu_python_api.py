@@ -630,6 +630,32 @@ def test_pointwise_wgrad_tensor_core(cuda, B, C, O, N, bias):
         assert gb is None
 
 
+@pytest.mark.parametrize("shape", [(4, 24, 700, 16), (3, 5, 77, 20), (2, 9, 31), (5, 1), (2, 3, 50, 7), (0, 4, 8)])
+def test_max_last_vs_torch(cuda, shape):
+    """fused.max_last (mvp_max_last / _grad) against torch.max(x, -1): values bit-identical, the FIRST position of the
+    maximum among equals (torch's choice, which routes the gradient), NaN wins (the first one), gradient identical."""
+    from mvp_benchmark_b200 import fused
+    g = torch.Generator(device=cuda).manual_seed(len(shape) * 31 + shape[-1])
+    x = (torch.round(torch.randn(*shape, device=cuda, generator=g) * 2) / 2).requires_grad_(True)   # many exact ties
+    v, a = fused.max_last(x)
+    wv, wi = torch.max(x.detach(), -1)
+    assert v.shape == wv.shape and torch.equal(v, wv)
+    if x.numel():
+        first = (x.detach() == wv.unsqueeze(-1)).float().argmax(-1)
+        assert torch.equal(a.long(), first)
+    go = torch.randn(*shape[:-1], device=cuda, generator=g)
+    v.backward(go)
+    want = torch.zeros_like(x).scatter_(-1, a.long().unsqueeze(-1), go.unsqueeze(-1)) if x.numel() else torch.zeros_like(x)
+    assert torch.equal(x.grad, want)
+    if x.numel() > 8:
+        y = x.detach().clone()
+        y.view(-1)[3] = float("nan")
+        v2, a2 = fused.max_last(y)
+        wv2, _ = torch.max(y, -1)
+        assert torch.equal(torch.isnan(v2), torch.isnan(wv2)) and torch.equal(torch.nan_to_num(v2), torch.nan_to_num(wv2))
+        assert int(a2.view(-1)[3 // shape[-1]]) == 3 % shape[-1]
+
+
 @pytest.mark.parametrize("B,C,N", [(8, 1024, 2048), (3, 5, 77), (64, 4, 3072), (2, 1000, 6), (7, 33, 1)])
 def test_bias_add_and_channel_sum(cuda, B, C, N):
     """mvp_bias_add: bit-identical to torch's broadcasting add (one IEEE add per element); mvp_channel_sum: the

@@ -107,6 +107,9 @@ for (b_, c_, o_, n_) in ((2, 64, 256, 300), (2, 67, 20, 130), (1, 600, 300, 77),
     pb = torch.randn(o_, device=dev, generator=g).requires_grad_(True)
     fused.pointwise_conv(px, pw, pb, relu=True).sum().backward()
     fused._pointwise_wgrad_raw(torch.randn(b_, o_, n_, device=dev, generator=g), px.detach(), c_ < 256) if c_ <= 256 else None
+mxl = torch.randn(2, 5, 77, 20, device=dev, generator=g).requires_grad_(True)
+fused.max_last(mxl)[0].sum().backward()
+fused.max_last(torch.randn(3, 50, 7, device=dev, generator=g))
 cx = torch.randn(2, 40, 515, device=dev, generator=g).requires_grad_(True)
 cw = torch.randn(24, 40, 1, device=dev, generator=g).requires_grad_(True)
 cb = torch.randn(24, device=dev, generator=g).requires_grad_(True)
