@@ -316,3 +316,32 @@ def chamfer_loss(dist1, dist2):
     if lib().oracle_chamfer_loss(b, n, m, _fp(d1), _fp(d2), _fp(cd_p), _fp(cd_t)) != 0:
         raise ValueError("oracle_chamfer_loss: n, m > 0 required")
     return cd_p, cd_t
+
+
+def pointwise_conv(x, weight, bias=None, relu=False):
+    """A 1x1 convolution as the completion models' nn.Conv1d / nn.Conv2d(kernel_size=1) layers compute it
+    (completion/models/vrcnet.py:26-38,68,161-164,197-207; ecg.py:46; pcn.py encoder): x (B, C, N), weight (O, C),
+    bias (O) or None -> (B, O, N); products and sums in float64, rounded once to fp32 (the exact contraction: a fp32 or
+    TF32 kernel is compared with a tolerance, small-integer operands exactly)."""
+    y = np.einsum("oc,bcn->bon", np.asarray(weight, np.float64), np.asarray(x, np.float64))
+    if bias is not None:
+        y = y + np.asarray(bias, np.float64)[None, :, None]
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y.astype(np.float32)
+
+
+def pointwise_conv_grads(x, weight, grad_out):
+    """The same layer's gradients: (grad_x (B, C, N), grad_w (O, C), grad_bias (O)), float64 sums rounded once."""
+    g, w, x64 = np.asarray(grad_out, np.float64), np.asarray(weight, np.float64), np.asarray(x, np.float64)
+    return (np.einsum("oc,bon->bcn", w, g).astype(np.float32), np.einsum("bon,bcn->oc", g, x64).astype(np.float32),
+            g.sum((0, 2)).astype(np.float32))
+
+
+def max_last(x):
+    """`torch.max(x, -1)` as completion/models/ecg.py:64 and completion/model_utils.py:53,104 use it: (values, the FIRST
+    position of the maximum), a NaN winning over any number (the first NaN)."""
+    a = np.asarray(x, np.float32)
+    nan = np.isnan(a)
+    arg = np.where(nan.any(-1), nan.argmax(-1), np.where(nan, -np.inf, a).argmax(-1))
+    return np.take_along_axis(a, arg[..., None], -1)[..., 0], arg.astype(np.int64)

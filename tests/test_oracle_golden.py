@@ -105,3 +105,33 @@ def test_oracle_chamfer_loss_vs_reference_calc_cd(case):
     cd_p, cd_t = oracle.chamfer_loss(G[case + "_dist1"], G[case + "_dist2"])
     np.testing.assert_allclose(cd_p, G[case + "_cd_p"], rtol=1e-5, atol=0)
     np.testing.assert_allclose(cd_t, G[case + "_cd_t"], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("B,C,O,N", [(2, 3, 5, 7), (3, 16, 8, 33), (1, 67, 30, 12)])
+def test_oracle_pointwise_conv_vs_torch_layers(B, C, O, N):
+    """oracle.pointwise_conv / _grads against what the reference's models call — torch's own nn.Conv1d(kernel_size=1)
+    forward and autograd on the CPU (fp32): 1e-5 relative, north_star's floating-point bar; max_last against torch.max
+    (values and index identical, ties and NaN included)."""
+    import oracle
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(B * 100 + C)
+    x = rng.standard_normal((B, C, N)).astype(np.float32)
+    w = rng.standard_normal((O, C)).astype(np.float32)
+    bs = rng.standard_normal(O).astype(np.float32)
+    g = rng.standard_normal((B, O, N)).astype(np.float32)
+    tx, tw, tb = (torch.from_numpy(a).requires_grad_(True) for a in (x, w[:, :, None].copy(), bs))
+    ty = F.conv1d(tx, tw, tb)
+    ty.backward(torch.from_numpy(g))
+    np.testing.assert_allclose(oracle.pointwise_conv(x, w, bs), ty.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(oracle.pointwise_conv(x, w, bs, relu=True), F.relu(ty).detach().numpy(), rtol=1e-5, atol=1e-5)
+    gx, gw, gb = oracle.pointwise_conv_grads(x, w, g)
+    np.testing.assert_allclose(gx, tx.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(gw, tw.grad.numpy()[:, :, 0], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(gb, tb.grad.numpy(), rtol=1e-5, atol=1e-4)
+    q = np.round(x * 2) / 2
+    q[0, 0, 1] = np.nan
+    v, a = oracle.max_last(q)
+    tv, ta = torch.max(torch.from_numpy(q), -1)
+    np.testing.assert_array_equal(v, tv.numpy())
+    np.testing.assert_array_equal(a, ta.numpy())
