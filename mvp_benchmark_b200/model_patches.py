@@ -70,6 +70,22 @@ def get_edge_features(x, idx):
     return mm3d_pn2.grouping_operation(x.squeeze(2).contiguous(), idx.transpose(1, 2).int().contiguous())
 
 
+def get_graph_feature(x, k=20, minus_center=True):
+    """model_utils.py:156-178: x (B, C, N) -> (B, 2C, N, k): every point's features next to (its k nearest neighbours'
+    features minus its own).  The original gathers rows of the transposed x with advanced indexing
+    (`x.view(B * N, -1)[idx, :]`: an index kernel forward, a sort + index_put backward), concatenates on the LAST axis
+    and returns a permuted, non-contiguous view that the next convolution copies.  Here: the same neighbours by ONE
+    grouping_operation call (the reference's own operator; its scatter is the backward), the subtraction and the
+    concatenation channel-first and contiguous.  Same values bit for bit in the forward pass."""
+    if not (x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and k <= x.size(2)):
+        return _ORIGINAL["get_graph_feature"](x, k, minus_center)
+    import mm3d_pn2
+    idx = knn(x, k)                                                           # (B, N, k) int64
+    feature = mm3d_pn2.grouping_operation(x.contiguous(), idx.int().contiguous())   # (B, C, N, k)
+    centre = x.unsqueeze(3).expand(-1, -1, -1, k)
+    return torch.cat((centre, feature - centre if minus_center else feature), dim=1)
+
+
 def three_nn_upsampling(target_points, source_points):
     """model_utils.py:286-293: (idx, weight) for three_interpolate — three_nn plus five torch kernels of glue as the
     grid search plus one elementwise kernel (fused.three_nn_weights).  Same values."""
@@ -260,15 +276,17 @@ def calc_cd(output, gt, calc_f1=False):
 
 
 def apply(*modules):
-    """Rebind knn / knn_point / knn_point_all / get_edge_features / calc_cd / three_nn_upsampling /
-    edge_preserve_sampling / get_uniform_loss in the given (already imported) modules.
+    """Rebind knn / knn_point / knn_point_all / get_edge_features / get_graph_feature / calc_cd / three_nn_upsampling /
+    edge_preserve_sampling / get_uniform_loss in the given (already imported) modules (and SA_module.forward,
+    Dense_conv.forward where the module defines those classes).
     Returns the number of names replaced."""
     from . import install
     install()  # `mm3d_pn2` must resolve to this repository's package
     count = 0
     for mod in modules:
         for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
-                         ("get_edge_features", get_edge_features), ("calc_cd", calc_cd),
+                         ("get_edge_features", get_edge_features), ("get_graph_feature", get_graph_feature),
+                         ("calc_cd", calc_cd),
                          ("three_nn_upsampling", three_nn_upsampling),
                          ("edge_preserve_sampling", edge_preserve_sampling), ("get_uniform_loss", get_uniform_loss)):
             cur = getattr(mod, name, None)

@@ -263,6 +263,40 @@ def test_model_patches_get_edge_features(cuda):
     torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("minus_center", [True, False])
+def test_model_patches_get_graph_feature(cuda, minus_center):
+    """ECG's / EF_expansion's neighbour-feature builder (model_utils.py:156-178) through one grouping_operation: the
+    same (B, 2C, N, k) values bit for bit (given the same neighbours), contiguous, gradients equal up to summation order."""
+    import types
+    from mvp_benchmark_b200 import model_patches as mp
+
+    def knn(x, k):                                         # model_utils.py:242-247, restated
+        inner = -2 * torch.matmul(x.transpose(2, 1).contiguous(), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        return (-xx - inner - xx.transpose(2, 1).contiguous()).topk(k=k, dim=-1)[1]
+
+    def original(x, k=20, minus_center=True):              # model_utils.py:156-178, restated
+        idx = knn(x, k=k)
+        batch_size, num_points, _ = idx.size()
+        idx = (idx + torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points).view(-1)
+        _, num_dims, _ = x.size()
+        x = x.transpose(2, 1).contiguous()
+        feature = x.view(batch_size * num_points, -1)[idx, :].view(batch_size, num_points, k, num_dims)
+        x = x.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)
+        return torch.cat((x, feature - x if minus_center else feature), dim=3).permute(0, 3, 1, 2)
+
+    fake = types.SimpleNamespace(get_graph_feature=original, knn=knn)
+    assert mp.apply(fake) == 2
+    B, C, N, k = 3, 24, 700, 16
+    x0 = torch.randn(B, C, N, device=cuda)
+    a, b = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    got, want = fake.get_graph_feature(a, k, minus_center), original(b, k, minus_center)
+    assert got.shape == (B, 2 * C, N, k) and got.is_contiguous() and torch.equal(got, want)
+    g = torch.randn_like(got)
+    got.backward(g), want.backward(g)
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("b,n,m", [(64, 2048, 1024), (3, 16384, 16384), (5, 7, 3), (2, 1000, 1)])
 def test_chamfer_loss_epilogue(cuda, cpu, b, n, m):
     """fused.chamfer_loss against the oracle and against the torch formula of
