@@ -269,6 +269,13 @@ int mvp_max_last_grad(long long rows, int k, const float *grad_out, const unsign
 int mvp_topk_rows(long long rows, int cols, int k, const float *scores, float *values, long long *idx64, int *idx32,
                   mvp_stream_t stream);
 
+/* The same selection on the feature-space kNN score of completion/model_utils.py:242-247 WITHOUT its (B, N, N) score
+ * matrix: gram (b,n,n) = x^T x (the original's torch.matmul), sqnorm (b,n) = sum_c x^2 (its torch.sum); the ranked
+ * value of row i, column j is  (-sqnorm[j] - (-2 * gram[i,j])) - sqnorm[i], computed with the IEEE operations torch's
+ * three elementwise kernels perform, in their order: identical values and indices. */
+int mvp_topk_rows_sqdist(int b, int n, int k, const float *gram, const float *sqnorm, float *values, long long *idx64,
+                         int *idx32, mvp_stream_t stream);
+
 /* furthest_point_sample followed by gather_points on the transposed cloud (completion/model_utils.py:91-93,
  * completion/models/vrcnet.py:451) as ONE launch: idx (b,m) as mvp_furthest_point_sampling, and the sampled points
  * themselves, (b,m,3) or — channels_first != 0 — (b,3,m), the layout gather_points returns. */

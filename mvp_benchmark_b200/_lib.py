@@ -68,6 +68,7 @@ def _load():
         "mvp_pointwise_conv_masked": (_c_int, [_c_int] * 4 + [_p] * 4 + [_p]),
         "mvp_pointwise_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 3),
         "mvp_pointwise_wgrad": (_c_int, [_c_int] * 4 + [_p] * 5 + [_c_size_t, _p]),
+        "mvp_topk_rows_sqdist": (_c_int, [_c_int] * 3 + [_p] * 5 + [_p]),
         "mvp_max_last": (_c_int, [ctypes.c_longlong, _c_int] + [_p] * 3 + [_p]),
         "mvp_max_last_grad": (_c_int, [ctypes.c_longlong, _c_int] + [_p] * 3 + [_p]),
         "mvp_bias_add": (_c_int, [_c_int] * 3 + [_p] * 2 + [_c_int, _p]),

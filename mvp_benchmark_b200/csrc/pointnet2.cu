@@ -242,15 +242,26 @@ knn_warp_kernel(int n, int m, int nsample, int done, int kk, const float *__rest
 // values and indices in DESCENDING value, equal values in ascending index (torch.topk leaves that order
 // unspecified); NaN scores are never selected.
 // ------------------------------------------------------------------------------------------------
+// kScore: `scores` is the Gram matrix x^T x of a cloud's feature vectors ((B, N, N), rows = B * N, cols = N) and the
+// ranked score is the original's  -|x_j|^2 - (-2 x_i.x_j) - |x_i|^2  (completion/model_utils.py:243-245), each step the
+// IEEE operation torch performs in its three elementwise kernels (x -2 is exact; two subtractions in that order): the
+// (B, N, N) score matrix is never written or re-read.
 constexpr int kTopkWarps = 8;
+template <bool kScore>
 __global__ void __launch_bounds__(kTopkWarps * 32)
-topk_rows_kernel(long long rows, int cols, int k, const float *__restrict__ scores, float *__restrict__ vals,
-                 long long *__restrict__ idx64, int *__restrict__ idx32) {
+topk_rows_kernel(long long rows, int cols, int k, const float *__restrict__ scores, const float *__restrict__ sqnorm,
+                 float *__restrict__ vals, long long *__restrict__ idx64, int *__restrict__ idx32) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)kTopkWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float *r = scores + row * cols;
+  const float *nb = nullptr;  // the cloud's squared norms
+  float own = 0.f;
+  if (kScore) {
+    nb = sqnorm + (row / cols) * cols;
+    own = __ldg(nb + (row % cols));
+  }
   const float ninf = __int_as_float(0xff800000);
   float lv = ninf, thr_v = ninf;  // this lane's entry; the k-th entry
   int li = 0x7fffffff, thr_i = 0x7fffffff;
@@ -262,6 +273,7 @@ topk_rows_kernel(long long rows, int cols, int k, const float *__restrict__ scor
     for (int u = 0; u < 4; u++) {
       const int j = t0 + 32 * u + lane;
       v4[u] = j < cols ? __ldg(r + j) : ninf;
+      if (kScore && j < cols) v4[u] = __fsub_rn(__fsub_rn(-__ldg(nb + j), __fmul_rn(-2.f, v4[u])), own);
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -583,8 +595,21 @@ MVP_API int mvp_topk_rows(long long rows, int cols, int k, const float *scores, 
   if (!scores || (!values && !idx64 && !idx32)) return MVP_ERR_INVALID_ARGUMENT;
   const long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
   if (blocks > 0x7fffffffLL) return MVP_ERR_INVALID_ARGUMENT;
-  topk_rows_kernel<<<(unsigned)blocks, kTopkWarps * 32, 0, (cudaStream_t)stream>>>(rows, cols, k, scores, values, idx64,
-                                                                                    idx32);
+  topk_rows_kernel<false><<<(unsigned)blocks, kTopkWarps * 32, 0, (cudaStream_t)stream>>>(rows, cols, k, scores, nullptr,
+                                                                                           values, idx64, idx32);
+  count_launch();
+  return launch_status();
+}
+
+MVP_API int mvp_topk_rows_sqdist(int b, int n, int k, const float *gram, const float *sqnorm, float *values,
+                                 long long *idx64, int *idx32, mvp_stream_t stream) {
+  if (b < 0 || n <= 0 || k <= 0 || k > 32 || k > n) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0) return MVP_OK;
+  if (!gram || !sqnorm || (!values && !idx64 && !idx32)) return MVP_ERR_INVALID_ARGUMENT;
+  const long long rows = (long long)b * n, blocks = (rows + kTopkWarps - 1) / kTopkWarps;
+  if (blocks > 0x7fffffffLL) return MVP_ERR_INVALID_ARGUMENT;
+  topk_rows_kernel<true><<<(unsigned)blocks, kTopkWarps * 32, 0, (cudaStream_t)stream>>>(rows, n, k, gram, sqnorm, values,
+                                                                                          idx64, idx32);
   count_launch();
   return launch_status();
 }

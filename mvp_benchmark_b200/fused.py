@@ -393,6 +393,24 @@ def topk_rows(scores, k):
     return vals, idx
 
 
+def topk_rows_sqdist(gram, sqnorm, k):
+    """The feature-space kNN of completion/model_utils.py:242-247 from its two reductions, without its (B, N, N) score
+    matrix: gram (B, N, N) = torch.matmul(x^T, x), sqnorm (B, N) = torch.sum(x ** 2, dim=1) -> (values, indices int64)
+    of the k largest  -sqnorm[j] - (-2 gram[i, j]) - sqnorm[i]  per row — identical to
+    topk_rows(-xx - (-2 * gram) - xx^T, k): the kernel performs torch's IEEE operations in torch's order on the fly."""
+    g_, n_ = gram.detach().contiguous(), sqnorm.detach().contiguous()
+    dev = _lib.require_cuda(g_, n_, dtype=torch.float32, what="topk_rows_sqdist")
+    if g_.dim() != 3 or g_.shape[1] != g_.shape[2] or n_.shape != g_.shape[:2]:
+        raise _lib.MvpOpsError("topk_rows_sqdist: gram must be (B, N, N) and sqnorm (B, N)")
+    B, N = n_.shape
+    vals = torch.empty(B, N, k, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, N, k, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.mvp_topk_rows_sqdist(B, N, int(k), _lib.ptr(g_), _lib.ptr(n_), _lib.ptr(vals), _lib.ptr(idx), None,
+                                                 _lib.stream_of(g_)), "mvp_topk_rows_sqdist")
+    return vals, idx
+
+
 class _GatherMax(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, idx):

@@ -34,11 +34,12 @@ def _neg_sqdist(queries, cloud, idx):
 def knn(x, k):
     """model_utils.py:242-247: x (B, C, N) -> idx (B, N, k) int64 of the k nearest points (self included)."""
     if x.dim() == 3 and x.size(1) != 3 and x.is_cuda and x.dtype == torch.float32 and k <= min(x.size(2), 32):
-        # feature-space neighbours (ECG's / EF_expansion's dynamic graph): the original's score matrix, its top-k by
-        # one warp per row (fused.topk_rows) instead of torch.topk's multi-block radix select
-        inner = -2 * torch.matmul(x.transpose(2, 1).contiguous(), x)
-        xx = torch.sum(x ** 2, dim=1, keepdim=True)
-        return fused.topk_rows(-xx - inner - xx.transpose(2, 1).contiguous(), k)[1]
+        # feature-space neighbours (ECG's / EF_expansion's dynamic graph): the original's matmul and squared norms; its
+        # three elementwise kernels over the (B, N, N) matrix (x -2, two broadcast subtractions: 2 ms at N = 3072) and
+        # torch.topk's multi-block radix select are ONE pass of one warp per row over the Gram matrix
+        # (fused.topk_rows_sqdist: the same IEEE operations in the same order, so the same neighbours)
+        gram = torch.matmul(x.transpose(2, 1).contiguous(), x)
+        return fused.topk_rows_sqdist(gram, torch.sum(x ** 2, dim=1), k)[1]
     if x.dim() != 3 or x.size(1) != 3 or not x.is_cuda or x.dtype != torch.float32 or k > min(x.size(2), 64):
         return _ORIGINAL["knn"](x, k)
     _, idx = fused.knn_points(k, x.transpose(1, 2))

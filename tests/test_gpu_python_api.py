@@ -560,6 +560,28 @@ def test_model_patches_pointwise_convs(cuda):
 
 
 
+@pytest.mark.parametrize("B,C,N,k", [(3, 24, 700, 16), (2, 5, 33, 32), (1, 96, 2048, 20), (2, 8, 129, 1)])
+def test_topk_rows_sqdist_is_the_original_formula(cuda, B, C, N, k):
+    """fused.topk_rows_sqdist (mvp_topk_rows_sqdist) against topk_rows / torch.topk on the score matrix the original
+    builds (completion/model_utils.py:243-245): the on-the-fly score is torch's, bit for bit, so values and indices are
+    identical — including on a lattice of features, where exact ties abound."""
+    from mvp_benchmark_b200 import fused
+    g = torch.Generator(device=cuda).manual_seed(N + k)
+    for lattice in (False, True):
+        x = torch.randn(B, C, N, device=cuda, generator=g)
+        if lattice:
+            x = torch.round(x)
+        inner = -2 * torch.matmul(x.transpose(2, 1).contiguous(), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        score = -xx - inner - xx.transpose(2, 1).contiguous()
+        wv, wi = fused.topk_rows(score, k)
+        v, i = fused.topk_rows_sqdist(torch.matmul(x.transpose(2, 1).contiguous(), x), torch.sum(x ** 2, dim=1), k)
+        assert torch.equal(v, wv) and torch.equal(i, wi)
+        if not lattice:
+            tv, ti = score.topk(k, dim=-1)
+            assert torch.equal(v, tv)
+
+
 def _tf32(t):
     """round to nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32 does"""
     i = t.contiguous().view(torch.int32)
