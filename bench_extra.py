@@ -387,6 +387,14 @@ def run(dev, hbm_gbs=None):
     sc = torch.randn(32, 2048, 2048, device=dev, generator=g)
     fused_entry("topk_rows_32x2048x2048_k16", lambda: fused.topk_rows(sc, 16), lambda: sc.topk(16, dim=-1),
                 "torch.topk on the feature-space score matrix (model_utils.py:246)")
+    fx = torch.randn(32, 24, 3072, device=dev, generator=g)
+
+    def knn_original():
+        inner = -2 * torch.matmul(fx.transpose(2, 1).contiguous(), fx)
+        xx = torch.sum(fx ** 2, dim=1, keepdim=True)
+        return (-xx - inner - xx.transpose(2, 1).contiguous()).topk(k=16, dim=-1)[1]
+    fused_entry("feature_knn_32x24x3072_k16", lambda: fused.topk_rows_sqdist(torch.matmul(fx.transpose(2, 1).contiguous(), fx), torch.sum(fx ** 2, dim=1), 16),
+                knn_original, "knn on features: matmul + three elementwise passes + torch.topk (model_utils.py:242-247)")
     fp = R(64, 3072, 3)
     fused_entry("fps_gather_64x3072_to_1536", lambda: fused.fps_gather(fp, 1536),
                 lambda: mm.gather_points(fp.transpose(1, 2).contiguous(), mm.furthest_point_sample(fp, 1536)).transpose(1, 2).contiguous(),
