@@ -295,6 +295,40 @@ def channel_sum(g):
     return out
 
 
+class _AddPerCloud(torch.autograd.Function):
+    """y (B, C, N) + v (B, C) broadcast over the points (then ReLU if asked), IN PLACE on y: mvp_bias_add on the
+    (1, B C, N) view; the gradient of v is mvp_channel_sum on the same view."""
+
+    @staticmethod
+    def forward(ctx, y, v, relu):
+        if not y.is_contiguous():
+            raise _lib.MvpOpsError("add_per_cloud: y must be contiguous")
+        B, C = y.shape[0], y.shape[1]
+        bias_add_(y.view(1, B * C, -1), v.contiguous().view(-1), relu)
+        ctx.mark_dirty(y)
+        ctx.relu = relu
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if ctx.relu:
+            (y,) = ctx.saved_tensors
+            g = g * (y > 0)
+        B, C = g.shape[0], g.shape[1]
+        gv = channel_sum(g.view(1, B * C, -1)).view(B, C) if ctx.needs_input_grad[1] else None
+        return g, gv, None
+
+
+def add_per_cloud(y, v, relu=False):
+    """y (B, C, N) += v (B, C)[:, :, None] in place (then ReLU): a per-cloud bias — what a 1x1 convolution contributes
+    for input channels that are CONSTANT over the points (PCN's decoder concatenates the global feature to every
+    point, completion/models/pcn.py:62-70).  y must be a fresh intermediate (it is overwritten)."""
+    return _AddPerCloud.apply(y, v, relu)
+
+
 class _ConvBias(torch.autograd.Function):
     """A wide 1x1 layer: the contraction on the library's TF32 GEMM (cuDNN, as nn.Conv would run it) WITHOUT its bias,
     the bias added in place by mvp_bias_add and its gradient summed by mvp_channel_sum."""

@@ -36,7 +36,7 @@ def test_first_training_step_matches_the_reference_kernels(cuda, model):
 
 
 @pytest.mark.skipif(not os.path.isfile(STAGED), reason="reference models not staged")
-@pytest.mark.parametrize("model", ["vrcnet", "ecg"])
+@pytest.mark.parametrize("model", ["vrcnet", "ecg", "pcn"])
 def test_step_with_the_opt_in_patches(cuda, model):
     """Every opt-in patch of model_patches applied (tools/model_step.py --patch-knn): the step runs and the loss of the
     first training step stays that of the unpatched model to 1e-3 (near-tie differences of the neighbour ranking, fp32

@@ -582,6 +582,71 @@ def test_topk_rows_sqdist_is_the_original_formula(cuda, B, C, N, k):
             assert torch.equal(v, tv)
 
 
+def test_model_patches_pcn_decoder(cuda):
+    """PCN_decoder.forward (completion/models/pcn.py:48-71, restated) against model_patches.pcn_decoder_forward: the
+    global feature's share of conv1 as a per-cloud vector — same outputs and parameter gradients up to TF32 / summation
+    order; fused.add_per_cloud against the broadcasting add it stands for."""
+    import types
+    import torch.nn.functional as F
+    from torch import nn
+    from mvp_benchmark_b200 import fused, model_patches as mp
+
+    class PCN_decoder(nn.Module):
+        def __init__(self, num_coarse, num_fine, scale, cat_feature_num):
+            super().__init__()
+            self.num_coarse, self.num_fine, self.scale = num_coarse, num_fine, scale
+            self.fc1, self.fc2, self.fc3 = nn.Linear(1024, 1024), nn.Linear(1024, 1024), nn.Linear(1024, num_coarse * 3)
+            r = int(scale ** 0.5)
+            gx, gy = torch.meshgrid(torch.linspace(-0.05, 0.05, r), torch.linspace(-0.05, 0.05, r), indexing="ij")
+            self.grid = torch.stack((gx, gy), -1).view(-1, 2).transpose(0, 1).contiguous().cuda()
+            self.conv1, self.conv2, self.conv3 = nn.Conv1d(cat_feature_num, 512, 1), nn.Conv1d(512, 512, 1), nn.Conv1d(512, 3, 1)
+
+        def forward(self, x):
+            batch_size = x.size()[0]
+            coarse = F.relu(self.fc1(x))
+            coarse = F.relu(self.fc2(coarse))
+            coarse = self.fc3(coarse).view(-1, 3, self.num_coarse)
+            grid = self.grid.clone().detach()
+            grid_feat = grid.unsqueeze(0).repeat(batch_size, 1, self.num_coarse).contiguous().cuda()
+            point_feat = ((coarse.transpose(1, 2).contiguous()).unsqueeze(2).repeat(1, 1, self.scale, 1).view(
+                -1, self.num_fine, 3)).transpose(1, 2).contiguous()
+            global_feat = x.unsqueeze(2).repeat(1, 1, self.num_fine)
+            feat = torch.cat((grid_feat, point_feat, global_feat), 1)
+            center = ((coarse.transpose(1, 2).contiguous()).unsqueeze(2).repeat(1, 1, self.scale, 1).view(
+                -1, self.num_fine, 3)).transpose(1, 2).contiguous()
+            fine = self.conv3(F.relu(self.conv2(F.relu(self.conv1(feat))))) + center
+            return coarse, fine
+
+    torch.manual_seed(3)
+    dec = PCN_decoder(96, 96 * 4, 4, 1024 + 5).to(cuda)
+    x = torch.randn(3, 1024, device=cuda)
+    original = PCN_decoder.forward
+    c0, f0 = dec(x)
+    (f0.square().sum() + c0.sum()).backward()
+    ref = {n_: p.grad.clone() for n_, p in dec.named_parameters()}
+    dec.zero_grad()
+    fake = types.SimpleNamespace(PCN_decoder=PCN_decoder)
+    try:
+        assert mp.apply(fake) == 1 and PCN_decoder.forward is mp.pcn_decoder_forward
+        c1, f1 = dec(x)
+        (f1.square().sum() + c1.sum()).backward()
+    finally:
+        PCN_decoder.forward = original
+    assert torch.equal(c0, c1) and (f1 - f0).abs().max().item() <= 3e-3 * f0.abs().max().item()
+    for n_, p in dec.named_parameters():      # TF32 sums in another order, a few ReLU signs near zero: compare in norm
+        assert (p.grad - ref[n_]).norm().item() <= 2e-2 * max(ref[n_].norm().item(), 1e-6), n_
+    y = torch.randn(4, 7, 130, device=cuda)
+    v = torch.randn(4, 7, device=cuda)
+    a, b = y.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    out = fused.add_per_cloud(a * 1.0, b, relu=True)
+    want = F.relu(y + v[:, :, None])
+    assert torch.equal(out, want)
+    go = torch.randn_like(out)
+    out.backward(go)
+    assert torch.equal(a.grad, go * (want > 0))
+    assert (b.grad - (go * (want > 0)).sum(2)).abs().max().item() <= 1e-5 * go.abs().sum(2).max().item()
+
+
 def _tf32(t):
     """round to nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32 does"""
     i = t.contiguous().view(torch.int32)
