@@ -416,7 +416,7 @@ static int pointwise_launch(int b, int cin, int cout, int n, const float *x, con
                             const float *bias, int relu, float *y, cudaStream_t s) {
   if (b < 0 || cin <= 0 || cout <= 0 || n < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || n == 0) return MVP_OK;
-  if (b > 65535) return MVP_ERR_INVALID_ARGUMENT;
+  if (b > 65535 || !x || !w || !y) return MVP_ERR_INVALID_ARGUMENT;
   const int tiles_n = (cout + kPwMaxN - 1) / kPwMaxN;
   int nt = (cout + tiles_n - 1) / tiles_n;  // even split over the channel tiles
   nt = (nt + 15) & ~15;
@@ -743,12 +743,14 @@ MVP_API int mvp_pointwise_conv(int b, int cin, int cout, int n, const float *x, 
 
 MVP_API int mvp_pointwise_conv_masked(int b, int cin, int cout, int n, const float *x, const float *mask, const float *w,
                                       float *y, mvp_stream_t stream) {
+  if (!mask && b > 0 && n > 0) return MVP_ERR_INVALID_ARGUMENT;
   return mvp::pointwise_launch(b, cin, cout, n, x, mask, w, nullptr, 0, y, (cudaStream_t)stream);
 }
 
 MVP_API int mvp_bias_add(int b, int c, int n, float *y, const float *bias, int relu, mvp_stream_t stream) {
   if (b < 0 || c <= 0 || n < 0) return MVP_ERR_INVALID_ARGUMENT;
   if (b == 0 || n == 0) return MVP_OK;
+  if (!y || !bias || (unsigned long long)b * c > 0x7fffffffULL) return MVP_ERR_INVALID_ARGUMENT;
   mvp::bias_add_kernel<<<(unsigned)((size_t)b * c), 128, 0, (cudaStream_t)stream>>>(c, n, y, bias, relu);
   mvp::count_launch();
   return mvp::launch_status();
@@ -762,7 +764,7 @@ MVP_API size_t mvp_channel_sum_workspace_bytes(int b, int c) {
 
 MVP_API int mvp_channel_sum(int b, int c, int n, const float *g, float *out, void *workspace, size_t workspace_bytes,
                             mvp_stream_t stream) {
-  if (b <= 0 || c <= 0 || n <= 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b <= 0 || c <= 0 || n <= 0 || !g || !out) return MVP_ERR_INVALID_ARGUMENT;
   if (!workspace || workspace_bytes < mvp_channel_sum_workspace_bytes(b, c)) return MVP_ERR_WORKSPACE;
   const int splits = std::max(1, std::min(b, (4 * mvp::kNumSMs + c - 1) / c));
   cudaStream_t s = (cudaStream_t)stream;
@@ -789,7 +791,7 @@ MVP_API size_t mvp_pointwise_wgrad_workspace_bytes(int cin, int cout, int with_b
 MVP_API int mvp_pointwise_wgrad(int b, int cin, int cout, int n, const float *g, const float *x, float *grad_w, float *grad_bias,
                                 void *workspace, size_t workspace_bytes, mvp_stream_t stream) {
   const int with_bias = grad_bias != nullptr;
-  if (b <= 0 || cin <= 0 || cout <= 0 || n <= 0 || cin + with_bias > 256) return MVP_ERR_INVALID_ARGUMENT;
+  if (b <= 0 || cin <= 0 || cout <= 0 || n <= 0 || cin + with_bias > 256 || !g || !x || !grad_w) return MVP_ERR_INVALID_ARGUMENT;
   if (!workspace || workspace_bytes < mvp_pointwise_wgrad_workspace_bytes(cin, cout, with_bias)) return MVP_ERR_WORKSPACE;
   int nb, G, rt;
   wgrad_geometry(cin, cout, with_bias, &nb, &G, &rt);

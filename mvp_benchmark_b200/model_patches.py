@@ -216,7 +216,7 @@ def pcn_decoder_forward(self, x):
     Same function of the same parameters (state_dict unchanged); sums are taken in a different order."""
     import torch.nn.functional as F
     if not (x.is_cuda and x.dtype == torch.float32 and self.conv1.weight.shape[1] == x.shape[1] + 5):
-        return _ORIGINAL["PCN_decoder.forward"](self, x)
+        return type(self)._mvp_original_forward(self, x)
     batch_size = x.size()[0]
     coarse = F.relu(self.fc1(x))
     coarse = F.relu(self.fc2(coarse))
@@ -330,7 +330,7 @@ def apply(*modules):
             count += 1
         pd = getattr(mod, "PCN_decoder", None)  # models.pcn
         if isinstance(pd, type) and pd.forward is not pcn_decoder_forward:
-            _ORIGINAL.setdefault("PCN_decoder.forward", pd.forward)
+            pd._mvp_original_forward = pd.forward   # kept on the class: several modules may define a PCN_decoder
             pd.forward = pcn_decoder_forward
             count += 1
         cls = getattr(mod, "SA_module", None)  # models.vrcnet: the class's forward, not a module-level function

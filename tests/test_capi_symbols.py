@@ -64,3 +64,16 @@ def test_argument_validation_needs_no_gpu():
     assert L.mvp_chamfer_forward(-1, 8, 8, z, z, z, z, z, z, z, 0, z) == -1
     assert L.mvp_chamfer_forward(0, 8, 8, z, z, z, z, z, z, z, 0, z) == 0     # empty batch is a no-op
     assert L.mvp_gather_points(2, 0, 8, 8, z, z, z, z) == 0
+    # the 1x1-layer entries (csrc/pointwise.cu) and the neighbour max
+    assert L.mvp_pointwise_conv(1, 0, 8, 8, z, z, z, 0, z, z) == -1
+    assert L.mvp_pointwise_conv(1, 8, 8, 8, z, z, z, 0, z, z) == -1            # null operands
+    assert L.mvp_pointwise_conv(0, 8, 8, 8, z, z, z, 0, z, z) == 0             # empty batch
+    assert L.mvp_pointwise_conv_masked(1, 8, 8, 8, z, z, z, z, z) == -1
+    assert L.mvp_pointwise_wgrad(1, 256, 8, 8, z, z, z, ctypes.c_void_p(16), z, 0, z) == -1   # 256 channels + the ones row
+    assert L.mvp_pointwise_wgrad_workspace_bytes(64, 256, 1) == 2 * 74 * 128 * 80 * 4
+    assert L.mvp_pointwise_wgrad_workspace_bytes(300, 8, 0) == 0
+    assert L.mvp_bias_add(1, 0, 8, z, z, 0, z) == -1 and L.mvp_bias_add(0, 4, 8, z, z, 0, z) == 0
+    assert L.mvp_channel_sum(1, 4, 8, ctypes.c_void_p(16), ctypes.c_void_p(16), z, 0, z) == -5    # workspace missing
+    assert L.mvp_channel_sum_workspace_bytes(64, 1024) == 1024 * 4 and L.mvp_channel_sum_workspace_bytes(64, 4) == 4 * 64 * 4
+    assert L.mvp_max_last(4, 0, z, z, z, z) == -1 and L.mvp_max_last(4, 256, z, z, z, z) == -1 and L.mvp_max_last(0, 16, z, z, z, z) == 0
+    assert L.mvp_topk_rows_sqdist(1, 8, 9, z, z, z, z, z, z) == -1 and L.mvp_topk_rows_sqdist(0, 8, 4, z, z, z, z, z, z) == 0

@@ -103,3 +103,38 @@ def test_model_patches_fall_through_for_what_the_fused_ops_do_not_cover():
     assert fake.knn_point(5, torch.zeros(2, 50, 3), torch.zeros(2, 10, 3)) == ("orig-d", "orig-i")
     assert fake.get_edge_features(torch.zeros(2, 8, 1, 50), torch.zeros(2, 50, 4, dtype=torch.long)) == "orig-gef"
     assert [s[0] for s in seen] == ["knn", "knn", "knn_point", "gef"]
+
+
+def test_model_patches_layer_routes_fall_through_on_the_cpu():
+    """The class- and module-level patches of round 2 (1x1 layers, PCN decoder, ECG's Dense_conv / get_graph_feature):
+    on CPU tensors every one of them runs the ORIGINAL code — nothing of this repository computes on the CPU."""
+    import types
+    import torch
+    from torch import nn
+    from mvp_benchmark_b200 import model_patches as mp
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv1d(64, 256, 1), nn.ReLU(), nn.Conv1d(256, 4, 1), nn.Conv2d(4, 4, 3, padding=1) if False else nn.Identity())
+    x = torch.randn(2, 64, 50)
+    want = net(x)
+    assert mp.apply_pointwise_convs(net) == 2 and mp.apply_pointwise_convs(net, max_weights=16) == 0
+    assert torch.equal(net(x), want)                        # module's own forward: not CUDA
+    calls = []
+
+    class PCN_decoder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv1d(1029, 8, 1)
+
+        def forward(self, x):
+            calls.append("pcn")
+            return "coarse", "fine"
+
+    fake = types.SimpleNamespace(PCN_decoder=PCN_decoder,
+                                 get_graph_feature=lambda x, k=20, minus_center=True: calls.append("ggf") or "orig-ggf")
+    assert mp.apply(fake) == 2
+    try:
+        assert PCN_decoder()(torch.zeros(2, 1024)) == ("coarse", "fine")
+        assert fake.get_graph_feature(torch.zeros(2, 8, 30), 4) == "orig-ggf"
+    finally:
+        PCN_decoder.forward = PCN_decoder._mvp_original_forward
+    assert calls == ["pcn", "ggf"]
