@@ -4,23 +4,31 @@
 // layers of completion/models/{pcn,ecg,vrcnet}.py and completion/model_utils.py (after model_patches moves them in
 // front of the neighbour gather, every one of them is this plain per-point contraction).
 //
-// One CTA = 128 points x up to 256 output channels of one cloud:
-//   * UMMA M = the 128 points (TMEM lane = point), N = the output channels (TMEM column = channel), K = input channels.
-//     With the points on the lanes, the epilogue's stores are coalesced as they come out of tcgen05.ld (lane = point,
-//     register = channel: a warp writes 128 contiguous bytes of one channel row per register), the bias is a
+// What is in this file:
+//   pointwise_conv_kernel       both operands streamed through two stages — any shape, and the masked form (input
+//                               gradient behind a ReLU)
+//   pointwise_resident_kernel   the HBM-bound layers: weight tile resident in shared memory, persistent CTAs, two
+//                               accumulators in tensor memory (the one that is fast: 66 % of the HBM peak at 64 -> 256)
+//   pointwise_wgrad_kernel      weight + bias gradient: K = points, both operands K-major as they lie in HBM
+//   bias_add_kernel, channel_sum_kernel   the bias of the wide layers that stay on the library GEMM
+//
+// Common to the three tcgen05 kernels:
+//   * forward orientation: UMMA M = 128 POINTS (TMEM lane = point), N = output channels (TMEM column), K = input
+//     channels.  With the points on the lanes, the epilogue's stores are coalesced as they come out of tcgen05.ld (lane =
+//     point, register = channel: a warp writes 128 contiguous bytes of one channel row per register), the bias is a
 //     per-register scalar, and a thin layer (4 or 16 output channels) pads N to 16 instead of M to 128.
 //   * operands in shared memory in the canonical K-major, no-swizzle layout (8-row x 16-byte core matrices):
 //       byte offset of (row r, channel k) = (k / 4) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4,  LBO = rows * 16
-//     A (points x channels) is the transpose of how x lies in HBM (channel rows, points contiguous): a thread reads four
-//     channels of ONE point with four loads, each coalesced across the warp's 32 points, rounds to TF32
-//     (cvt.rna, what cuDNN / cuBLAS feed their TF32 kernels) and writes one 16-byte core-matrix row; the warp's 32
-//     stores cover 512 contiguous bytes: no bank conflicts.  B (output channel x input channel) is w as it lies.
-//   * two stages of 32 input channels: while the tensor core works on one (tcgen05.mma is asynchronous; one thread
-//     issues 4 MMAs of K = 8 and commits them to the stage's mbarrier), all 256 threads load the next.
-//   * accumulator: 128 lanes x N columns of fp32 in TMEM; epilogue warp w reads lanes 32 (w % 4)... (its quarter),
-//     column blocks w / 4, w / 4 + 2, ...
+//     A (points x channels) is the transpose of how x lies in HBM (channel rows, points contiguous): a thread reads
+//     consecutive channels of ONE point, each load coalesced across the warp's 32 points, rounds to TF32 (cvt.rna, what
+//     cuDNN / cuBLAS feed their TF32 kernels) and writes 16-byte core-matrix rows; the warp's 32 stores cover 512
+//     contiguous bytes: no bank conflicts.  B (output channel x input channel) is w as it lies.
+//   * steps of 32 input channels: tcgen05.mma is asynchronous; one thread issues 4 MMAs of K = 8 per step and commits
+//     them to the stage's mbarrier, the other threads are already loading the next steps.
+//   * accumulator: 128 lanes x N columns of fp32 in TMEM; epilogue warp w reads lanes 32 (w % 4)... (its quarter) and
+//     every (warps / 4)-th block of 32 columns.
 // Roofline: HBM for the thin layers (64 -> 256 channels over 64 x 3072 points: 50 MB in, 201 MB out), TF32 tensor
-// throughput for the wide ones (512 -> 1024: 137 GFLOP).
+// throughput for the wide ones (512 -> 1024: 137 GFLOP) — those are left to the library (see pointwise_conv_kernel).
 #include <cstdlib>
 
 #include "sm100.cuh"
