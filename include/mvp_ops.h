@@ -182,6 +182,12 @@ int mvp_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int mvp_knn(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
             float *dist2, mvp_stream_t stream);
 
+/* The F-score of a Chamfer result (utils/metrics/CD/fscore.py:12-15; completion/model_utils.py:74-76 with calc_f1):
+ * precision_k[b] = mean_i (dist_k[b,i] < threshold), fscore = 2 p1 p2 / (p1 + p2) with NaN -> 0, torch's arithmetic
+ * (mean = count * fl(1/n)).  dist1 (b,n), dist2 (b,m); outputs (b). */
+int mvp_fscore(int b, int n, int m, const float *dist1, const float *dist2, float threshold, float *fscore,
+               float *precision1, float *precision2, mvp_stream_t stream);
+
 /* SURVEY.md §8(f) row 3 — the loss epilogue the models compute from the Chamfer outputs with torch glue
  * (completion/model_utils.py:67-72, calc_cd):  cd_p[b] = (mean_i sqrt(dist1[b,i]) + mean_j sqrt(dist2[b,j])) / 2,
  * cd_t[b] = mean_i dist1[b,i] + mean_j dist2[b,j];  dist1 (b,n), dist2 (b,m) -> cd_p (b), cd_t (b).  fp32, fixed

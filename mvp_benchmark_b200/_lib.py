@@ -78,6 +78,7 @@ def _load():
         "mvp_three_nn_weights_ws": (_c_int, [_c_int] * 3 + [_p] * 6 + [_c_size_t, _p]),
         "mvp_furthest_point_sampling_gather": (_c_int, [_c_int] * 3 + [_p] * 4 + [_c_int, _p]),
         "mvp_ball_query_group": (_c_int, [_c_int] * 3 + [_c_float] * 2 + [_c_int] + [_p] * 4 + [_p]),
+        "mvp_fscore": (_c_int, [_c_int] * 3 + [_p] * 2 + [_c_float] + [_p] * 3 + [_p]),
         "mvp_chamfer_loss": (_c_int, [_c_int] * 3 + [_p] * 4 + [_p]),
         "mvp_chamfer_loss_grad": (_c_int, [_c_int] * 3 + [_p] * 6 + [_p]),
         "mvp_knn_points_workspace_bytes": (_c_size_t, [_c_int] * 4),

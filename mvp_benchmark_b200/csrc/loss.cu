@@ -69,6 +69,34 @@ chamfer_loss_grad_kernel(int b, int n, int m, const float *__restrict__ dist1, c
   }
 }
 
+// F-score of a Chamfer result (utils/metrics/CD/fscore.py:12-15): precision_k = mean over the cloud of (dist_k <
+// threshold), fscore = 2 p1 p2 / (p1 + p2), NaN (p1 = p2 = 0) -> 0 — four elementwise kernels, two reductions and an
+// indexed assignment in torch; here one CTA per cloud counts both directions.  The arithmetic is torch's: a mean is
+// count * fl(1 / n) (its reduce kernel multiplies the sum by a float factor), then ((2 p1) p2) / (p1 + p2).
+__global__ void __launch_bounds__(kLossThreads)
+fscore_kernel(int n, int m, float threshold, const float *__restrict__ dist1, const float *__restrict__ dist2,
+              float *__restrict__ f, float *__restrict__ p1, float *__restrict__ p2) {
+  __shared__ int s_part[2][kLossThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *d1 = dist1 + (size_t)b * n, *d2 = dist2 + (size_t)b * m;
+  int c1 = 0, c2 = 0;
+  for (int i = tid; i < n; i += kLossThreads) c1 += __ldg(d1 + i) < threshold ? 1 : 0;
+  for (int i = tid; i < m; i += kLossThreads) c2 += __ldg(d2 + i) < threshold ? 1 : 0;
+  c1 = __reduce_add_sync(0xffffffffu, c1);
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  if (lane == 0) s_part[0][warp] = c1, s_part[1][warp] = c2;
+  __syncthreads();
+  if (tid == 0) {
+    int t1 = 0, t2 = 0;
+    for (int w = 0; w < kLossThreads / 32; w++) t1 += s_part[0][w], t2 += s_part[1][w];
+    const float q1 = __fmul_rn((float)t1, __fdiv_rn(1.f, (float)n)), q2 = __fmul_rn((float)t2, __fdiv_rn(1.f, (float)m));
+    const float v = __fdiv_rn(__fmul_rn(__fmul_rn(2.f, q1), q2), __fadd_rn(q1, q2));
+    f[b] = v != v ? 0.f : v;
+    p1[b] = q1;
+    p2[b] = q2;
+  }
+}
+
 // Inverse-distance weights of the three nearest sources (completion/model_utils.py:286-293, three_nn_upsampling):
 //     dist = max(sqrt(d2), 1e-10);  w_k = (1 / dist_k) / ((1 / dist_0 + 1 / dist_2) + 1 / dist_1)
 // from the SQUARED distances mvp_three_nn returns — the sqrt of three_nn.py:38 and the five torch kernels of the
@@ -91,6 +119,16 @@ MVP_API int mvp_three_nn_weights(int b, int n, const float *dist2, float *weight
   const long long total = (long long)b * n;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
   three_nn_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(total, dist2, weight);
+  count_launch();
+  return launch_status();
+}
+
+MVP_API int mvp_fscore(int b, int n, int m, const float *dist1, const float *dist2, float threshold, float *fscore,
+                       float *precision1, float *precision2, mvp_stream_t stream) {
+  if (b < 0 || n <= 0 || m <= 0) return MVP_ERR_INVALID_ARGUMENT;
+  if (b == 0) return MVP_OK;
+  if (!dist1 || !dist2 || !fscore || !precision1 || !precision2) return MVP_ERR_INVALID_ARGUMENT;
+  fscore_kernel<<<b, kLossThreads, 0, (cudaStream_t)stream>>>(n, m, threshold, dist1, dist2, fscore, precision1, precision2);
   count_launch();
   return launch_status();
 }

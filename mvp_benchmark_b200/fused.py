@@ -75,6 +75,26 @@ def chamfer_loss(dist1, dist2):
     return _ChamferLoss.apply(dist1, dist2)
 
 
+def emd_loss(dist):
+    """calc_emd's epilogue (completion/model_utils.py:84: `torch.sqrt(dist).mean(1)`) on the EMD operator's dist (B, N):
+    the Chamfer epilogue's cd_p half with both arguments equal ((m + m) / 2 == m exactly).  Differentiable."""
+    return _ChamferLoss.apply(dist, dist)[0]
+
+
+def fscore(dist1, dist2, threshold=0.0001):
+    """(fscore, precision_1, precision_2) per cloud — utils/metrics/CD/fscore.py:12-15 as ONE launch (mvp_fscore: a CTA
+    per cloud counts both directions; torch's arithmetic, NaN -> 0).  Not differentiable (comparisons)."""
+    d1, d2 = dist1.detach().contiguous(), dist2.detach().contiguous()
+    dev = _lib.require_cuda(d1, d2, dtype=torch.float32, what="fscore")
+    B, n = d1.shape
+    m = d2.shape[1]
+    f, p1, p2 = (torch.empty(B, device=dev, dtype=torch.float32) for _ in range(3))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.mvp_fscore(B, n, m, _lib.ptr(d1), _lib.ptr(d2), float(threshold), _lib.ptr(f), _lib.ptr(p1),
+                                       _lib.ptr(p2), _lib.stream_of(d1)), "mvp_fscore")
+    return f, p1, p2
+
+
 def three_nn_weights(target, source):
     """The three nearest points of `source` (B, M, 3) for every point of `target` (B, N, 3) and their normalised
     inverse-distance weights — completion/model_utils.py:286-293 (three_nn_upsampling: three_nn, clamp, reciprocal,

@@ -298,13 +298,23 @@ def calc_cd(output, gt, calc_f1=False):
         return _ORIGINAL["calc_cd"](output, gt, calc_f1)
     cd_p, cd_t = fused.chamfer_loss(dist1, dist2)
     if calc_f1:
-        f1, _, _ = metrics.fscore(dist1, dist2)
+        f1, _, _ = fused.fscore(dist1, dist2)
         return cd_p, cd_t, f1
     return cd_p, cd_t
 
 
+def calc_emd(output, gt, eps=0.005, iterations=50):
+    """model_utils.py:80-85: the EMD operator, then `torch.sqrt(dist).mean(1)` as the one reduction kernel of the
+    Chamfer epilogue (fused.emd_loss).  Same return."""
+    import metrics
+    dist, _ = metrics.emd()(output, gt, eps, iterations)
+    if not dist.is_cuda:
+        return _ORIGINAL["calc_emd"](output, gt, eps, iterations)
+    return fused.emd_loss(dist)
+
+
 def apply(*modules):
-    """Rebind knn / knn_point / knn_point_all / get_edge_features / get_graph_feature / calc_cd / three_nn_upsampling /
+    """Rebind knn / knn_point / knn_point_all / get_edge_features / get_graph_feature / calc_cd / calc_emd / three_nn_upsampling /
     edge_preserve_sampling / get_uniform_loss in the given (already imported) modules (and SA_module.forward,
     Dense_conv.forward where the module defines those classes).
     Returns the number of names replaced."""
@@ -314,7 +324,7 @@ def apply(*modules):
     for mod in modules:
         for name, fn in (("knn", knn), ("knn_point", knn_point), ("knn_point_all", knn_point),
                          ("get_edge_features", get_edge_features), ("get_graph_feature", get_graph_feature),
-                         ("calc_cd", calc_cd),
+                         ("calc_cd", calc_cd), ("calc_emd", calc_emd),
                          ("three_nn_upsampling", three_nn_upsampling),
                          ("edge_preserve_sampling", edge_preserve_sampling), ("get_uniform_loss", get_uniform_loss)):
             cur = getattr(mod, name, None)

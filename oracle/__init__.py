@@ -345,3 +345,22 @@ def max_last(x):
     nan = np.isnan(a)
     arg = np.where(nan.any(-1), nan.argmax(-1), np.where(nan, -np.inf, a).argmax(-1))
     return np.take_along_axis(a, arg[..., None], -1)[..., 0], arg.astype(np.int64)
+
+
+def fscore(dist1, dist2, threshold=0.0001, mean="factor"):
+    """utils/metrics/CD/fscore.py:12-15 -> (fscore, precision_1, precision_2), each (B,), in torch's fp32 arithmetic:
+    fscore = ((2 p1) p2) / (p1 + p2), NaN -> 0.  The mean of the 0/1 values is count * fl(1 / n) the way torch's CUDA
+    reduce kernel takes it (mean="factor": the sum times a float factor) or count / n the way its CPU path does
+    (mean="div": sum, then div_) — one ulp apart when n is not a power of two."""
+    d1, d2 = _f32(dist1), _f32(dist2)
+    one = np.float32(1.0)
+    c1 = (d1 < np.float32(threshold)).sum(1).astype(np.float32)
+    c2 = (d2 < np.float32(threshold)).sum(1).astype(np.float32)
+    if mean == "factor":
+        p1, p2 = c1 * (one / np.float32(d1.shape[1])), c2 * (one / np.float32(d2.shape[1]))
+    else:
+        p1, p2 = c1 / np.float32(d1.shape[1]), c2 / np.float32(d2.shape[1])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        f = (np.float32(2.0) * p1 * p2) / (p1 + p2)
+    f[np.isnan(f)] = 0
+    return f.astype(np.float32), p1.astype(np.float32), p2.astype(np.float32)

@@ -76,4 +76,5 @@ def test_argument_validation_needs_no_gpu():
     assert L.mvp_channel_sum(1, 4, 8, ctypes.c_void_p(16), ctypes.c_void_p(16), z, 0, z) == -5    # workspace missing
     assert L.mvp_channel_sum_workspace_bytes(64, 1024) == 1024 * 4 and L.mvp_channel_sum_workspace_bytes(64, 4) == 4 * 64 * 4
     assert L.mvp_max_last(4, 0, z, z, z, z) == -1 and L.mvp_max_last(4, 256, z, z, z, z) == -1 and L.mvp_max_last(0, 16, z, z, z, z) == 0
+    assert L.mvp_fscore(1, 0, 8, z, z, 1e-4, z, z, z, z) == -1 and L.mvp_fscore(0, 8, 8, z, z, 1e-4, z, z, z, z) == 0
     assert L.mvp_topk_rows_sqdist(1, 8, 9, z, z, z, z, z, z) == -1 and L.mvp_topk_rows_sqdist(0, 8, 4, z, z, z, z, z, z) == 0

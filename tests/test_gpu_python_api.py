@@ -647,6 +647,49 @@ def test_model_patches_pcn_decoder(cuda):
     assert (b.grad - (go * (want > 0)).sum(2)).abs().max().item() <= 1e-5 * go.abs().sum(2).max().item()
 
 
+def test_fscore_and_emd_loss_epilogues(cuda):
+    """fused.fscore (mvp_fscore) against the oracle and the reference's torch lines (utils/metrics/CD/fscore.py:12-15):
+    identical, NaN -> 0 included; fused.emd_loss against `torch.sqrt(dist).mean(1)` (model_utils.py:84) forward and
+    backward at 1e-5; model_patches.calc_emd returns what the original returns."""
+    import types
+    import oracle
+    from mvp_benchmark_b200 import fused, model_patches as mp
+    rng = np.random.default_rng(11)
+    d1 = (rng.random((5, 2048), dtype=np.float32) * 3e-4).astype(np.float32)
+    d2 = (rng.random((5, 777), dtype=np.float32) * 3e-4).astype(np.float32)
+    d1[2] += 1.0
+    d2[2] += 1.0
+    t1, t2 = torch.from_numpy(d1).to(cuda), torch.from_numpy(d2).to(cuda)
+    f, p1, p2 = fused.fscore(t1, t2)
+    of, o1, o2 = oracle.fscore(d1, d2)
+    assert np.array_equal(p1.cpu().numpy(), o1) and np.array_equal(p2.cpu().numpy(), o2) and np.array_equal(f.cpu().numpy(), of)
+    w1 = torch.mean((t1 < 0.0001).float(), dim=1)
+    w2 = torch.mean((t2 < 0.0001).float(), dim=1)
+    wf = 2 * w1 * w2 / (w1 + w2)
+    wf[torch.isnan(wf)] = 0
+    torch.testing.assert_close(p1, w1, rtol=1e-6, atol=0), torch.testing.assert_close(f, wf, rtol=1e-6, atol=0)
+    a = (t1 + 1e-6).clone().requires_grad_(True)
+    b = (t1 + 1e-6).clone().requires_grad_(True)
+    got, want = fused.emd_loss(a), torch.sqrt(b).mean(1)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=0)
+    go = torch.randn(5, device=cuda)
+    got.backward(go), want.backward(go)
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=0)
+
+    def original(output, gt, eps=0.005, iterations=50):    # model_utils.py:80-85, restated
+        import metrics
+        dist, _ = metrics.emd()(output, gt, eps, iterations)
+        return torch.sqrt(dist).mean(1)
+
+    import mvp_benchmark_b200
+    mvp_benchmark_b200.install()
+    fake = types.SimpleNamespace(calc_emd=original)
+    assert mp.apply(fake) == 1
+    x = torch.rand(2, 1024, 3, device=cuda)
+    y = torch.rand(2, 1024, 3, device=cuda)
+    torch.testing.assert_close(fake.calc_emd(x, y), original(x, y), rtol=1e-5, atol=0)
+
+
 def _tf32(t):
     """round to nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32 does"""
     i = t.contiguous().view(torch.int32)

@@ -135,3 +135,27 @@ def test_oracle_pointwise_conv_vs_torch_layers(B, C, O, N):
     tv, ta = torch.max(torch.from_numpy(q), -1)
     np.testing.assert_array_equal(v, tv.numpy())
     np.testing.assert_array_equal(a, ta.numpy())
+
+
+def test_oracle_fscore_vs_reference_fscore():
+    """oracle.fscore against the reference's own fscore (utils/metrics/CD/fscore.py, restated line by line and run by
+    torch on the CPU): identical, including a cloud with no point under the threshold (NaN -> 0) and odd sizes."""
+    import oracle
+    import torch
+    rng = np.random.default_rng(11)
+    d1 = (rng.random((5, 2048), dtype=np.float32) * 3e-4).astype(np.float32)
+    d2 = (rng.random((5, 777), dtype=np.float32) * 3e-4).astype(np.float32)
+    d1[2] += 1.0
+    d2[2] += 1.0
+    t1, t2 = torch.from_numpy(d1), torch.from_numpy(d2)
+    p1 = torch.mean((t1 < 0.0001).float(), dim=1)
+    p2 = torch.mean((t2 < 0.0001).float(), dim=1)
+    f = 2 * p1 * p2 / (p1 + p2)
+    f[torch.isnan(f)] = 0
+    of, o1, o2 = oracle.fscore(d1, d2, mean="div")        # torch on the CPU: sum, then div_
+    np.testing.assert_array_equal(o1, p1.numpy())
+    np.testing.assert_array_equal(o2, p2.numpy())
+    np.testing.assert_array_equal(of, f.numpy())
+    assert of[2] == 0
+    ff, f1, f2 = oracle.fscore(d1, d2)                     # the CUDA reduce kernel's arithmetic: within one ulp
+    np.testing.assert_allclose(f2, o2, rtol=2e-7) and np.testing.assert_array_equal(f1, o1)   # 2048 is a power of two
