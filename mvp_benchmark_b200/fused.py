@@ -423,7 +423,7 @@ class _MaxLast(torch.autograd.Function):
 def max_last(x):
     """(values, arg) of the maximum over the LAST axis of x (..., k), k <= 255 — `torch.max(x, -1)` on the (B, C, N, k)
     neighbour tensors of the completion models (ecg.py:64, model_utils.py:53,104) as one bandwidth-bound launch; arg is
-    uint8, the first position of the maximum; the gradient goes there."""
+    uint8, the first position of the maximum; the gradient goes there.  (k > 255: torch.max itself, int64 indices.)"""
     if x.shape[-1] > 255 or x.shape[-1] == 0:
         v, i = torch.max(x, -1)
         return v, i
