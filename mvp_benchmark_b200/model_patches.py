@@ -235,7 +235,7 @@ def _pointwise_conv_forward(self, x):
     """An nn.Conv1d / nn.Conv2d with a 1x1 kernel as what it is over a point cloud — one (out, in) matrix applied to every
     point's feature vector — routed by shape (measured on B200, tools/pointwise_probe.py, profiles/r2_pointwise.md):
       * up to 128 input and at least 64 output channels (HBM-bound: 64 -> 256 over 64 x 3072 points moves 252 MB for
-        6.4 GFLOP): this repository's tcgen05 kernel, bias in its epilogue (fused.pointwise_conv; 0.086 ms against
+        6.4 GFLOP): this repository's tcgen05 kernel, bias in its epilogue (fused.pointwise_conv; 0.058 ms against
         cuDNN + torch's bias add 0.187 ms), input gradient through the same kernel;
       * THIN layers ((64, 64, 1, 3072) -> 4, 16 or 64 channels; 68 -> 2): torch.baddbmm, a library fp32 GEMM — cuDNN's
         heuristics pick `wgrad2d_grouped_direct_kernel` for their weight gradient, 0.5-1.6 ms per call for 0.1-1.6 GFLOP:
